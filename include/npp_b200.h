@@ -1,0 +1,132 @@
+/*
+ * npp_b200.h -- C ABI of libnpp_b200.so, the B200 (sm_100a) implementation of NPP-Net's
+ * per-image training hot path:
+ *
+ *   periodicity-aware positional encoding -> coordinate MLP forward -> masked-MSE loss
+ *   -> backward -> Adam
+ *
+ * The reference (ArmastusChen/Learning-Continuous-Implicit-Representation-for-Near-Periodic-
+ * Patterns) has no FFI: its boundary for this path is the Python surface of models/.  Each entry
+ * point below names the reference code it replaces (paths relative to the reference root).
+ * The Python binding is learning-..._b200/_native.py (ctypes); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; npp_last_error() returns the
+ *     message of the last failure on the calling thread.  Nothing throws across the ABI.
+ *   - all pointers marked "device" are CUDA device pointers owned by the caller (torch tensors);
+ *     the plan owns only its activation workspace, fp16 shadow weights and TMA descriptors.
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it.
+ *   - one plan per (process, device); one process per GPU.  No CPU fallback exists.
+ */
+#ifndef NPP_B200_H_
+#define NPP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct NppPlan NppPlan;
+
+enum { NPP_MODEL_TOPK = 0, /* models/networks.py:8-95   NPP_Net      (p_topk > 1) */
+       NPP_MODEL_TOP1 = 1  /* models/networks.py:99-173 NPP_Net_top1 (p_topk == 1) */ };
+
+typedef struct NppConfig {
+  int32_t model;          /* NPP_MODEL_* */
+  int32_t topk;           /* number of periodicity proposals K (create_npp_net, models/helpers.py:108-116) */
+  int32_t depth;          /* netdepth D (options/arg_config.py:55-74), default 8 */
+  int32_t width;          /* netwidth W, default 512; this build requires W % 512 == 0 */
+  int32_t skip_layer;     /* skips=[4] (models/helpers.py:90); -1 = none */
+  int32_t n_aug;          /* len(freq_scales)*len(freq_offsets)*len(angle_offsets), embedder.py:117-120 */
+  int32_t n_freq;         /* multires, number of Gaussian Fourier frequencies (embedder.py:25-26) */
+  int32_t include_input;  /* 1 outside search mode (embedder.py:105-109) */
+  int32_t res_h, res_w;   /* image resolution res=(H,W) (NPP_completion/train.py:64) */
+  int32_t wgrad_splits;   /* split-K factor of the weight-gradient GEMM, 0 = auto */
+  int32_t reserved;
+  int64_t max_rows;       /* workspace capacity in coordinate rows per step */
+  const float* cos_t;     /* host [topk][2][n_aug]  cos(deg2rad(angle+offset))   embedder.py:123-124 */
+  const float* sin_t;     /* host [topk][2][n_aug]  sin(...)                                         */
+  const float* period;    /* host [topk][2][n_aug]  (period + freq_offset) * freq_scale  embedder.py:121 */
+  const float* freq;      /* host [n_freq]          torch.normal(0,1,(n,1))*10            embedder.py:26 */
+} NppConfig;
+
+typedef struct NppTensorInfo {
+  char name[64];     /* state_dict key of the reference module, e.g. "periodic_linears.0.weight" */
+  int64_t offset;    /* float offset inside the parameter arena */
+  int32_t rows;      /* out_features (or 1 for a bias) */
+  int32_t cols;      /* in_features  (or out_features for a bias) */
+  int32_t is_bias;
+  int32_t trained;   /* 0 for parameters the reference allocates but never uses (alpha_linear, ...) */
+} NppTensorInfo;
+
+const char* npp_last_error(void);
+int npp_abi_version(void);
+
+/* Replaces create_npp_net's model construction (models/helpers.py:121-132) for the fused path. */
+int npp_plan_create(const NppConfig* cfg, NppPlan** out);
+int npp_plan_destroy(NppPlan* plan);
+
+/* Parameter arena layout: trained tensors first (Adam runs flat over [0, trained_floats)). */
+int npp_plan_arena_floats(const NppPlan* plan, int64_t* total_floats, int64_t* trained_floats);
+int npp_plan_tensor_count(const NppPlan* plan);
+int npp_plan_tensor_info(const NppPlan* plan, int index, NppTensorInfo* info);
+int npp_plan_encoding_width(const NppPlan* plan); /* K * B * (1+2*n_freq), 1386 at the defaults */
+
+/* Bind caller-owned device arenas (fp32, `total_floats` each; grads/exp_avg/exp_avg_sq may be NULL
+ * for inference-only use). */
+int npp_plan_bind(NppPlan* plan, float* params, float* grads, float* exp_avg, float* exp_avg_sq);
+
+/* Re-derive the fp16 shadow weights from the fp32 arena (after init, load_state_dict or any
+ * external in-place edit of the parameters). */
+int npp_sync_weights(NppPlan* plan, void* stream);
+
+/* Embedder_periodic.embed + Embedder.embed (models/embedder.py:51-56,140-148), materialised in the
+ * reference layout [n, K*462] fp32.  coords: device [n,2] fp32 (row y, col x). */
+int npp_encode(NppPlan* plan, const float* coords, int64_t n, float* out, void* stream);
+
+/* NPP_Net.forward / NPP_Net_top1.forward on raw coordinates (models/networks.py:56-95,145-173);
+ * writes the pre-sigmoid logits [n,3] fp32 and keeps the activations needed by npp_backward. */
+int npp_forward(NppPlan* plan, const float* coords, int64_t n, float* logits, void* stream);
+
+/* autograd backward of the forward above: grad_logits device [n,3] fp32 -> bound grads arena
+ * (reference: loss.backward(), NPP_completion/train.py:253). */
+int npp_backward(NppPlan* plan, int64_t n, const float* grad_logits, void* stream);
+
+/* render()'s sigmoid (models/helpers.py:55-56) + img2mse(...,'l2',...,mask) (models/mse_calculator.py:
+ * 13-27) and its gradient w.r.t. the logits.  n_norm is the number of pixel rows the mean runs over
+ * (global count under data parallelism).  mask may be NULL (all ones); pred may be NULL.
+ * loss is a device float that this call accumulates into (zero it first). */
+int npp_mse_fwd_bwd(NppPlan* plan, const float* logits, const float* target, const float* mask, int64_t n,
+                    int64_t n_norm, float* pred, float* grad_logits, float* loss, void* stream);
+
+/* torch.optim.Adam.step over the trained part of the arena (models/helpers.py:164) followed by the
+ * shadow-weight refresh.  `step` is the 1-based step count used for bias correction. */
+int npp_adam_step(NppPlan* plan, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/* One whole train step (NPP_completion/train.py:187-254 with --loss_type l2): encode, forward,
+ * loss, backward, Adam.  loss: device float, overwritten. */
+int npp_train_step(NppPlan* plan, const float* coords, const float* target, const float* mask, int64_t n,
+                   int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
+                   void* stream);
+
+/* Number of kernels the last npp_train_step / forward / backward call launched. */
+int npp_last_launch_count(const NppPlan* plan);
+
+/* Test hooks: copy an internal fp16 activation/gradient buffer ("h0".."h7","d0",...,"delta0",...,
+ * "f1","hs","f2","hp","enc1","enc_aux") to a caller fp32 [n, width] device buffer. */
+int npp_debug_width(NppPlan* plan, const char* name);
+int npp_debug_copy(NppPlan* plan, const char* name, int64_t n, float* out, void* stream);
+float npp_debug_grad_scale(NppPlan* plan, void* stream); /* synchronises */
+
+/* Stand-alone tcgen05 GEMM checks (no plan): C[m,n] = A[m,k] . B[n,k]^T (fp16 in, fp32 out) and
+ * C[m,n] = A[rows,m]^T . B[rows,n] summed over `splits` row ranges. Dimensions: m%128==0 not required
+ * for the first (rows are masked), n%256==0, k%64==0. */
+int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, void* stream);
+int npp_debug_wgrad(const void* a, const void* b, float* c_partials, int rows, int m, int n, int splits,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPP_B200_H_ */

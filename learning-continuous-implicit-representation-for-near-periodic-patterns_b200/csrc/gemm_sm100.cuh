@@ -1,0 +1,483 @@
+// tcgen05 / TMEM / TMA GEMM kernels for the NPP-Net coordinate MLP (sm_100a only).
+//
+// Two persistent, warp-specialised kernels share one pipeline skeleton
+//   warp 0      : TMA producer      (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      : UMMA issuer       (tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warps 2..5  : epilogue          (tcgen05.ld -> registers -> fused math -> HBM)
+// with a 4-stage smem ring (full/empty mbarriers) and a 2-stage TMEM accumulator
+// ring (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+//  * npp_gemm_kmajor<EPI> : C[M, 256*tiles_n] = [A0 | A1] . [B0 | B1]^T, all operands
+//    K-major fp16.  Used for every dense layer of the forward pass
+//    (reference models/networks.py:63-94, concat inputs become a second K segment so
+//    torch.cat at networks.py:71,76,85 never materialises) and for every dgrad.
+//  * npp_gemm_wgrad : dW[out, in] = delta^T . a, contraction over the coordinate rows,
+//    both operands MN-major straight out of the row-major activation buffers,
+//    split-K over row ranges with deterministic fp32 partial slabs.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace npp {
+
+constexpr int BM = 128;      // UMMA M  (rows of the coordinate batch / out-features for wgrad)
+constexpr int BN = 256;      // UMMA N
+constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle atom of halves
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * BN * 4 + 256 + 1024;
+
+enum : int {
+  EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
+  EPI_SNAKE = 1,      // z = acc + bias; out0 = z + sin^2 z; out1 = 1 + sin 2z   (activations.py:34-35)
+  EPI_DGRAD_MUL = 2,  // out0 = acc * mul  (mul = stored snake derivative); colsum += out0
+  EPI_DGRAD = 3,      // out0 = acc; colsum += out0
+};
+
+struct alignas(64) KmajorParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  int nseg;
+  int kblocks[2];  // K blocks (of 64) per segment
+  int a_k0[2];     // first K element of the segment inside A's tensor
+  int b_k0[2];     // first K element inside B's tensor
+  int b_row0[2];   // first row of B (weight shadow) for output column 0
+  int M;           // valid rows
+  int tiles_m, tiles_n;
+  const float* bias;
+  __half* out0;
+  int ld0;
+  __half* out1;
+  int ld1;
+  const __half* mul;
+  int ldm;
+  float* colsum;
+  float* out_f32;  // optional raw fp32 copy of the epilogue value (tests)
+  int ldf;
+  unsigned long long desc_hi;  // UMMA smem descriptor bits [16,64) (0 = default K-major SW128)
+  int k_adv;                   // byte advance per UMMA_K slice (0 = default 32)
+};
+
+struct WgUnit {
+  short a_map, b_map;  // indices into WgradParams::maps
+  int a_m0;            // first out-feature (inner coordinate of the delta tensor)
+  int b_n0;            // first in-feature inside the activation tensor
+  int split;           // which row range
+  int out_off;         // float offset of (m0, col0) inside one partial slab
+  int ld;              // row pitch (floats) of this layer inside the slab
+  int ncols_left;      // valid columns from col0 to the padded layer width
+};
+
+constexpr int WG_MAX_MAPS = 28;
+struct alignas(64) WgradParams {
+  CUtensorMap maps[WG_MAX_MAPS];
+  const WgUnit* units;
+  int n_units;
+  int rows;           // contraction length (coordinate rows)
+  int kb_per_split;   // 64-row blocks per split
+  int n_splits;       // splits actually used for this row count
+  float* partial;     // [n_splits][slab_stride]
+  long long slab_stride;
+  unsigned long long desc_hi;  // 0 = default MN-major SW128 (LBO 8192, SBO 1024)
+  int k_adv;                   // 0 = default 2048
+};
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+struct GemmSmem {
+  uint8_t* a;
+  uint8_t* b;
+  float* bias;  // 2 x BN
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* tfull;
+  uint64_t* tempty;
+  uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
+  uint32_t addr = smem_u32(raw);
+  uint8_t* base = raw + ((1024u - (addr & 1023u)) & 1023u);
+  GemmSmem s;
+  s.a = base;
+  s.b = base + STAGES * A_STAGE_BYTES;
+  s.bias = reinterpret_cast<float*>(s.b + STAGES * B_STAGE_BYTES);
+  s.full = reinterpret_cast<uint64_t*>(s.bias + 2 * BN);
+  s.empty = s.full + STAGES;
+  s.tfull = s.empty + STAGES;
+  s.tempty = s.tfull + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tempty + 2);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tfull[i], 1);
+      mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *s.tmem_ptr;
+}
+
+__device__ __forceinline__ void gemm_teardown(uint32_t tmem_base, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// 32x32 transpose-reduce: on return lane j holds sum over the 32 lanes of v[j].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float send = up ? v[i] : v[i + s];
+      float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+// ---------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ KmajorParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmSmem s = carve_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nseg; ++i) {
+      tma_prefetch_desc(&p.tmA[i]);
+      tma_prefetch_desc(&p.tmB[i]);
+    }
+  }
+  const uint32_t tmem_base = gemm_prologue(s, warp);
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    PipeState ps;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
+          mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+          if (lane == 0) {
+            mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], p.a_k0[seg] + kb * BK,
+                        m0);
+            tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], p.b_k0[seg] + kb * BK,
+                        p.b_row0[seg] + n0);
+          }
+          __syncwarp();
+          ps.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ UMMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
+    const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
+    PipeState ps;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&s.tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      int it = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        for (int kb = 0; kb < p.kblocks[seg]; ++kb, ++it) {
+          mbar_wait(&s.full[ps.stage], ps.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi),
+                       idesc, (it | k) != 0);
+            }
+            umma_commit(&s.empty[ps.stage]);
+          }
+          __syncwarp();
+          ps.advance();
+        }
+      }
+      if (lane == 0) umma_commit(&s.tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int et = threadIdx.x - 64;          // 0..127
+    const int lane_base = (warp & 3) * 32;    // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      const int row = m0 + lane_base + lane;
+      const bool row_ok = row < p.M;
+      float* sbias = s.bias + acc * BN;
+      if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+        float2 bv = make_float2(0.f, 0.f);
+        if (p.bias != nullptr) bv = *reinterpret_cast<const float2*>(p.bias + n0 + et * 2);
+        *reinterpret_cast<float2*>(sbias + et * 2) = bv;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      uint4 mreg[4];
+      if (EPI == EPI_DGRAD_MUL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mreg[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.mul + (size_t)row * p.ldm + n0) + j)
+                           : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&s.tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + chunk * 32, raw);
+        uint4 mcur[4];
+        if (EPI == EPI_DGRAD_MUL) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mcur[j] = mreg[j];
+          if (chunk + 1 < BN / 32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              mreg[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.mul + (size_t)row * p.ldm + n0 +
+                                                                       (chunk + 1) * 32) + j)
+                               : make_uint4(0, 0, 0, 0);
+          }
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        const int col = n0 + chunk * 32;
+
+        if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 b4 = *reinterpret_cast<const float4*>(sbias + chunk * 32 + i);
+            v[i] += b4.x;
+            v[i + 1] += b4.y;
+            v[i + 2] += b4.z;
+            v[i + 3] += b4.w;
+          }
+        }
+        if (p.out_f32 != nullptr && row_ok) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldf + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (EPI == EPI_SNAKE) {
+          uint32_t hd[16], dd[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float h2[2], d2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float z = v[i + e];
+              const float w = z + z;
+              const float sn = __sinf(w);
+              const float cs = __cosf(w);
+              h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
+              d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+            }
+            hd[i >> 1] = pack_h2(h2[0], h2[1]);
+            dd[i >> 1] = pack_h2(d2[0], d2[1]);
+          }
+          if (row_ok) {
+            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ld0 + col);
+            uint4* o1 = reinterpret_cast<uint4*>(p.out1 + (size_t)row * p.ld1 + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              o0[j] = make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+              o1[j] = make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+            }
+          }
+        } else {
+          if (EPI == EPI_DGRAD_MUL) {
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(mcur);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 m2 = unpack_h2(mw[i]);
+              v[2 * i] *= m2.x;
+              v[2 * i + 1] *= m2.y;
+            }
+          }
+          uint32_t hd[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+          if (row_ok) {
+            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ld0 + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o0[j] = make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+          }
+          if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && p.colsum != nullptr) {
+            // bias gradient of the layer that produced this delta: column sums of the
+            // fp16-rounded values, so it matches what the wgrad GEMM consumes.
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 r = unpack_h2(hd[i]);
+              v[2 * i] = r.x;
+              v[2 * i + 1] = r.y;
+            }
+            const float cs = warp_colsum32(v, lane);
+            atomicAdd(p.colsum + col + lane, cs);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  gemm_teardown(tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmSmem s = carve_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = gemm_prologue(s, warp);
+  const int kb_total = (p.rows + BK - 1) / BK;
+
+  if (warp == 0) {
+    PipeState ps;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const WgUnit un = p.units[u];
+      if (un.split >= p.n_splits) continue;
+      const int kb0 = un.split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+      const CUtensorMap* ma = &p.maps[un.a_map];
+      const CUtensorMap* mb = &p.maps[un.b_map];
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          uint8_t* sa = s.a + ps.stage * A_STAGE_BYTES;
+          uint8_t* sb = s.b + ps.stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], un.a_m0 + j * 64, kb * BK);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mb, &s.full[ps.stage], un.b_n0 + j * 64, kb * BK);
+        }
+        __syncwarp();
+        ps.advance();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 1, 1);
+    const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(8192, 1024);
+    const int kadv = p.k_adv ? p.k_adv : 2048;
+    PipeState ps;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const WgUnit un = p.units[u];
+      if (un.split >= p.n_splits) continue;
+      const int kb0 = un.split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+      mbar_wait(&s.tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&s.full[ps.stage], ps.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&s.empty[ps.stage]);
+        }
+        __syncwarp();
+        ps.advance();
+      }
+      if (lane == 0) umma_commit(&s.tfull[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const WgUnit un = p.units[u];
+      if (un.split >= p.n_splits) continue;
+      float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off + (size_t)(lane_base + lane) * un.ld;
+      mbar_wait(&s.tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + chunk * 32, raw);
+        tmem_ld_wait();
+        if (chunk * 32 < un.ncols_left) {
+          float4* o = reinterpret_cast<float4*>(out + chunk * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                               __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  gemm_teardown(tmem_base, warp);
+}
+
+}  // namespace npp

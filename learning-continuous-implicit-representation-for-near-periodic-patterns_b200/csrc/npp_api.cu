@@ -1,0 +1,952 @@
+// Host side of libnpp_b200.so: the plan (layer graph, arena layout, workspace, TMA descriptors)
+// and the extern "C" entry points declared in include/npp_b200.h.
+#include "../../include/npp_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemm_sm100.cuh"
+#include "simt_kernels.cuh"
+
+using namespace npp;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define CK(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +   \
+                  std::to_string(__LINE__) + ")");                                                       \
+  } while (0)
+#define CKI(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+// ------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess)
+    return fail("cuTensorMapEncodeTiled is not available from the CUDA driver (need a Hopper/Blackwell driver)");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// fp16 row-major [rows, cols] tensor with pitch `ld` elements; box = {64 cols, box_rows}, 128B swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  CKI(load_encode_fn());
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (rows=" +
+                std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld) + ")");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- plan
+struct Buf {
+  std::string name;
+  int width = 0;  // elements per row == pitch
+  __half* ptr = nullptr;
+};
+
+struct Seg {
+  int buf;        // activation buffer feeding this K segment
+  int ref_lo;     // first reference input column
+  int ref_w;      // reference columns
+  int pad_off;    // first padded column inside the shadow weight
+  int pad_w;      // padded width (multiple of 64) == buffer width
+  int producer;   // layer whose output this is, -1 for the encoding
+  int wt_row0;    // first row inside the transposed shadow, -1 if no dgrad flows here
+};
+
+struct Layer {
+  std::string name;  // reference module path
+  int out = 0, in_ref = 0, kpad = 0;
+  std::vector<Seg> segs;
+  int act = 0;  // 1 = snake
+  int buf_h = -1, buf_d = -1, buf_delta = -1;
+  long long w_off = 0, b_off = 0;  // arena
+  long long pg_off = 0, bg_off = 0;
+  __half* wf = nullptr;
+  __half* wt = nullptr;
+  int wt_rows = 0;
+  CUtensorMap map_wf, map_wt;
+};
+
+struct DgradOp {
+  int producer;  // layer whose delta is produced
+  struct Src {
+    int layer, seg;
+  } src[2];
+  int nsrc;
+};
+
+struct NppPlan {
+  NppConfig cfg;
+  EncTable enc;
+  int E = 0, Ep = 0, A = 0, Ap = 0;  // encoding widths (top-1 / aux), reference and padded
+  std::vector<Buf> bufs;
+  std::vector<Layer> layers;
+  std::vector<DgradOp> dgrads;
+  std::vector<NppTensorInfo> tensors;
+  long long arena_total = 0, arena_trained = 0;
+  long long rgb_w_off = 0, rgb_b_off = 0;
+  int buf_enc1 = -1, buf_enca = -1;
+  int head_width = 0;  // W/2
+
+  // device memory owned by the plan
+  void* workspace = nullptr;
+  void* shadow_mem = nullptr;
+  float* partial = nullptr;
+  long long slab_stride = 0;
+  float* acc = nullptr;  // [bias accumulators | head accumulators | amax | loss scratch]
+  long long acc_floats = 0, headacc_off = 0, amax_off = 0;
+  float* g_buf = nullptr;       // [max_rows,3] grad wrt logits (fused path)
+  float* logits_buf = nullptr;  // [max_rows,3] (fused path)
+  FinalizeLayer* d_fin = nullptr;
+  ShadowLayer* d_shadow = nullptr;
+  WgUnit* d_units = nullptr;
+  int n_units = 0;
+  int splits_max = 0;
+  int num_sms = 148;
+
+  // bound arenas
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+
+  // per-row-count state
+  long long prepared_n = -1;
+  std::vector<CUtensorMap> map_a;   // per buffer, box {64,128}: K-major A operand
+  std::vector<CUtensorMap> map_mn;  // per buffer, box {64,64}: MN-major wgrad operand
+  std::vector<KmajorParams> fwd_params, dgrad_params;
+  WgradParams wg_params;
+  std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
+  int launches = 0;
+};
+
+static int add_buf(NppPlan* p, const std::string& name, int width) {
+  Buf b;
+  b.name = name;
+  b.width = width;
+  p->bufs.push_back(b);
+  return (int)p->bufs.size() - 1;
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static void add_tensor(NppPlan* p, const std::string& name, int rows, int cols, int is_bias, int trained,
+                       long long* off_out) {
+  NppTensorInfo t;
+  memset(&t, 0, sizeof(t));
+  snprintf(t.name, sizeof(t.name), "%s", name.c_str());
+  t.offset = p->arena_total;
+  t.rows = rows;
+  t.cols = cols;
+  t.is_bias = is_bias;
+  t.trained = trained;
+  p->tensors.push_back(t);
+  if (off_out) *off_out = t.offset;
+  long long cnt = (long long)rows * cols;
+  p->arena_total += (cnt + 3) / 4 * 4;
+}
+
+// Adds a dense layer reading `srcs` (buffer, reference width, producer layer) in reference order.
+static int add_layer(NppPlan* p, const std::string& name, int out, int act,
+                     const std::vector<std::pair<int, std::pair<int, int>>>& srcs) {
+  Layer L;
+  L.name = name;
+  L.out = out;
+  L.act = act;
+  int ref = 0, pad = 0;
+  for (auto& s : srcs) {
+    Seg g;
+    g.buf = s.first;
+    g.ref_lo = ref;
+    g.ref_w = s.second.first;
+    g.pad_off = pad;
+    g.pad_w = p->bufs[g.buf].width;
+    g.producer = s.second.second;
+    g.wt_row0 = -1;
+    if (g.producer >= 0) {
+      g.wt_row0 = L.wt_rows;
+      L.wt_rows += g.ref_w;
+    }
+    ref += g.ref_w;
+    pad += g.pad_w;
+    L.segs.push_back(g);
+  }
+  L.in_ref = ref;
+  L.kpad = pad;
+  const int idx = (int)p->layers.size();
+  const std::string tag = std::to_string(idx);
+  L.buf_h = add_buf(p, "h" + tag, out);
+  if (act) L.buf_d = add_buf(p, "d" + tag, out);
+  L.buf_delta = add_buf(p, "delta" + tag, out);
+  p->layers.push_back(L);
+  return idx;
+}
+
+static int build_graph(NppPlan* p) {
+  const NppConfig& c = p->cfg;
+  const int W = c.width, D = c.depth;
+  const int B = 2 * (c.include_input + 2 * c.n_aug);
+  const int F = 1 + 2 * c.n_freq;
+  p->E = B * F;
+  p->Ep = round_up(p->E, 256);
+  p->A = p->E * (c.topk - 1);
+  p->Ap = round_up(p->A, 64);
+  p->head_width = W / 2;
+  p->buf_enc1 = add_buf(p, "enc1", p->Ep);
+  if (c.model == NPP_MODEL_TOPK) p->buf_enca = add_buf(p, "enc_aux", p->Ap);
+
+  typedef std::pair<int, std::pair<int, int>> S;
+  auto src = [](int buf, int w, int prod) { return S(buf, std::make_pair(w, prod)); };
+  // periodic_linears (networks.py:42-43, loop at :63-71)
+  int prev = -1;
+  for (int i = 0; i < D; ++i) {
+    std::vector<S> in;
+    if (i == 0) {
+      in.push_back(src(p->buf_enc1, p->E, -1));
+    } else if (i - 1 == c.skip_layer) {
+      in.push_back(src(p->buf_enc1, p->E, -1));  // torch.cat([input_periodic, h], -1)
+      in.push_back(src(p->layers[prev].buf_h, W, prev));
+    } else {
+      in.push_back(src(p->layers[prev].buf_h, W, prev));
+    }
+    prev = add_layer(p, "periodic_linears." + std::to_string(i), W, 1, in);
+  }
+  const int f1 = add_layer(p, "feature_linear1", W, 0, {src(p->layers[prev].buf_h, W, prev)});  // :73
+  int last;
+  if (c.model == NPP_MODEL_TOPK) {
+    const int s0 = add_layer(p, "scale_linears.0", W, 1,
+                             {src(p->layers[f1].buf_h, W, f1), src(p->buf_enca, p->A, -1)});        // :76-82
+    const int f2 = add_layer(p, "feature_linear2", W, 0, {src(p->layers[s0].buf_h, W, s0)});        // :84
+    last = add_layer(p, "pos_linears.0", W / 2, 1,
+                     {src(p->layers[f1].buf_h, W, f1), src(p->layers[f2].buf_h, W, f2)});           // :85-92
+  } else {
+    last = add_layer(p, "pos_linears.0", W / 2, 1, {src(p->layers[f1].buf_h, W, f1)});              // :161-170
+  }
+  (void)last;
+
+  // arena: trained tensors first, in reference module order within that group
+  for (auto& L : p->layers) {
+    add_tensor(p, L.name + ".weight", L.out, L.in_ref, 0, 1, &L.w_off);
+    add_tensor(p, L.name + ".bias", 1, L.out, 1, 1, &L.b_off);
+  }
+  add_tensor(p, "rgb_linear.weight", 3, W / 2, 0, 1, &p->rgb_w_off);
+  add_tensor(p, "rgb_linear.bias", 1, 3, 1, 1, &p->rgb_b_off);
+  p->arena_trained = p->arena_total;
+  if (c.model == NPP_MODEL_TOP1) {  // allocated but unused by NPP_Net_top1.forward (networks.py:135)
+    add_tensor(p, "feature_linear2.weight", W, W, 0, 0, nullptr);
+    add_tensor(p, "feature_linear2.bias", 1, W, 1, 0, nullptr);
+  }
+  add_tensor(p, "alpha_linear.weight", 1, W, 0, 0, nullptr);  // networks.py:48, never used
+  add_tensor(p, "alpha_linear.bias", 1, 1, 1, 0, nullptr);
+
+  // backward schedule: producers in reverse order; the last layer's delta comes from the head.
+  const int nl = (int)p->layers.size();
+  for (int P = nl - 2; P >= 0; --P) {
+    DgradOp op;
+    op.producer = P;
+    op.nsrc = 0;
+    for (int cidx = P + 1; cidx < nl; ++cidx)
+      for (int s = 0; s < (int)p->layers[cidx].segs.size(); ++s)
+        if (p->layers[cidx].segs[s].producer == P) {
+          if (op.nsrc == 2) return fail("layer graph: more than two consumers of one activation");
+          op.src[op.nsrc].layer = cidx;
+          op.src[op.nsrc].seg = s;
+          ++op.nsrc;
+        }
+    if (op.nsrc == 0) return fail("layer graph: activation without consumer");
+    p->dgrads.push_back(op);
+  }
+  return 0;
+}
+
+static int alloc_plan_memory(NppPlan* p) {
+  const long long R = p->cfg.max_rows;
+  // activation workspace
+  size_t bytes = 0;
+  std::vector<size_t> offs;
+  for (auto& b : p->bufs) {
+    offs.push_back(bytes);
+    bytes += ((size_t)R * b.width * 2 + 1023) / 1024 * 1024;
+  }
+  CK(cudaMalloc(&p->workspace, bytes));
+  CK(cudaMemset(p->workspace, 0, bytes));  // encoding pad columns stay zero forever
+  for (size_t i = 0; i < p->bufs.size(); ++i) p->bufs[i].ptr = reinterpret_cast<__half*>((char*)p->workspace + offs[i]);
+
+  // shadow weights
+  size_t sbytes = 0;
+  std::vector<size_t> wf_off, wt_off;
+  for (auto& L : p->layers) {
+    wf_off.push_back(sbytes);
+    sbytes += ((size_t)L.out * L.kpad * 2 + 1023) / 1024 * 1024;
+    wt_off.push_back(sbytes);
+    sbytes += ((size_t)L.wt_rows * L.out * 2 + 1023) / 1024 * 1024;
+  }
+  CK(cudaMalloc(&p->shadow_mem, sbytes));
+  CK(cudaMemset(p->shadow_mem, 0, sbytes));  // K padding columns stay zero forever
+  long long pg = 0, bg = 0;
+  for (size_t i = 0; i < p->layers.size(); ++i) {
+    Layer& L = p->layers[i];
+    L.wf = reinterpret_cast<__half*>((char*)p->shadow_mem + wf_off[i]);
+    L.wt = L.wt_rows ? reinterpret_cast<__half*>((char*)p->shadow_mem + wt_off[i]) : nullptr;
+    CKI(make_map(&L.map_wf, L.wf, L.out, L.kpad, L.kpad, 256));
+    if (L.wt) CKI(make_map(&L.map_wt, L.wt, L.wt_rows, L.out, L.out, 256));
+    L.pg_off = pg;
+    pg += (long long)L.out * L.kpad;
+    L.bg_off = bg;
+    bg += L.out;
+  }
+  p->slab_stride = pg;
+
+  // split-K factor of the grouped weight-gradient kernel
+  int tiles = 0;
+  for (auto& L : p->layers) tiles += (L.out / BM) * ((L.kpad + BN - 1) / BN);
+  int S = p->cfg.wgrad_splits;
+  if (S <= 0) {
+    double best = -1;
+    for (int s = 3; s <= 10; ++s) {
+      const int units = tiles * s;
+      const double eff = (double)units / ((double)((units + p->num_sms - 1) / p->num_sms) * p->num_sms);
+      if (eff > best + 0.02) {
+        best = eff;
+        S = s;
+      }
+    }
+  }
+  p->splits_max = S;
+  CK(cudaMalloc(&p->partial, (size_t)S * p->slab_stride * sizeof(float)));
+
+  // accumulators: [bias acc (bg) | head acc (3*hw+3) | amax | loss]
+  p->headacc_off = (bg + 3) / 4 * 4;
+  p->amax_off = p->headacc_off + (3 * p->head_width + 3 + 3) / 4 * 4;
+  p->acc_floats = p->amax_off + 4;
+  CK(cudaMalloc(&p->acc, p->acc_floats * sizeof(float)));
+  CK(cudaMemset(p->acc, 0, p->acc_floats * sizeof(float)));
+  CK(cudaMalloc(&p->g_buf, (size_t)R * 3 * sizeof(float)));
+  CK(cudaMalloc(&p->logits_buf, (size_t)R * 3 * sizeof(float)));
+
+  // device tables
+  std::vector<FinalizeLayer> fin;
+  std::vector<ShadowLayer> sh;
+  for (auto& L : p->layers) {
+    FinalizeLayer f;
+    f.w_off = L.w_off;
+    f.b_off = L.b_off;
+    f.pg_off = L.pg_off;
+    f.bg_off = L.bg_off;
+    f.out = L.out;
+    f.in_ref = L.in_ref;
+    f.kpad = L.kpad;
+    f.split_col = L.segs.size() > 1 ? L.segs[1].ref_lo : L.in_ref;
+    f.off0 = L.segs[0].pad_off;
+    f.off1 = L.segs.size() > 1 ? L.segs[1].pad_off : 0;
+    fin.push_back(f);
+    ShadowLayer s;
+    memset(&s, 0, sizeof(s));
+    s.w_off = L.w_off;
+    s.out = L.out;
+    s.in_ref = L.in_ref;
+    s.kpad = L.kpad;
+    s.split_col = f.split_col;
+    s.off0 = f.off0;
+    s.off1 = f.off1;
+    s.wf = L.wf;
+    s.wt = L.wt;
+    s.t_lo = s.t_hi = s.t_lo2 = s.t_hi2 = -1;
+    int nt = 0;
+    for (auto& g : L.segs)
+      if (g.wt_row0 >= 0) {
+        if (nt == 0) {
+          s.t_lo = g.ref_lo;
+          s.t_hi = g.ref_lo + g.ref_w;
+          s.t_row0 = g.wt_row0;
+        } else {
+          s.t_lo2 = g.ref_lo;
+          s.t_hi2 = g.ref_lo + g.ref_w;
+          s.t_row02 = g.wt_row0;
+        }
+        ++nt;
+      }
+    sh.push_back(s);
+  }
+  CK(cudaMalloc(&p->d_fin, fin.size() * sizeof(FinalizeLayer)));
+  CK(cudaMemcpy(p->d_fin, fin.data(), fin.size() * sizeof(FinalizeLayer), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
+  CK(cudaMemcpy(p->d_shadow, sh.data(), sh.size() * sizeof(ShadowLayer), cudaMemcpyHostToDevice));
+
+  // wgrad work units: layer-major, then split, then (m, n) tiles so that concurrently running CTAs
+  // share the same row range of the same delta/activation tensors in L2.
+  // map index convention inside WgradParams::maps: [0, nl) = delta of layer i; nl + k = k-th distinct source buffer
+  std::vector<int> src_bufs;
+  auto src_index = [&](int buf) {
+    for (size_t i = 0; i < src_bufs.size(); ++i)
+      if (src_bufs[i] == buf) return (int)i;
+    src_bufs.push_back(buf);
+    return (int)src_bufs.size() - 1;
+  };
+  std::vector<WgUnit> units;
+  const int nl = (int)p->layers.size();
+  for (int li = 0; li < nl; ++li) {
+    const Layer& L = p->layers[li];
+    for (int s = 0; s < S; ++s)
+      for (int m0 = 0; m0 < L.out; m0 += BM)
+        for (int n0 = 0; n0 < L.kpad; n0 += BN) {
+          const Seg* sg = nullptr;
+          for (auto& g : L.segs)
+            if (n0 >= g.pad_off && n0 < g.pad_off + g.pad_w) sg = &g;
+          if (!sg) return fail("wgrad tiling: column without segment");
+          if ((sg->pad_off % BN) != 0) return fail("wgrad tiling: segment boundary not aligned to 256 columns");
+          WgUnit u;
+          u.a_map = (short)li;
+          u.b_map = (short)(nl + src_index(sg->buf));
+          u.a_m0 = m0;
+          u.b_n0 = n0 - sg->pad_off;
+          u.split = s;
+          u.out_off = (int)(L.pg_off + (long long)m0 * L.kpad + n0);
+          u.ld = L.kpad;
+          u.ncols_left = sg->pad_off + sg->pad_w - n0;
+          units.push_back(u);
+        }
+  }
+  if (nl + (int)src_bufs.size() > WG_MAX_MAPS) return fail("wgrad: too many tensor maps");
+  if (p->slab_stride > 0x7fffffffLL) return fail("wgrad: slab too large for 32-bit offsets");
+  p->n_units = (int)units.size();
+  CK(cudaMalloc(&p->d_units, units.size() * sizeof(WgUnit)));
+  CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
+  p->wg_src_bufs = src_bufs;
+  return 0;
+}
+
+// ------------------------------------------------------------------- per-row-count setup
+static int prepare(NppPlan* p, long long n) {
+  if (n <= 0 || n > p->cfg.max_rows)
+    return fail("row count " + std::to_string(n) + " outside (0, max_rows=" + std::to_string(p->cfg.max_rows) + "]");
+  if (p->prepared_n == n) return 0;
+  const int nb = (int)p->bufs.size();
+  p->map_a.assign(nb, CUtensorMap());
+  p->map_mn.assign(nb, CUtensorMap());
+  for (int i = 0; i < nb; ++i) {
+    const Buf& b = p->bufs[i];
+    // rows == n exactly: TMA zero-fills rows >= n, which keeps stale workspace rows out of the
+    // row-contraction of the weight-gradient GEMM.
+    CKI(make_map(&p->map_a[i], b.ptr, n, b.width, b.width, BM));
+    CKI(make_map(&p->map_mn[i], b.ptr, n, b.width, b.width, 64));
+  }
+  const int tiles_m = (int)((n + BM - 1) / BM);
+  p->fwd_params.clear();
+  for (auto& L : p->layers) {
+    KmajorParams k;
+    memset(&k, 0, sizeof(k));
+    k.nseg = (int)L.segs.size();
+    for (int s = 0; s < k.nseg; ++s) {
+      k.tmA[s] = p->map_a[L.segs[s].buf];
+      k.tmB[s] = L.map_wf;
+      k.kblocks[s] = L.segs[s].pad_w / BK;
+      k.a_k0[s] = 0;
+      k.b_k0[s] = L.segs[s].pad_off;
+      k.b_row0[s] = 0;
+    }
+    k.M = (int)n;
+    k.tiles_m = tiles_m;
+    k.tiles_n = L.out / BN;
+    k.bias = p->params + L.b_off;
+    k.out0 = p->bufs[L.buf_h].ptr;
+    k.ld0 = L.out;
+    if (L.act) {
+      k.out1 = p->bufs[L.buf_d].ptr;
+      k.ld1 = L.out;
+    }
+    p->fwd_params.push_back(k);
+  }
+  p->dgrad_params.clear();
+  for (auto& op : p->dgrads) {
+    const Layer& P = p->layers[op.producer];
+    KmajorParams k;
+    memset(&k, 0, sizeof(k));
+    k.nseg = op.nsrc;
+    for (int s = 0; s < op.nsrc; ++s) {
+      const Layer& C = p->layers[op.src[s].layer];
+      k.tmA[s] = p->map_a[C.buf_delta];
+      k.tmB[s] = C.map_wt;
+      k.kblocks[s] = C.out / BK;
+      k.a_k0[s] = 0;
+      k.b_k0[s] = 0;
+      k.b_row0[s] = C.segs[op.src[s].seg].wt_row0;
+    }
+    k.M = (int)n;
+    k.tiles_m = tiles_m;
+    k.tiles_n = P.out / BN;
+    k.out0 = p->bufs[P.buf_delta].ptr;
+    k.ld0 = P.out;
+    if (P.act) {
+      k.mul = p->bufs[P.buf_d].ptr;
+      k.ldm = P.out;
+    }
+    k.colsum = p->acc + P.bg_off;
+    p->dgrad_params.push_back(k);
+  }
+  WgradParams& w = p->wg_params;
+  const int nl = (int)p->layers.size();
+  for (int i = 0; i < nl; ++i) w.maps[i] = p->map_mn[p->layers[i].buf_delta];
+  for (size_t i = 0; i < p->wg_src_bufs.size(); ++i) w.maps[nl + i] = p->map_mn[p->wg_src_bufs[i]];
+  w.units = p->d_units;
+  w.n_units = p->n_units;
+  w.rows = (int)n;
+  const int kb_total = (int)((n + BK - 1) / BK);
+  w.kb_per_split = (kb_total + p->splits_max - 1) / p->splits_max;
+  w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
+  w.partial = p->partial;
+  w.slab_stride = p->slab_stride;
+  p->prepared_n = n;
+  return 0;
+}
+
+static int g_smem_attr_done = 0;
+static int set_smem_attrs() {
+  if (g_smem_attr_done) return 0;
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_DGRAD_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  g_smem_attr_done = 1;
+  return 0;
+}
+
+static int launch_kmajor(const KmajorParams& k, int epi, int num_sms, cudaStream_t st) {
+  CKI(set_smem_attrs());
+  const int tiles = k.tiles_m * k.tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  switch (epi) {
+    case EPI_LINEAR: npp_gemm_kmajor<EPI_LINEAR><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
+    case EPI_SNAKE: npp_gemm_kmajor<EPI_SNAKE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
+    case EPI_DGRAD_MUL: npp_gemm_kmajor<EPI_DGRAD_MUL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
+    default: npp_gemm_kmajor<EPI_DGRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int run_forward(NppPlan* p, const float* coords, long long n, float* logits, cudaStream_t st) {
+  if (!p->params) return fail("npp_plan_bind has not been called");
+  CKI(prepare(p, n));
+  {
+    const int width = p->E;
+    dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
+    __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
+    npp_encode_kernel<<<grid, 512, ENC_ROWS * width * sizeof(__half), st>>>(
+        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
+    CK(cudaGetLastError());
+    ++p->launches;
+  }
+  for (size_t i = 0; i < p->layers.size(); ++i) {
+    CKI(launch_kmajor(p->fwd_params[i], p->layers[i].act ? EPI_SNAKE : EPI_LINEAR, p->num_sms, st));
+    ++p->launches;
+  }
+  const Layer& last = p->layers.back();
+  npp_head_fwd_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(
+      p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off, p->params + p->rgb_b_off,
+      logits);
+  CK(cudaGetLastError());
+  ++p->launches;
+  return 0;
+}
+
+// grad_logits must already be reflected in acc[amax] (loss kernel or amax kernel).
+static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st) {
+  if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
+  CKI(prepare(p, n));
+  CKI(set_smem_attrs());
+  const Layer& last = p->layers.back();
+  unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
+  npp_head_bwd_kernel<<<(unsigned)((n + HEAD_BWD_ROWS - 1) / HEAD_BWD_ROWS), 256, 0, st>>>(
+      g, p->bufs[last.buf_h].ptr, p->bufs[last.buf_d].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off,
+      amax, p->bufs[last.buf_delta].ptr, last.out, p->acc + p->headacc_off, p->acc + last.bg_off);
+  CK(cudaGetLastError());
+  ++p->launches;
+  for (size_t i = 0; i < p->dgrads.size(); ++i) {
+    const Layer& P = p->layers[p->dgrads[i].producer];
+    CKI(launch_kmajor(p->dgrad_params[i], P.act ? EPI_DGRAD_MUL : EPI_DGRAD, p->num_sms, st));
+    ++p->launches;
+  }
+  {
+    const int grid = p->n_units < p->num_sms ? p->n_units : p->num_sms;
+    npp_gemm_wgrad<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p->wg_params);
+    CK(cudaGetLastError());
+    ++p->launches;
+  }
+  {
+    dim3 grid(64, (unsigned)p->layers.size());
+    npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin, p->partial, p->wg_params.n_splits, p->slab_stride, p->acc,
+                                                   amax, p->grads);
+    CK(cudaGetLastError());
+    const int hn = 3 * p->head_width + 3;
+    // rgb_linear weight [3, W/2] and bias [3] are contiguous in the head accumulator and (up to the
+    // 4-float arena padding) in the arena: copy them separately.
+    npp_copy_kernel<<<2, 256, 0, st>>>(p->acc + p->headacc_off, p->grads + p->rgb_w_off, 3 * p->head_width);
+    npp_copy_kernel<<<1, 32, 0, st>>>(p->acc + p->headacc_off + 3 * p->head_width, p->grads + p->rgb_b_off, 3);
+    (void)hn;
+    CK(cudaGetLastError());
+    p->launches += 3;
+  }
+  return 0;
+}
+
+static int zero_acc(NppPlan* p, cudaStream_t st) {
+  CK(cudaMemsetAsync(p->acc, 0, p->acc_floats * sizeof(float), st));
+  return 0;
+}
+
+static int run_adam(NppPlan* p, float lr, float beta1, float beta2, float eps, long long step, cudaStream_t st) {
+  if (!p->params || !p->grads || !p->m || !p->v) return fail("npp_adam_step needs params, grads, exp_avg and exp_avg_sq bound");
+  if (step < 1) return fail("Adam step must be >= 1");
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  npp_adam_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->params, p->grads, p->m, p->v, p->arena_trained, beta1, beta2,
+                                                  step_size, inv_sqrt_bc2, eps);
+  CK(cudaGetLastError());
+  ++p->launches;
+  return 0;
+}
+
+static int run_shadow(NppPlan* p, cudaStream_t st) {
+  dim3 grid(96, (unsigned)p->layers.size());
+  npp_shadow_kernel<<<grid, 256, 0, st>>>(p->d_shadow, p->params);
+  CK(cudaGetLastError());
+  ++p->launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------ entry points
+extern "C" {
+
+const char* npp_last_error(void) { return g_err.c_str(); }
+int npp_abi_version(void) { return 1; }
+
+int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
+  if (!cfg || !out) return fail("npp_plan_create: null argument");
+  *out = nullptr;
+  if (cfg->model != NPP_MODEL_TOPK && cfg->model != NPP_MODEL_TOP1) return fail("unknown model kind");
+  if (cfg->model == NPP_MODEL_TOPK && cfg->topk < 2) return fail("NPP_Net (top-K) needs topk >= 2");
+  if (cfg->model == NPP_MODEL_TOP1 && cfg->topk != 1) return fail("NPP_Net_top1 needs topk == 1");
+  if (cfg->topk > MAX_TOPK) return fail("topk exceeds MAX_TOPK=8");
+  if (cfg->width <= 0 || cfg->width % 512 != 0) return fail("this build supports netwidth % 512 == 0 only");
+  if (cfg->depth < 2 || cfg->depth > 16) return fail("netdepth must be in [2,16]");
+  if (cfg->skip_layer >= cfg->depth - 1) return fail("skip layer must be < depth-1");
+  if (cfg->n_aug < 1 || cfg->n_aug > MAX_AUG) return fail("n_aug out of range");
+  if (cfg->n_freq < 0 || cfg->n_freq > MAX_FREQ) return fail("n_freq out of range");
+  if (cfg->max_rows < 1 || cfg->max_rows > (1LL << 24)) return fail("max_rows out of range");
+  if (!cfg->cos_t || !cfg->sin_t || !cfg->period || (cfg->n_freq > 0 && !cfg->freq))
+    return fail("encoder tables missing");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(std::string("libnpp_b200 requires an sm_100 (B200) device, found sm_") + std::to_string(prop.major) +
+                std::to_string(prop.minor) + "; there is no fallback path");
+  NppPlan* p = new NppPlan();
+  p->cfg = *cfg;
+  p->num_sms = prop.multiProcessorCount;
+  memset(&p->enc, 0, sizeof(p->enc));
+  p->enc.topk = cfg->topk;
+  p->enc.n_aug = cfg->n_aug;
+  p->enc.n_freq = cfg->n_freq;
+  p->enc.include_input = cfg->include_input;
+  p->enc.res_h = (float)cfg->res_h;
+  p->enc.res_w = (float)cfg->res_w;
+  for (int j = 0; j < cfg->topk; ++j)
+    for (int d = 0; d < 2; ++d)
+      for (int a = 0; a < cfg->n_aug; ++a) {
+        const int i = (j * 2 + d) * cfg->n_aug + a;
+        p->enc.cos_t[j][d][a] = cfg->cos_t[i];
+        p->enc.sin_t[j][d][a] = cfg->sin_t[i];
+        p->enc.period[j][d][a] = cfg->period[i];
+      }
+  for (int k = 0; k < cfg->n_freq; ++k) p->enc.freq[k] = cfg->freq[k];
+  p->cfg.cos_t = p->cfg.sin_t = p->cfg.period = p->cfg.freq = nullptr;
+  int r = build_graph(p);
+  if (r == 0) r = alloc_plan_memory(p);
+  if (r != 0) {
+    npp_plan_destroy(p);
+    return r;
+  }
+  *out = p;
+  return 0;
+}
+
+int npp_plan_destroy(NppPlan* p) {
+  if (!p) return 0;
+  cudaFree(p->workspace);
+  cudaFree(p->shadow_mem);
+  cudaFree(p->partial);
+  cudaFree(p->acc);
+  cudaFree(p->g_buf);
+  cudaFree(p->logits_buf);
+  cudaFree(p->d_fin);
+  cudaFree(p->d_shadow);
+  cudaFree(p->d_units);
+  delete p;
+  return 0;
+}
+
+int npp_plan_arena_floats(const NppPlan* p, int64_t* total, int64_t* trained) {
+  if (!p) return fail("null plan");
+  if (total) *total = p->arena_total;
+  if (trained) *trained = p->arena_trained;
+  return 0;
+}
+int npp_plan_tensor_count(const NppPlan* p) { return p ? (int)p->tensors.size() : 0; }
+int npp_plan_tensor_info(const NppPlan* p, int i, NppTensorInfo* info) {
+  if (!p || !info || i < 0 || i >= (int)p->tensors.size()) return fail("tensor index out of range");
+  *info = p->tensors[i];
+  return 0;
+}
+int npp_plan_encoding_width(const NppPlan* p) { return p ? p->E * p->cfg.topk : 0; }
+
+int npp_plan_bind(NppPlan* p, float* params, float* grads, float* m, float* v) {
+  if (!p || !params) return fail("npp_plan_bind: params arena is required");
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) return fail("arenas must be 16-byte aligned");
+  p->params = params;
+  p->grads = grads;
+  p->m = m;
+  p->v = v;
+  p->prepared_n = -1;  // bias pointers live in the cached kernel parameters
+  return 0;
+}
+
+int npp_sync_weights(NppPlan* p, void* stream) {
+  if (!p || !p->params) return fail("npp_sync_weights: no parameter arena bound");
+  return run_shadow(p, (cudaStream_t)stream);
+}
+
+int npp_encode(NppPlan* p, const float* coords, int64_t n, float* out, void* stream) {
+  if (!p || !coords || !out) return fail("npp_encode: null argument");
+  if (n <= 0) return 0;
+  npp_encode_f32_kernel<<<p->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(coords, (int)n, p->enc, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int npp_forward(NppPlan* p, const float* coords, int64_t n, float* logits, void* stream) {
+  if (!p || !coords || !logits) return fail("npp_forward: null argument");
+  p->launches = 0;
+  return run_forward(p, coords, n, logits, (cudaStream_t)stream);
+}
+
+int npp_backward(NppPlan* p, int64_t n, const float* g, void* stream) {
+  if (!p || !g) return fail("npp_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  p->launches = 0;
+  CKI(zero_acc(p, st));
+  npp_amax_kernel<<<64, 256, 0, st>>>(g, (int)(n * 3), reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
+  CK(cudaGetLastError());
+  ++p->launches;
+  return run_backward(p, n, g, st);
+}
+
+int npp_mse_fwd_bwd(NppPlan* p, const float* logits, const float* target, const float* mask, int64_t n, int64_t n_norm,
+                    float* pred, float* g, float* loss, void* stream) {
+  if (!p || !logits || !target || !g || !loss) return fail("npp_mse_fwd_bwd: null argument");
+  if (n_norm <= 0) return fail("n_norm must be positive");
+  // a private amax slot is not needed: npp_backward recomputes it from g.
+  unsigned int* scratch = reinterpret_cast<unsigned int*>(p->acc + p->amax_off + 1);
+  const float inv_count = 1.0f / (3.0f * (float)n_norm);
+  npp_mse_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(logits, target, mask, (int)n, inv_count, pred, g, loss, scratch);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int npp_adam_step(NppPlan* p, float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
+  if (!p) return fail("null plan");
+  p->launches = 0;
+  CKI(run_adam(p, lr, beta1, beta2, eps, step, (cudaStream_t)stream));
+  return run_shadow(p, (cudaStream_t)stream);
+}
+
+int npp_train_step(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n, int64_t n_norm,
+                   float lr, float beta1, float beta2, float eps, int64_t step, float* loss, void* stream) {
+  if (!p || !coords || !target || !loss) return fail("npp_train_step: null argument");
+  if (n_norm <= 0) return fail("n_norm must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  p->launches = 0;
+  CKI(run_forward(p, coords, n, p->logits_buf, st));
+  CKI(zero_acc(p, st));
+  CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  const float inv_count = 1.0f / (3.0f * (float)n_norm);
+  npp_mse_kernel<<<128, 256, 0, st>>>(p->logits_buf, target, mask, (int)n, inv_count, nullptr, p->g_buf, loss,
+                                      reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
+  CK(cudaGetLastError());
+  ++p->launches;
+  CKI(run_backward(p, n, p->g_buf, st));
+  CKI(run_adam(p, lr, beta1, beta2, eps, step, st));
+  return run_shadow(p, st);
+}
+
+int npp_last_launch_count(const NppPlan* p) { return p ? p->launches : 0; }
+
+__global__ void npp_half_to_float_kernel(const __half* __restrict__ src, int ld, int width, long long n,
+                                         float* __restrict__ dst) {
+  const long long total = n * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / width;
+    const int c = (int)(i - r * width);
+    dst[i] = __half2float(src[r * ld + c]);
+  }
+}
+
+static int find_buf(NppPlan* p, const char* name) {
+  if (!p || !name) return -1;
+  std::string s(name);
+  // aliases in reference vocabulary
+  const int nl = (int)p->layers.size();
+  if (s == "hp") s = "h" + std::to_string(nl - 1);
+  for (size_t i = 0; i < p->bufs.size(); ++i)
+    if (p->bufs[i].name == s) return (int)i;
+  return -1;
+}
+
+int npp_debug_width(NppPlan* p, const char* name) {
+  const int b = find_buf(p, name);
+  return b < 0 ? -1 : p->bufs[b].width;
+}
+
+int npp_debug_copy(NppPlan* p, const char* name, int64_t n, float* out, void* stream) {
+  const int b = find_buf(p, name);
+  if (b < 0) return fail(std::string("unknown buffer ") + (name ? name : "(null)"));
+  npp_half_to_float_kernel<<<p->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(p->bufs[b].ptr, p->bufs[b].width,
+                                                                            p->bufs[b].width, n, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+float npp_debug_grad_scale(NppPlan* p, void* stream) {
+  float amax = 0.f;
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaMemcpy(&amax, p->acc + p->amax_off, sizeof(float), cudaMemcpyDeviceToHost);
+  if (!(amax > 0.0f) || !std::isfinite(amax)) return 1.0f;
+  int e;
+  std::frexp(amax, &e);
+  int k = 10 - e;
+  k = k < -60 ? -60 : (k > 60 ? 60 : k);
+  return std::ldexp(1.0f, k);
+}
+
+int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, void* stream) {
+  if (n % BN != 0 || k % BK != 0) return fail("npp_debug_gemm: n % 256 == 0 and k % 64 == 0 required");
+  KmajorParams kp;
+  memset(&kp, 0, sizeof(kp));
+  CKI(make_map(&kp.tmA[0], a, m, k, k, BM));
+  CKI(make_map(&kp.tmB[0], b, n, k, k, 256));
+  kp.nseg = 1;
+  kp.kblocks[0] = k / BK;
+  kp.M = m;
+  kp.tiles_m = (m + BM - 1) / BM;
+  kp.tiles_n = n / BN;
+  kp.out_f32 = c;
+  kp.ldf = n;
+  if (const char* e = getenv("NPP_DEBUG_KM_LBO")) {
+    const char* s2 = getenv("NPP_DEBUG_KM_SBO");
+    kp.desc_hi = umma_desc_hi((uint32_t)atoi(e), s2 ? (uint32_t)atoi(s2) : 1024u);
+  }
+  if (const char* e = getenv("NPP_DEBUG_KM_KADV")) kp.k_adv = atoi(e);
+  // out0 unused: EPI_LINEAR writes fp16 to out0, so route it to a scratch buffer
+  __half* scratch = nullptr;
+  CK(cudaMalloc(&scratch, (size_t)m * n * sizeof(__half)));
+  kp.out0 = scratch;
+  kp.ld0 = n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int r = launch_kmajor(kp, EPI_LINEAR, sms, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(scratch);
+  if (r) return r;
+  CK(e);
+  return 0;
+}
+
+int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int n, int splits, void* stream) {
+  if (m % BM != 0 || n % BN != 0 || splits < 1) return fail("npp_debug_wgrad: m % 128 == 0, n % 256 == 0 required");
+  CKI(set_smem_attrs());
+  WgradParams w;
+  memset(&w, 0, sizeof(w));
+  CKI(make_map(&w.maps[0], a, rows, m, m, 64));
+  CKI(make_map(&w.maps[1], b, rows, n, n, 64));
+  std::vector<WgUnit> units;
+  for (int s = 0; s < splits; ++s)
+    for (int m0 = 0; m0 < m; m0 += BM)
+      for (int n0 = 0; n0 < n; n0 += BN) {
+        WgUnit u;
+        u.a_map = 0;
+        u.b_map = 1;
+        u.a_m0 = m0;
+        u.b_n0 = n0;
+        u.split = s;
+        u.out_off = m0 * n + n0;
+        u.ld = n;
+        u.ncols_left = n - n0;
+        units.push_back(u);
+      }
+  WgUnit* d_units = nullptr;
+  CK(cudaMalloc(&d_units, units.size() * sizeof(WgUnit)));
+  CK(cudaMemcpy(d_units, units.data(), units.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
+  const int kb_total = (rows + BK - 1) / BK;
+  w.units = d_units;
+  w.n_units = (int)units.size();
+  w.rows = rows;
+  w.kb_per_split = (kb_total + splits - 1) / splits;
+  w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
+  w.partial = c;
+  w.slab_stride = (long long)m * n;
+  if (const char* e = getenv("NPP_DEBUG_MN_LBO")) {
+    const char* s2 = getenv("NPP_DEBUG_MN_SBO");
+    w.desc_hi = umma_desc_hi((uint32_t)atoi(e), s2 ? (uint32_t)atoi(s2) : 1024u);
+  }
+  if (const char* e = getenv("NPP_DEBUG_MN_KADV")) w.k_adv = atoi(e);
+  if (w.n_splits < splits) CK(cudaMemsetAsync(c, 0, (size_t)splits * m * n * sizeof(float), (cudaStream_t)stream));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = w.n_units < sms ? w.n_units : sms;
+  npp_gemm_wgrad<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(w);
+  cudaError_t e1 = cudaGetLastError();
+  cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(d_units);
+  CK(e1);
+  CK(e2);
+  return 0;
+}
+
+}  // extern "C"

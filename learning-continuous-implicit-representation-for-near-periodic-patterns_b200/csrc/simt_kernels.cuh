@@ -1,0 +1,388 @@
+// CUDA-core kernels of the NPP-Net train step that are HBM/latency bound rather than
+// tensor bound: the periodicity-aware positional encoding, the 256->3 RGB head, the
+// masked-MSE loss, gradient finalisation, Adam and the fp16 shadow-weight refresh.
+// Every kernel cites the reference lines whose arithmetic it reproduces.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+namespace npp {
+
+constexpr int MAX_TOPK = 8;   // proposals
+constexpr int MAX_AUG = 16;   // (freq_scale x freq_offset x angle_offset) combinations per direction
+constexpr int MAX_FREQ = 16;  // Fourier frequencies of the NeRF-style expansion
+
+// Encoder constants, computed on the host in fp32 with the reference's own torch ops
+// (models/embedder.py:112-127) so that cos(theta), sin(theta) and the period match bit for bit.
+struct EncTable {
+  int topk;
+  int n_aug;
+  int n_freq;
+  int include_input;  // 1: [x_norm, sin/cos...] per direction (embedder.py:105-109)
+  float res_h, res_w;
+  float cos_t[MAX_TOPK][2][MAX_AUG];
+  float sin_t[MAX_TOPK][2][MAX_AUG];
+  float period[MAX_TOPK][2][MAX_AUG];
+  float freq[MAX_FREQ];
+};
+
+// torch.remainder semantics (sign of the divisor), embedder.py:127 uses the % operator.
+__device__ __forceinline__ float torch_remainder(float a, float b) {
+  float r = fmodf(a, b);
+  if (r != 0.0f && ((r < 0.0f) != (b < 0.0f))) r += b;
+  return r;
+}
+
+// Base periodic feature c (0 .. 2*(1+2*n_aug)-1) of one proposal for pixel (row y, col x).
+// Layout (embedder.py:140-148): fn_x list then fn_y list; each list is
+// [normalised coordinate, sin phi_0, cos phi_0, sin phi_1, cos phi_1, ...].
+__device__ __forceinline__ float npp_base_feature(const EncTable& t, int j, int c, float y, float x) {
+  const int per_dir = t.include_input + 2 * t.n_aug;
+  const int dir = c / per_dir;
+  int r = c - dir * per_dir;
+  if (t.include_input) {
+    if (r == 0) {
+      // (x / res[1] - 0.5) * 2  |  (y / res[0] - 0.5) * 2      embedder.py:107-108
+      const float v = dir == 0 ? __fdiv_rn(x, t.res_w) : __fdiv_rn(y, t.res_h);
+      return __fmul_rn(__fsub_rn(v, 0.5f), 2.0f);
+    }
+    r -= 1;
+  }
+  const int aug = r >> 1;
+  const float ct = t.cos_t[j][dir][aug], st = t.sin_t[j][dir][aug], P = t.period[j][dir][aug];
+  // (((y*cos + x*sin) % P) / P) * 2 * pi, every step rounded to fp32 like the eager torch ops
+  const float proj = __fadd_rn(__fmul_rn(y, ct), __fmul_rn(x, st));
+  const float frac = __fdiv_rn(torch_remainder(proj, P), P);
+  const float phi = __fmul_rn(__fmul_rn(frac, 2.0f), 3.14159265358979323846f);
+  return (r & 1) ? cosf(phi) : sinf(phi);
+}
+
+// Expanded encoding of ENC_ROWS rows of one proposal -> fp16, reference column order
+// out[:, b*B + c]: b = 0 identity, b = 1+2k sin(f_k u_c), b = 2+2k cos(f_k u_c)   (embedder.py:41-44,56)
+constexpr int ENC_ROWS = 16;
+__global__ void __launch_bounds__(512) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
+                                                         __half* __restrict__ enc1, int ld1,
+                                                         __half* __restrict__ enca, int lda) {
+  extern __shared__ __half enc_tile[];  // [ENC_ROWS][width]
+  const int B = 2 * (t.include_input + 2 * t.n_aug);
+  const int F = 1 + 2 * t.n_freq;
+  const int width = B * F;
+  const int j = blockIdx.y;
+  const int row0 = blockIdx.x * ENC_ROWS;
+  for (int idx = threadIdx.x; idx < ENC_ROWS * B; idx += blockDim.x) {
+    const int r = idx / B, c = idx - r * B;
+    const int row = row0 + r;
+    if (row < n) {
+      const float y = coords[2 * row], x = coords[2 * row + 1];
+      const float u = npp_base_feature(t, j, c, y, x);
+      __half* o = enc_tile + r * width + c;
+      o[0] = __float2half_rn(u);
+      for (int k = 0; k < t.n_freq; ++k) {
+        const float a = __fmul_rn(u, t.freq[k]);  // p_fn(x * freq), embedder.py:43
+        o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
+        o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
+      }
+    }
+  }
+  __syncthreads();
+  __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
+  const int ld = j == 0 ? ld1 : lda;
+  const int w2 = width >> 1;  // width is even (B is even)
+  for (int idx = threadIdx.x; idx < ENC_ROWS * w2; idx += blockDim.x) {
+    const int r = idx / w2, c2 = idx - r * w2;
+    const int row = row0 + r;
+    if (row < n)
+      *reinterpret_cast<__half2*>(dst + (size_t)row * ld + 2 * c2) =
+          *reinterpret_cast<const __half2*>(enc_tile + r * width + 2 * c2);
+  }
+}
+
+// fp32 materialised encoding in the reference layout [n, topk*width] (parity tests and
+// the "materialised mode" of the drop-in embedder).
+__global__ void npp_encode_f32_kernel(const float* __restrict__ coords, int n, EncTable t, float* __restrict__ out) {
+  const int B = 2 * (t.include_input + 2 * t.n_aug);
+  const int F = 1 + 2 * t.n_freq;
+  const int width = B * F;
+  const long long total = (long long)n * t.topk * B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % B;
+    const int j = (idx / B) % t.topk;
+    const long long row = idx / ((long long)B * t.topk);
+    const float y = coords[2 * row], x = coords[2 * row + 1];
+    const float u = npp_base_feature(t, j, c, y, x);
+    float* o = out + row * (long long)(t.topk * width) + j * width + c;
+    o[0] = u;
+    for (int k = 0; k < t.n_freq; ++k) {
+      const float a = __fmul_rn(u, t.freq[k]);
+      o[(1 + 2 * k) * B] = sinf(a);
+      o[(2 + 2 * k) * B] = cosf(a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ RGB head
+// logits = h_P . W_rgb^T + b_rgb   (models/networks.py:94), one warp per row.
+__global__ void __launch_bounds__(256) npp_head_fwd_kernel(const __half* __restrict__ hp, int ld, int width, int n,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           float* __restrict__ logits) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const __half* h = hp + (size_t)warp * ld;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = lane * 8; k < width; k += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      const int kk = k + 2 * i;
+      a0 = fmaf(f.x, w[kk], fmaf(f.y, w[kk + 1], a0));
+      a1 = fmaf(f.x, w[width + kk], fmaf(f.y, w[width + kk + 1], a1));
+      a2 = fmaf(f.x, w[2 * width + kk], fmaf(f.y, w[2 * width + kk + 1], a2));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+  }
+  if (lane == 0) {
+    logits[3 * (size_t)warp + 0] = a0 + b[0];
+    logits[3 * (size_t)warp + 1] = a1 + b[1];
+    logits[3 * (size_t)warp + 2] = a2 + b[2];
+  }
+}
+
+// Power-of-two gradient scale so that fp16 deltas sit in the middle of the half range:
+// amax * scale == 2^10 (rounded down to a power of two).  Exact to undo in fp32.
+__device__ __forceinline__ float npp_grad_scale(float amax) {
+  if (!(amax > 0.0f) || !isfinite(amax)) return 1.0f;
+  int e;
+  frexpf(amax, &e);  // amax = m * 2^e, m in [0.5, 1)
+  int k = 10 - e;
+  k = max(-60, min(60, k));
+  return ldexpf(1.0f, k);
+}
+
+// sigmoid + masked MSE (models/helpers.py:55-56, models/mse_calculator.py:13-27 'l2' branch)
+//   y_hat = sigmoid(logit); d = (y_hat - y) * (m + 0.3 (1 - m)); loss = mean(d^2) over n_norm*3
+// also emits g = dLoss/dlogit and the running max |g| (as uint bits) for the fp16 delta scale.
+__global__ void __launch_bounds__(256) npp_mse_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                      const float* __restrict__ mask, int n, float inv_count,
+                                                      float* __restrict__ pred, float* __restrict__ g,
+                                                      float* __restrict__ loss, unsigned int* __restrict__ amax_bits) {
+  float lsum = 0.f, lmax = 0.f;
+  const int total = n * 3;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int row = idx / 3;
+    const float z = logits[idx];
+    const float yh = 1.0f / (1.0f + expf(-z));
+    const float m = mask ? mask[row] : 1.0f;
+    const float w = m + (1.0f - m) * 0.3f;
+    const float d = (yh - target[idx]) * w;
+    lsum += d * d;
+    const float gi = 2.0f * d * w * inv_count * yh * (1.0f - yh);
+    if (pred) pred[idx] = yh;
+    g[idx] = gi;
+    lmax = fmaxf(lmax, fabsf(gi));
+  }
+  __shared__ float ssum[8], smax[8];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, s);
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = lsum;
+    smax[threadIdx.x >> 5] = lmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      a += ssum[i];
+      b = fmaxf(b, smax[i]);
+    }
+    atomicAdd(loss, a * inv_count);
+    atomicMax(amax_bits, __float_as_uint(b));  // non-negative floats order like their bit patterns
+  }
+}
+
+// max |g| of an externally supplied gradient (autograd path).
+__global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__ g, int total,
+                                                       unsigned int* __restrict__ amax_bits) {
+  float lmax = 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    lmax = fmaxf(lmax, fabsf(g[idx]));
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, s));
+  if ((threadIdx.x & 31) == 0 && lmax > 0.f) atomicMax(amax_bits, __float_as_uint(lmax));
+}
+
+// Backward of the RGB head: delta_P = (g . W_rgb) * snake'(z_P) * scale (fp16), plus
+// dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
+constexpr int HEAD_BWD_ROWS = 64;
+__global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
+                                                           const __half* __restrict__ dp, int ld, int width, int n,
+                                                           const float* __restrict__ w,
+                                                           const unsigned int* __restrict__ amax_bits,
+                                                           __half* __restrict__ delta, int ldd,
+                                                           float* __restrict__ head_acc /*[3*width+3]*/,
+                                                           float* __restrict__ bias_acc /*[width]*/) {
+  __shared__ float sg[HEAD_BWD_ROWS * 3];
+  const float scale = npp_grad_scale(__uint_as_float(*amax_bits));
+  const int row0 = blockIdx.x * HEAD_BWD_ROWS;
+  const int rows = min(HEAD_BWD_ROWS, n - row0);
+  for (int i = threadIdx.x; i < rows * 3; i += blockDim.x) sg[i] = g[(size_t)row0 * 3 + i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < width; k += blockDim.x) {
+    const float w0 = w[k], w1 = w[width + k], w2 = w[2 * width + k];
+    float aw0 = 0.f, aw1 = 0.f, aw2 = 0.f, ab = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      const float g0 = sg[3 * r], g1 = sg[3 * r + 1], g2 = sg[3 * r + 2];
+      const size_t off = (size_t)(row0 + r) * ld + k;
+      const float h = __half2float(hp[off]);
+      const float d = __half2float(dp[off]);
+      const float da = fmaf(g0, w0, fmaf(g1, w1, g2 * w2));
+      const __half dh = __float2half_rn(da * d * scale);
+      delta[(size_t)(row0 + r) * ldd + k] = dh;
+      ab += __half2float(dh);
+      aw0 = fmaf(g0, h, aw0);
+      aw1 = fmaf(g1, h, aw1);
+      aw2 = fmaf(g2, h, aw2);
+    }
+    atomicAdd(head_acc + k, aw0);
+    atomicAdd(head_acc + width + k, aw1);
+    atomicAdd(head_acc + 2 * width + k, aw2);
+    atomicAdd(bias_acc + k, ab);
+  }
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += sg[3 * r + threadIdx.x];
+    atomicAdd(head_acc + 3 * width + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------- gradients / Adam
+struct FinalizeLayer {
+  long long w_off, b_off;    // arena offsets (floats) of weight [out, in_ref] and bias [out]
+  long long pg_off;          // offset of this layer's [out, kpad] block inside a partial slab
+  long long bg_off;          // offset of the scaled bias-gradient accumulator
+  int out, in_ref, kpad;
+  int split_col;             // reference columns < split_col map to off0 + c, others to off1 + (c - split_col)
+  int off0, off1;
+};
+
+// grads[w] = (sum over split-K slabs) / scale ; grads[b] = bias_acc / scale
+__global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLayer* __restrict__ layers,
+                                                                const float* __restrict__ partial, int n_splits,
+                                                                long long slab_stride, const float* __restrict__ bias_acc,
+                                                                const unsigned int* __restrict__ amax_bits,
+                                                                float* __restrict__ grads) {
+  const FinalizeLayer L = layers[blockIdx.y];
+  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
+  const long long total = (long long)L.out * L.in_ref;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o = idx / L.in_ref;
+    const int c = idx - (long long)o * L.in_ref;
+    const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
+    const float* p = partial + L.pg_off + (long long)o * L.kpad + pc;
+    float s = 0.f;
+    for (int k = 0; k < n_splits; ++k) s += p[k * slab_stride];
+    grads[L.w_off + idx] = s * inv;
+  }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < L.out; o += gridDim.x * blockDim.x)
+    grads[L.b_off + o] = bias_acc[L.bg_off + o] * inv;
+}
+
+__global__ void npp_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// torch.optim.Adam single-tensor arithmetic (torch/optim/adam.py _single_tensor_adam, constructed at
+// reference models/helpers.py:164): m.lerp_(g, 1-b1); v = b2 v + (1-b2) g g;
+// p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) npp_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, long long n,
+                                                       float beta1, float beta2, float step_size, float inv_sqrt_bc2,
+                                                       float eps) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define NPP_ADAM1(c)                                                   \
+  mm.c = mm.c + (gg.c - mm.c) * (1.0f - beta1);                        \
+  vv.c = vv.c * beta2 + (1.0f - beta2) * gg.c * gg.c;                  \
+  pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) * inv_sqrt_bc2 + eps));
+    NPP_ADAM1(x) NPP_ADAM1(y) NPP_ADAM1(z) NPP_ADAM1(w)
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (arena sizes are padded to 4, kept for safety)
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float mm = m[i] + (g[i] - m[i]) * (1.0f - beta1);
+    float vv = v[i] * beta2 + (1.0f - beta2) * g[i] * g[i];
+    p[i] -= step_size * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+    m[i] = mm;
+    v[i] = vv;
+  }
+#undef NPP_ADAM1
+}
+
+// fp32 master weights -> fp16 shadows: K-padded forward copy [out, kpad] and the transposed
+// copy [in_sub, out] that the dgrad GEMMs read K-major.
+struct ShadowLayer {
+  long long w_off;
+  int out, in_ref, kpad;
+  int split_col, off0, off1;  // reference column -> padded column (same rule as FinalizeLayer)
+  __half* wf;                 // [out, kpad]
+  __half* wt;                 // [wt_rows, out] or null
+  int t_lo, t_hi, t_row0;     // reference columns [t_lo, t_hi) go to wt rows t_row0 + (c - t_lo)
+  int t_lo2, t_hi2, t_row02;  // optional second range
+};
+
+__global__ void __launch_bounds__(256) npp_shadow_kernel(const ShadowLayer* __restrict__ layers,
+                                                         const float* __restrict__ params) {
+  __shared__ float tile[32][33];
+  const ShadowLayer L = layers[blockIdx.y];
+  const int tiles_c = (L.in_ref + 31) / 32;
+  const int tiles_r = L.out / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      float v = 0.f;
+      if (c < L.in_ref) {
+        v = params[L.w_off + (long long)r * L.in_ref + c];
+        const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
+        L.wf[(long long)r * L.kpad + pc] = __float2half_rn(v);
+      }
+      tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+    if (L.wt != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        int trow = -1;
+        if (c >= L.t_lo && c < L.t_hi) trow = L.t_row0 + (c - L.t_lo);
+        else if (c >= L.t_lo2 && c < L.t_hi2) trow = L.t_row02 + (c - L.t_lo2);
+        if (trow >= 0) L.wt[(long long)trow * L.out + r] = __float2half_rn(tile[tx][ty + 8 * i]);
+      }
+    }
+  }
+}
+
+}  // namespace npp
