@@ -113,6 +113,15 @@ int npp_train_step(NppPlan* plan, const float* coords, const float* target, cons
 /* Number of kernels the last npp_train_step / forward / backward call launched. */
 int npp_last_launch_count(const NppPlan* plan);
 
+/* Per-kernel-class device timing with CUDA events on the launching stream (bench.py's roofline).
+ * Classes: 0 encode, 1 forward GEMMs (npp_gemm_kmajor), 2 head+loss, 3 dgrad GEMMs (npp_gemm_kmajor),
+ * 4 wgrad GEMM (npp_gemm_wgrad), 5 gradient finalize, 6 Adam + shadow refresh.
+ * npp_profile_read synchronises the device and returns accumulated milliseconds / launch counts
+ * since npp_profile_enable(plan, 1). */
+#define NPP_PROFILE_CLASSES 7
+int npp_profile_enable(NppPlan* plan, int on);
+int npp_profile_read(NppPlan* plan, int n_classes, double* ms, int64_t* launches);
+
 /* Test hooks: copy an internal fp16 activation/gradient buffer ("h0".."h7","d0",...,"delta0",...,
  * "f1","hs","f2","hp","enc1","enc_aux") to a caller fp32 [n, width] device buffer. */
 int npp_debug_width(NppPlan* plan, const char* name);

@@ -65,6 +65,8 @@ SIGNATURES = {
     "npp_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, _P, _P]),
     "npp_last_launch_count": (C.c_int, [_P]),
+    "npp_profile_enable": (C.c_int, [_P, C.c_int]),
+    "npp_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "npp_debug_width": (C.c_int, [_P, C.c_char_p]),
     "npp_debug_copy": (C.c_int, [_P, C.c_char_p, C.c_int64, _P, _P]),
     "npp_debug_grad_scale": (C.c_float, [_P, _P]),

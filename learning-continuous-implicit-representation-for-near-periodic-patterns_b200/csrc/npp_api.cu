@@ -108,6 +108,8 @@ struct DgradOp {
   int nsrc;
 };
 
+enum { PROF_ENCODE = 0, PROF_GEMM_FWD, PROF_HEAD_LOSS, PROF_GEMM_DGRAD, PROF_GEMM_WGRAD, PROF_FINALIZE, PROF_ADAM, NPP_PROF_CLASSES };
+
 struct NppPlan {
   NppConfig cfg;
   EncTable enc;
@@ -148,6 +150,32 @@ struct NppPlan {
   WgradParams wg_params;
   std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
   int launches = 0;
+
+  // optional per-kernel-class timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+  double cls_ms[NPP_PROF_CLASSES] = {0};
+  long long cls_launches[NPP_PROF_CLASSES] = {0};
+};
+
+struct ProfScope {
+  NppPlan* p; cudaStream_t st; int cls; int n; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(NppPlan* p_, cudaStream_t st_, int cls_, int n_launches) : p(p_), st(st_), cls(cls_), n(n_launches) {
+    if (!p->profiling) return;
+    while (p->ev_pool.size() < p->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->ev_pool.push_back(e); }
+    a = p->ev_pool[p->ev_used++]; b = p->ev_pool[p->ev_used++];
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    NppPlan::Span s; s.cls = cls; s.a = a; s.b = b;
+    p->spans.push_back(s);
+    p->cls_launches[cls] += n;
+  }
 };
 
 static int add_buf(NppPlan* p, const std::string& name, int width) {
@@ -560,6 +588,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
   if (!p->params) return fail("npp_plan_bind has not been called");
   CKI(prepare(p, n));
   {
+    ProfScope ps(p, st, PROF_ENCODE, 1);
     const int width = p->E;
     dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
@@ -568,11 +597,15 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     CK(cudaGetLastError());
     ++p->launches;
   }
-  for (size_t i = 0; i < p->layers.size(); ++i) {
-    CKI(launch_kmajor(p->fwd_params[i], p->layers[i].act ? EPI_SNAKE : EPI_LINEAR, p->num_sms, st));
-    ++p->launches;
+  {
+    ProfScope ps(p, st, PROF_GEMM_FWD, (int)p->layers.size());
+    for (size_t i = 0; i < p->layers.size(); ++i) {
+      CKI(launch_kmajor(p->fwd_params[i], p->layers[i].act ? EPI_SNAKE : EPI_LINEAR, p->num_sms, st));
+      ++p->launches;
+    }
   }
   const Layer& last = p->layers.back();
+  ProfScope ps_head(p, st, PROF_HEAD_LOSS, 1);
   npp_head_fwd_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(
       p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off, p->params + p->rgb_b_off,
       logits);
@@ -588,23 +621,31 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   CKI(set_smem_attrs());
   const Layer& last = p->layers.back();
   unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
+  {
+  ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
   npp_head_bwd_kernel<<<(unsigned)((n + HEAD_BWD_ROWS - 1) / HEAD_BWD_ROWS), 256, 0, st>>>(
       g, p->bufs[last.buf_h].ptr, p->bufs[last.buf_d].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off,
       amax, p->bufs[last.buf_delta].ptr, last.out, p->acc + p->headacc_off, p->acc + last.bg_off);
   CK(cudaGetLastError());
   ++p->launches;
-  for (size_t i = 0; i < p->dgrads.size(); ++i) {
-    const Layer& P = p->layers[p->dgrads[i].producer];
-    CKI(launch_kmajor(p->dgrad_params[i], P.act ? EPI_DGRAD_MUL : EPI_DGRAD, p->num_sms, st));
-    ++p->launches;
   }
   {
+    ProfScope ps(p, st, PROF_GEMM_DGRAD, (int)p->dgrads.size());
+    for (size_t i = 0; i < p->dgrads.size(); ++i) {
+      const Layer& P = p->layers[p->dgrads[i].producer];
+      CKI(launch_kmajor(p->dgrad_params[i], P.act ? EPI_DGRAD_MUL : EPI_DGRAD, p->num_sms, st));
+      ++p->launches;
+    }
+  }
+  {
+    ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
     const int grid = p->n_units < p->num_sms ? p->n_units : p->num_sms;
     npp_gemm_wgrad<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p->wg_params);
     CK(cudaGetLastError());
     ++p->launches;
   }
   {
+    ProfScope ps(p, st, PROF_FINALIZE, 3);
     dim3 grid(64, (unsigned)p->layers.size());
     npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin, p->partial, p->wg_params.n_splits, p->slab_stride, p->acc,
                                                    amax, p->grads);
@@ -633,6 +674,7 @@ static int run_adam(NppPlan* p, float lr, float beta1, float beta2, float eps, l
   const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  ProfScope ps(p, st, PROF_ADAM, 1);
   npp_adam_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->params, p->grads, p->m, p->v, p->arena_trained, beta1, beta2,
                                                   step_size, inv_sqrt_bc2, eps);
   CK(cudaGetLastError());
@@ -641,6 +683,7 @@ static int run_adam(NppPlan* p, float lr, float beta1, float beta2, float eps, l
 }
 
 static int run_shadow(NppPlan* p, cudaStream_t st) {
+  ProfScope ps(p, st, PROF_ADAM, 1);
   dim3 grid(96, (unsigned)p->layers.size());
   npp_shadow_kernel<<<grid, 256, 0, st>>>(p->d_shadow, p->params);
   CK(cudaGetLastError());
@@ -717,6 +760,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_fin);
   cudaFree(p->d_shadow);
   cudaFree(p->d_units);
+  for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;
 }
@@ -805,16 +849,42 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   CKI(zero_acc(p, st));
   CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
+  {
+  ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
   npp_mse_kernel<<<128, 256, 0, st>>>(p->logits_buf, target, mask, (int)n, inv_count, nullptr, p->g_buf, loss,
                                       reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
   CK(cudaGetLastError());
   ++p->launches;
+  }
   CKI(run_backward(p, n, p->g_buf, st));
   CKI(run_adam(p, lr, beta1, beta2, eps, step, st));
   return run_shadow(p, st);
 }
 
 int npp_last_launch_count(const NppPlan* p) { return p ? p->launches : 0; }
+
+int npp_profile_enable(NppPlan* p, int on) {
+  if (!p) return fail("null plan");
+  p->profiling = on != 0;
+  p->spans.clear();
+  p->ev_used = 0;
+  for (int i = 0; i < NPP_PROF_CLASSES; ++i) { p->cls_ms[i] = 0; p->cls_launches[i] = 0; }
+  return 0;
+}
+
+int npp_profile_read(NppPlan* p, int n_classes, double* ms, int64_t* launches) {
+  if (!p || !ms || !launches) return fail("npp_profile_read: null argument");
+  CK(cudaDeviceSynchronize());
+  for (auto& s : p->spans) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, s.a, s.b));
+    p->cls_ms[s.cls] += t;
+  }
+  p->spans.clear();
+  p->ev_used = 0;
+  for (int i = 0; i < n_classes && i < NPP_PROF_CLASSES; ++i) { ms[i] = p->cls_ms[i]; launches[i] = p->cls_launches[i]; }
+  return 0;
+}
 
 __global__ void npp_half_to_float_kernel(const __half* __restrict__ src, int ld, int width, long long n,
                                          float* __restrict__ dst) {

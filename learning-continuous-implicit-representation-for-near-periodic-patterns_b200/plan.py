@@ -172,6 +172,21 @@ class Plan:
             v.copy_(src.to(self.device, torch.float32).reshape(v.shape))
         self.sync_weights()
 
+    def reset_parameters(self, seed: Optional[int] = None):
+        """torch.nn.Linear default init for every tensor: U(-1/sqrt(in), 1/sqrt(in)) for weight and bias
+        (the reference keeps PyTorch's default because weights_init_normal only touches Conv/BatchNorm,
+        models/helpers.py:65-71,140-141)."""
+        gen = torch.Generator(device="cpu")
+        if seed is not None:
+            gen.manual_seed(seed)
+        views = self.param_views()
+        for s in self.slots:
+            fan_in = s.shape[1] if len(s.shape) == 2 else dict((t.name, t) for t in self.slots)[
+                s.name.replace(".bias", ".weight")].shape[1]
+            bound = 1.0 / math.sqrt(fan_in)
+            views[s.name].copy_((torch.rand(s.shape, generator=gen) * 2 - 1) * bound)
+        self.sync_weights()
+
     def state(self) -> Dict[str, torch.Tensor]:
         return {k: v.detach().clone() for k, v in self.param_views().items()}
 
@@ -236,6 +251,19 @@ class Plan:
 
     def launch_count(self) -> int:
         return self.lib.npp_last_launch_count(self.handle)
+
+    PROFILE_CLASSES = ("encode", "gemm_fwd", "head_loss", "gemm_dgrad", "gemm_wgrad", "grad_finalize", "adam_shadow")
+
+    def profile(self, on: bool):
+        nat.check(self.lib.npp_profile_enable(self.handle, int(on)))
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} accumulated since profile(True); synchronises."""
+        k = len(self.PROFILE_CLASSES)
+        ms = (C.c_double * k)()
+        ln = (C.c_int64 * k)()
+        nat.check(self.lib.npp_profile_read(self.handle, k, ms, ln))
+        return {name: (ms[i], ln[i]) for i, name in enumerate(self.PROFILE_CLASSES)}
 
     # --------------------------------------------------------------------- tests
     def debug(self, name: str, n: int) -> torch.Tensor:
