@@ -265,11 +265,18 @@ def test_linearity_of_backward_in_grad():
     plan.forward(cd)
     g = torch.randn(n, 3, device="cuda") * 1e-5
     plan.backward(n, g)
-    g1 = plan.grads.clone()
+    g1 = {k: v.clone() for k, v in plan.grad_views().items()}
     plan.backward(n, g * 1024.0)
-    g2 = plan.grads.clone()
-    assert torch.equal(g1 * 1024.0, g2)
-    assert torch.isfinite(g1).all() and g1.abs().max() > 0
+    g2 = plan.grad_views()
+    for k in g1:
+        assert torch.isfinite(g1[k]).all() and g1[k].abs().max() > 0, k
+        if k.endswith(".weight") and not k.startswith("rgb_linear"):
+            # split-K slabs are reduced in a fixed order -> bit-exact linearity
+            assert torch.equal(g1[k] * 1024.0, g2[k]), k
+        else:
+            # bias / head gradients are accumulated with atomics: linear up to fp32 summation order
+            err = ((g1[k] * 1024.0 - g2[k]).abs().max() / g2[k].abs().max()).item()
+            assert err < 1e-4, (k, err)
 
 
 def test_rejects_bad_input():
