@@ -89,6 +89,10 @@ int npp_encode(NppPlan* plan, const float* coords, int64_t n, float* out, void* 
  * writes the pre-sigmoid logits [n,3] fp32 and keeps the activations needed by npp_backward. */
 int npp_forward(NppPlan* plan, const float* coords, int64_t n, float* logits, void* stream);
 
+/* Same network on a materialised encoding: enc device [n, K*462] fp32 in the reference layout (rows of the
+ * table built at NPP_completion/train.py:93-105), i.e. NPP_Net.forward(None, x_periodic) verbatim. */
+int npp_forward_encoded(NppPlan* plan, const float* enc, int64_t n, float* logits, void* stream);
+
 /* autograd backward of the forward above: grad_logits device [n,3] fp32 -> bound grads arena
  * (reference: loss.backward(), NPP_completion/train.py:253). */
 int npp_backward(NppPlan* plan, int64_t n, const float* grad_logits, void* stream);

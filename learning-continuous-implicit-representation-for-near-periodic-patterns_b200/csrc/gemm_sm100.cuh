@@ -28,7 +28,10 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * BN * 4 + 256 + 1024;
+constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
+constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
+constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;  // 4 epilogue warps x 2 buffers = 32 KB
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + 256 + 1024;
 
 enum : int {
   EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
@@ -40,6 +43,9 @@ enum : int {
 struct alignas(64) KmajorParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];
+  CUtensorMap tmOut0;  // box {64, 32} store maps of out0 / out1, load map of mul
+  CUtensorMap tmOut1;
+  CUtensorMap tmMul;
   int nseg;
   int kblocks[2];  // K blocks (of 64) per segment
   int a_k0[2];     // first K element of the segment inside A's tensor
@@ -99,11 +105,12 @@ struct PipeState {
 struct GemmSmem {
   uint8_t* a;
   uint8_t* b;
-  float* bias;  // 2 x BN
+  uint8_t* epi;  // 4 warps x 2 x 4 KB staging, 1024-B aligned
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tfull;
   uint64_t* tempty;
+  uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
   uint32_t* tmem_ptr;
 };
 
@@ -113,12 +120,13 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   GemmSmem s;
   s.a = base;
   s.b = base + STAGES * A_STAGE_BYTES;
-  s.bias = reinterpret_cast<float*>(s.b + STAGES * B_STAGE_BYTES);
-  s.full = reinterpret_cast<uint64_t*>(s.bias + 2 * BN);
+  s.epi = s.b + STAGES * B_STAGE_BYTES;
+  s.full = reinterpret_cast<uint64_t*>(s.epi + EPI_STAGE_BYTES);
   s.empty = s.full + STAGES;
   s.tfull = s.empty + STAGES;
   s.tempty = s.tfull + 2;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tempty + 2);
+  s.epi_bar = s.tempty + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
   return s;
 }
 
@@ -132,6 +140,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
       mbar_init(&s.tfull[i], 1);
       mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
@@ -185,6 +194,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       tma_prefetch_desc(&p.tmA[i]);
       tma_prefetch_desc(&p.tmB[i]);
     }
+    tma_prefetch_desc(&p.tmOut0);
+    if (EPI == EPI_SNAKE) tma_prefetch_desc(&p.tmOut1);
+    if (EPI == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
   }
   const uint32_t tmem_base = gemm_prologue(s, warp);
   const int total_tiles = p.tiles_m * p.tiles_n;
@@ -248,111 +260,115 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int et = threadIdx.x - 64;          // 0..127
+    // Each warp owns 32 accumulator rows (its TMEM lane quadrant).  Results are staged in a per-warp
+    // 128B-swizzled 32x64 smem box and written with TMA stores (full 128-byte lines); the dgrad
+    // multiplier (stored snake derivative) arrives the same way through a TMA load.
     const int lane_base = (warp & 3) * 32;    // TMEM lane quadrant this warp may access
+    uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
+    uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
+    uint64_t* ebar = &s.epi_bar[warp & 3];
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+    uint32_t ld_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      const int row = m0 + lane_base + lane;
+      const int row0 = m0 + lane_base;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      float* sbias = s.bias + acc * BN;
-      if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
-        float2 bv = make_float2(0.f, 0.f);
-        if (p.bias != nullptr) bv = *reinterpret_cast<const float2*>(p.bias + n0 + et * 2);
-        *reinterpret_cast<float2*>(sbias + et * 2) = bv;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      uint4 mreg[4];
+      const bool warp_ok = row0 < p.M;
       if (EPI == EPI_DGRAD_MUL) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          mreg[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.mul + (size_t)row * p.ldm + n0) + j)
-                           : make_uint4(0, 0, 0, 0);
+        if (lane == 0) {  // multiplier sub-tile 0, overlapped with the wait for the accumulator
+          mbar_expect_tx(ebar, EPI_BUF_BYTES);
+          tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
+        }
       }
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + chunk * 32, raw);
-        uint4 mcur[4];
+      for (int sub = 0; sub < BN / EPI_COLS; ++sub) {
+        const int col = n0 + sub * EPI_COLS;
         if (EPI == EPI_DGRAD_MUL) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mcur[j] = mreg[j];
-          if (chunk + 1 < BN / 32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              mreg[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.mul + (size_t)row * p.ldm + n0 +
-                                                                       (chunk + 1) * 32) + j)
-                               : make_uint4(0, 0, 0, 0);
-          }
+          mbar_wait(ebar, ld_phase);
+          ld_phase ^= 1;
         }
-        tmem_ld_wait();
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const int col = n0 + chunk * 32;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + sub * EPI_COLS + half * 32,
+                        raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          const int hcol = col + half * 32;
 
-        if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+          if ((EPI == EPI_LINEAR || EPI == EPI_SNAKE) && p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 b4 = *reinterpret_cast<const float4*>(sbias + chunk * 32 + i);
-            v[i] += b4.x;
-            v[i + 1] += b4.y;
-            v[i + 2] += b4.z;
-            v[i + 3] += b4.w;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + hcol + i));
+              v[i] += b4.x;
+              v[i + 1] += b4.y;
+              v[i + 2] += b4.z;
+              v[i + 3] += b4.w;
+            }
           }
-        }
-        if (p.out_f32 != nullptr && row_ok) {
-          float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldf + col);
+          if (p.out_f32 != nullptr && row_ok) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldf + hcol);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (EPI == EPI_SNAKE) {
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
           uint32_t hd[16], dd[16];
+          if (EPI == EPI_SNAKE) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float h2[2], d2[2];
+            for (int i = 0; i < 32; i += 2) {
+              float h2[2], d2[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float z = v[i + e];
-              const float w = z + z;
-              const float sn = __sinf(w);
-              const float cs = __cosf(w);
-              h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
-              d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+              for (int e = 0; e < 2; ++e) {
+                const float z = v[i + e];
+                const float w = z + z;
+                const float sn = __sinf(w);
+                const float cs = __cosf(w);
+                h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
+                d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+              }
+              hd[i >> 1] = pack_h2(h2[0], h2[1]);
+              dd[i >> 1] = pack_h2(d2[0], d2[1]);
             }
-            hd[i >> 1] = pack_h2(h2[0], h2[1]);
-            dd[i >> 1] = pack_h2(d2[0], d2[1]);
-          }
-          if (row_ok) {
-            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ld0 + col);
-            uint4* o1 = reinterpret_cast<uint4*>(p.out1 + (size_t)row * p.ld1 + col);
+          } else {
+            if (EPI == EPI_DGRAD_MUL) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              o0[j] = make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
-              o1[j] = make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+                const uint4 m4 = *reinterpret_cast<const uint4*>(buf0 + row_off + ((c ^ sw) << 4));
+                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 m2 = unpack_h2(mw[q]);
+                  v[8 * j + 2 * q] *= m2.x;
+                  v[8 * j + 2 * q + 1] *= m2.y;
+                }
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
           }
-        } else {
-          if (EPI == EPI_DGRAD_MUL) {
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>(mcur);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 m2 = unpack_h2(mw[i]);
-              v[2 * i] *= m2.x;
-              v[2 * i + 1] *= m2.y;
-            }
+          if (half == 0) {
+            // the previous sub-tile's TMA stores must have finished reading the staging buffers
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
           }
-          uint32_t hd[16];
+          uint8_t* obuf = (EPI == EPI_DGRAD_MUL) ? buf1 : buf0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
-          if (row_ok) {
-            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ld0 + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o0[j] = make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+            *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
+                make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+            if (EPI == EPI_SNAKE)
+              *reinterpret_cast<uint4*>(buf1 + row_off + ((c ^ sw) << 4)) =
+                  make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
           }
           if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && p.colsum != nullptr) {
             // bias gradient of the layer that produced this delta: column sums of the
@@ -360,12 +376,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float2 r = unpack_h2(hd[i]);
-              v[2 * i] = r.x;
-              v[2 * i + 1] = r.y;
+              v[2 * i] = row_ok ? r.x : 0.f;
+              v[2 * i + 1] = row_ok ? r.y : 0.f;
             }
             const float cs = warp_colsum32(v, lane);
-            atomicAdd(p.colsum + col + lane, cs);
+            if (warp_ok) atomicAdd(p.colsum + hcol + lane, cs);
           }
+        }
+        if (EPI == EPI_DGRAD_MUL) {
+          __syncwarp();  // every lane has consumed buf0
+          if (lane == 0 && sub + 1 < BN / EPI_COLS) {
+            mbar_expect_tx(ebar, EPI_BUF_BYTES);
+            tma_load_2d(buf0, &p.tmMul, ebar, col + EPI_COLS, row0);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && warp_ok) {
+          tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
+          if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -374,6 +404,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   }
   gemm_teardown(tmem_base, warp);
 }

@@ -146,6 +146,7 @@ struct NppPlan {
   long long prepared_n = -1;
   std::vector<CUtensorMap> map_a;   // per buffer, box {64,128}: K-major A operand
   std::vector<CUtensorMap> map_mn;  // per buffer, box {64,64}: MN-major wgrad operand
+  std::vector<CUtensorMap> map_ep;  // per buffer, box {64,32}: per-warp epilogue store / load
   std::vector<KmajorParams> fwd_params, dgrad_params;
   WgradParams wg_params;
   std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
@@ -482,12 +483,14 @@ static int prepare(NppPlan* p, long long n) {
   const int nb = (int)p->bufs.size();
   p->map_a.assign(nb, CUtensorMap());
   p->map_mn.assign(nb, CUtensorMap());
+  p->map_ep.assign(nb, CUtensorMap());
   for (int i = 0; i < nb; ++i) {
     const Buf& b = p->bufs[i];
     // rows == n exactly: TMA zero-fills rows >= n, which keeps stale workspace rows out of the
     // row-contraction of the weight-gradient GEMM.
     CKI(make_map(&p->map_a[i], b.ptr, n, b.width, b.width, BM));
     CKI(make_map(&p->map_mn[i], b.ptr, n, b.width, b.width, 64));
+    CKI(make_map(&p->map_ep[i], b.ptr, n, b.width, b.width, 32));
   }
   const int tiles_m = (int)((n + BM - 1) / BM);
   p->fwd_params.clear();
@@ -509,9 +512,11 @@ static int prepare(NppPlan* p, long long n) {
     k.bias = p->params + L.b_off;
     k.out0 = p->bufs[L.buf_h].ptr;
     k.ld0 = L.out;
+    k.tmOut0 = p->map_ep[L.buf_h];
     if (L.act) {
       k.out1 = p->bufs[L.buf_d].ptr;
       k.ld1 = L.out;
+      k.tmOut1 = p->map_ep[L.buf_d];
     }
     p->fwd_params.push_back(k);
   }
@@ -535,9 +540,11 @@ static int prepare(NppPlan* p, long long n) {
     k.tiles_n = P.out / BN;
     k.out0 = p->bufs[P.buf_delta].ptr;
     k.ld0 = P.out;
+    k.tmOut0 = p->map_ep[P.buf_delta];
     if (P.act) {
       k.mul = p->bufs[P.buf_d].ptr;
       k.ldm = P.out;
+      k.tmMul = p->map_ep[P.buf_d];
     }
     k.colsum = p->acc + P.bg_off;
     p->dgrad_params.push_back(k);
@@ -584,10 +591,18 @@ static int launch_kmajor(const KmajorParams& k, int epi, int num_sms, cudaStream
   return 0;
 }
 
-static int run_forward(NppPlan* p, const float* coords, long long n, float* logits, cudaStream_t st) {
+static int run_forward(NppPlan* p, const float* coords, long long n, float* logits, cudaStream_t st, bool with_head = true,
+                       const float* enc_f32 = nullptr) {
   if (!p->params) return fail("npp_plan_bind has not been called");
   CKI(prepare(p, n));
-  {
+  if (enc_f32 != nullptr) {
+    ProfScope ps(p, st, PROF_ENCODE, 1);
+    __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
+    npp_load_encoding_kernel<<<p->num_sms * 8, 256, 0, st>>>(enc_f32, (int)n, p->cfg.topk, p->E,
+                                                             p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
+    CK(cudaGetLastError());
+    ++p->launches;
+  } else {
     ProfScope ps(p, st, PROF_ENCODE, 1);
     const int width = p->E;
     dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
@@ -604,6 +619,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
       ++p->launches;
     }
   }
+  if (!with_head) return 0;
   const Layer& last = p->layers.back();
   ProfScope ps_head(p, st, PROF_HEAD_LOSS, 1);
   npp_head_fwd_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(
@@ -646,7 +662,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_FINALIZE, 3);
-    dim3 grid(64, (unsigned)p->layers.size());
+    dim3 grid(128, (unsigned)p->layers.size());
     npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin, p->partial, p->wg_params.n_splits, p->slab_stride, p->acc,
                                                    amax, p->grads);
     CK(cudaGetLastError());
@@ -809,6 +825,12 @@ int npp_forward(NppPlan* p, const float* coords, int64_t n, float* logits, void*
   return run_forward(p, coords, n, logits, (cudaStream_t)stream);
 }
 
+int npp_forward_encoded(NppPlan* p, const float* enc, int64_t n, float* logits, void* stream) {
+  if (!p || !enc || !logits) return fail("npp_forward_encoded: null argument");
+  p->launches = 0;
+  return run_forward(p, nullptr, n, logits, (cudaStream_t)stream, true, enc);
+}
+
 int npp_backward(NppPlan* p, int64_t n, const float* g, void* stream) {
   if (!p || !g) return fail("npp_backward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -845,16 +867,21 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   if (n_norm <= 0) return fail("n_norm must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
-  CKI(run_forward(p, coords, n, p->logits_buf, st));
   CKI(zero_acc(p, st));
   CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
   {
-  ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
-  npp_mse_kernel<<<128, 256, 0, st>>>(p->logits_buf, target, mask, (int)n, inv_count, nullptr, p->g_buf, loss,
-                                      reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
-  CK(cudaGetLastError());
-  ++p->launches;
+    ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
+    const Layer& last = p->layers.back();
+    int blocks = (int)((n + 7) / 8);
+    if (blocks > p->num_sms * 8) blocks = p->num_sms * 8;
+    npp_head_loss_kernel<<<blocks, 256, 0, st>>>(p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)n,
+                                                 p->params + p->rgb_w_off, p->params + p->rgb_b_off, target, mask,
+                                                 inv_count, p->logits_buf, p->g_buf, loss,
+                                                 reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
+    CK(cudaGetLastError());
+    ++p->launches;
   }
   CKI(run_backward(p, n, p->g_buf, st));
   CKI(run_adam(p, lr, beta1, beta2, eps, step, st));
@@ -956,6 +983,7 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   CK(cudaMalloc(&scratch, (size_t)m * n * sizeof(__half)));
   kp.out0 = scratch;
   kp.ld0 = n;
+  CKI(make_map(&kp.tmOut0, scratch, m, n, n, 32));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -122,6 +122,21 @@ __global__ void npp_encode_f32_kernel(const float* __restrict__ coords, int n, E
   }
 }
 
+// Materialised mode: a caller-supplied fp32 encoding [n, topk*width] (reference layout, e.g. rows gathered
+// from the reference's precomputed table, NPP_completion/train.py:166-181) -> the fp16 operand buffers.
+__global__ void npp_load_encoding_kernel(const float* __restrict__ enc, int n, int topk, int width,
+                                         __half* __restrict__ enc1, int ld1, __half* __restrict__ enca, int lda) {
+  const long long total = (long long)n * topk * width;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / (topk * width);
+    const int c = (int)(idx - row * (topk * width));
+    const __half v = __float2half_rn(enc[idx]);
+    if (c < width) enc1[row * ld1 + c] = v;
+    else enca[row * lda + (c - width)] = v;
+  }
+}
+
 // ------------------------------------------------------------------ RGB head
 // logits = h_P . W_rgb^T + b_rgb   (models/networks.py:94), one warp per row.
 __global__ void __launch_bounds__(256) npp_head_fwd_kernel(const __half* __restrict__ hp, int ld, int width, int n,
@@ -212,6 +227,72 @@ __global__ void __launch_bounds__(256) npp_mse_kernel(const float* __restrict__ 
   }
 }
 
+// Fused RGB head + sigmoid + masked MSE for the train-step path: one warp per row computes the three
+// logits (networks.py:94), lanes 0..2 then apply helpers.py:55-56 and mse_calculator.py:13-27 ('l2').
+__global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __restrict__ hp, int ld, int width, int n,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            const float* __restrict__ target,
+                                                            const float* __restrict__ mask, float inv_count,
+                                                            float* __restrict__ logits, float* __restrict__ g,
+                                                            float* __restrict__ loss, unsigned int* __restrict__ amax_bits) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float lsum = 0.f, lmax = 0.f;
+  for (int row = blockIdx.x * 8 + wib; row < n; row += gridDim.x * 8) {
+    const __half* h = hp + (size_t)row * ld;
+    float a[3] = {0.f, 0.f, 0.f};
+    for (int k = lane * 8; k < width; k += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        const int kk = k + 2 * i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, w[c * width + kk], fmaf(f.y, w[c * width + kk + 1], a[c]));
+      }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[c] += __shfl_xor_sync(0xffffffffu, a[c], s);
+    }
+    if (lane < 3) {
+      const float z = (lane == 0 ? a[0] : (lane == 1 ? a[1] : a[2])) + b[lane];
+      const size_t idx = 3 * (size_t)row + lane;
+      const float yh = 1.0f / (1.0f + expf(-z));
+      const float m = mask ? mask[row] : 1.0f;
+      const float wgt = m + (1.0f - m) * 0.3f;
+      const float d = (yh - target[idx]) * wgt;
+      lsum += d * d;
+      const float gi = 2.0f * d * wgt * inv_count * yh * (1.0f - yh);
+      if (logits) logits[idx] = z;
+      g[idx] = gi;
+      lmax = fmaxf(lmax, fabsf(gi));
+    }
+  }
+  __shared__ float ssum[8], smax[8];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, s);
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, s));
+  }
+  if (lane == 0) {
+    ssum[wib] = lsum;
+    smax[wib] = lmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.f, y = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      x += ssum[i];
+      y = fmaxf(y, smax[i]);
+    }
+    atomicAdd(loss, x * inv_count);
+    atomicMax(amax_bits, __float_as_uint(y));
+  }
+}
+
 // max |g| of an externally supplied gradient (autograd path).
 __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__ g, int total,
                                                        unsigned int* __restrict__ amax_bits) {
@@ -225,7 +306,8 @@ __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__
 
 // Backward of the RGB head: delta_P = (g . W_rgb) * snake'(z_P) * scale (fp16), plus
 // dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
-constexpr int HEAD_BWD_ROWS = 64;
+// Block = 256 threads: thread -> (column pair, row group); rows of a block are split in two groups.
+constexpr int HEAD_BWD_ROWS = 32;
 __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
                                                            const __half* __restrict__ dp, int ld, int width, int n,
                                                            const float* __restrict__ w,
@@ -237,28 +319,49 @@ __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restri
   const float scale = npp_grad_scale(__uint_as_float(*amax_bits));
   const int row0 = blockIdx.x * HEAD_BWD_ROWS;
   const int rows = min(HEAD_BWD_ROWS, n - row0);
-  for (int i = threadIdx.x; i < rows * 3; i += blockDim.x) sg[i] = g[(size_t)row0 * 3 + i];
+  for (int i = threadIdx.x; i < HEAD_BWD_ROWS * 3; i += blockDim.x) sg[i] = i < rows * 3 ? g[(size_t)row0 * 3 + i] : 0.f;
   __syncthreads();
-  for (int k = threadIdx.x; k < width; k += blockDim.x) {
-    const float w0 = w[k], w1 = w[width + k], w2 = w[2 * width + k];
-    float aw0 = 0.f, aw1 = 0.f, aw2 = 0.f, ab = 0.f;
-    for (int r = 0; r < rows; ++r) {
-      const float g0 = sg[3 * r], g1 = sg[3 * r + 1], g2 = sg[3 * r + 2];
-      const size_t off = (size_t)(row0 + r) * ld + k;
-      const float h = __half2float(hp[off]);
-      const float d = __half2float(dp[off]);
-      const float da = fmaf(g0, w0, fmaf(g1, w1, g2 * w2));
-      const __half dh = __float2half_rn(da * d * scale);
-      delta[(size_t)(row0 + r) * ldd + k] = dh;
-      ab += __half2float(dh);
-      aw0 = fmaf(g0, h, aw0);
-      aw1 = fmaf(g1, h, aw1);
-      aw2 = fmaf(g2, h, aw2);
+  const int pairs = width >> 1;            // column pairs
+  const int groups = blockDim.x / 128;     // 2 row groups of 128 threads
+  const int grp = threadIdx.x / 128;
+  const int rper = HEAD_BWD_ROWS / groups;
+  for (int cp = threadIdx.x % 128; cp < pairs; cp += 128) {
+    const int k = 2 * cp;
+    const float2 w0 = make_float2(w[k], w[k + 1]);
+    const float2 w1 = make_float2(w[width + k], w[width + k + 1]);
+    const float2 w2 = make_float2(w[2 * width + k], w[2 * width + k + 1]);
+    float2 aw0 = make_float2(0.f, 0.f), aw1 = aw0, aw2 = aw0, ab = aw0;
+#pragma unroll 8
+    for (int rr = 0; rr < rper; ++rr) {
+      const int r = grp * rper + rr;
+      if (r < rows) {
+        const float g0 = sg[3 * r], g1 = sg[3 * r + 1], g2 = sg[3 * r + 2];
+        const size_t off = (size_t)(row0 + r) * ld + k;
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(hp + off));
+        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(dp + off));
+        const float dax = fmaf(g0, w0.x, fmaf(g1, w1.x, g2 * w2.x));
+        const float day = fmaf(g0, w0.y, fmaf(g1, w1.y, g2 * w2.y));
+        const __half2 dh = __floats2half2_rn(dax * d.x * scale, day * d.y * scale);
+        *reinterpret_cast<__half2*>(delta + (size_t)(row0 + r) * ldd + k) = dh;
+        const float2 df = __half22float2(dh);
+        ab.x += df.x;
+        ab.y += df.y;
+        aw0.x = fmaf(g0, h.x, aw0.x);
+        aw0.y = fmaf(g0, h.y, aw0.y);
+        aw1.x = fmaf(g1, h.x, aw1.x);
+        aw1.y = fmaf(g1, h.y, aw1.y);
+        aw2.x = fmaf(g2, h.x, aw2.x);
+        aw2.y = fmaf(g2, h.y, aw2.y);
+      }
     }
-    atomicAdd(head_acc + k, aw0);
-    atomicAdd(head_acc + width + k, aw1);
-    atomicAdd(head_acc + 2 * width + k, aw2);
-    atomicAdd(bias_acc + k, ab);
+    atomicAdd(head_acc + k, aw0.x);
+    atomicAdd(head_acc + k + 1, aw0.y);
+    atomicAdd(head_acc + width + k, aw1.x);
+    atomicAdd(head_acc + width + k + 1, aw1.y);
+    atomicAdd(head_acc + 2 * width + k, aw2.x);
+    atomicAdd(head_acc + 2 * width + k + 1, aw2.y);
+    atomicAdd(bias_acc + k, ab.x);
+    atomicAdd(bias_acc + k + 1, ab.y);
   }
   if (threadIdx.x < 3) {
     float s = 0.f;
@@ -277,7 +380,8 @@ struct FinalizeLayer {
   int off0, off1;
 };
 
-// grads[w] = (sum over split-K slabs) / scale ; grads[b] = bias_acc / scale
+// grads[w] = (sum over split-K slabs) / scale ; grads[b] = bias_acc / scale.
+// grid = (row groups, layers); each block walks whole rows so the slab reads are coalesced.
 __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLayer* __restrict__ layers,
                                                                 const float* __restrict__ partial, int n_splits,
                                                                 long long slab_stride, const float* __restrict__ bias_acc,
@@ -285,19 +389,18 @@ __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLa
                                                                 float* __restrict__ grads) {
   const FinalizeLayer L = layers[blockIdx.y];
   const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
-  const long long total = (long long)L.out * L.in_ref;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int o = idx / L.in_ref;
-    const int c = idx - (long long)o * L.in_ref;
-    const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
-    const float* p = partial + L.pg_off + (long long)o * L.kpad + pc;
-    float s = 0.f;
-    for (int k = 0; k < n_splits; ++k) s += p[k * slab_stride];
-    grads[L.w_off + idx] = s * inv;
+  for (int o = blockIdx.x; o < L.out; o += gridDim.x) {
+    const float* prow = partial + L.pg_off + (long long)o * L.kpad;
+    float* grow = grads + L.w_off + (long long)o * L.in_ref;
+    for (int c = threadIdx.x; c < L.in_ref; c += blockDim.x) {
+      const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
+      float s = 0.f;
+      for (int k = 0; k < n_splits; ++k) s += prow[k * slab_stride + pc];
+      grow[c] = s * inv;
+    }
   }
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < L.out; o += gridDim.x * blockDim.x)
-    grads[L.b_off + o] = bias_acc[L.bg_off + o] * inv;
+  if (blockIdx.x == 0)
+    for (int o = threadIdx.x; o < L.out; o += blockDim.x) grads[L.b_off + o] = bias_acc[L.bg_off + o] * inv;
 }
 
 __global__ void npp_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {

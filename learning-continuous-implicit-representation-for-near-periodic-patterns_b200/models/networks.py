@@ -1,0 +1,180 @@
+"""NPP_Net / NPP_Net_top1 with the reference constructor and forward signatures (models/networks.py:8-173),
+executed by libnpp_b200 (tcgen05 GEMMs with fused bias / snake epilogues, recomputation-free backward, see
+DESIGN.md).  NPP_Net_light (periodicity search) stays reference PyTorch and is loaded from the reference checkout.
+
+Parameters are ``nn.Parameter`` views into one flat fp32 arena owned by the plan, under the reference's state_dict
+names, so ``model.parameters()``, ``state_dict()`` / ``load_state_dict()`` and foreign optimisers keep working.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401  (re-exported like the reference module)
+
+from .activations import *  # noqa: F401,F403
+from . import embedder as _embedder
+from ._core import Plan, native
+
+
+class _NppFunction(torch.autograd.Function):
+    """coords (or a materialised encoding) -> logits; backward fills the plan's gradient arena and hands autograd
+    views of it.  Activations live in the plan's workspace, so one backward per forward."""
+
+    @staticmethod
+    def forward(ctx, x, net, *params):
+        plan = net._plan_for(x.shape[0])
+        net._sync_if_dirty(params)
+        if x.shape[1] == 2:
+            logits = plan.forward(x)
+        else:
+            logits = plan.forward_encoded(x)
+        net._generation += 1
+        ctx.net, ctx.n, ctx.generation = net, x.shape[0], net._generation
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        net = ctx.net
+        if ctx.generation != net._generation:
+            raise RuntimeError("NPP_Net: the activations of this forward were overwritten by a later forward; "
+                               "call backward() before running the network again")
+        plan = net._plan
+        plan.backward(ctx.n, grad_logits)
+        gv = plan.grad_views()
+        grads = tuple(gv.get(name) for name in net._param_names)
+        return (None, None) + grads
+
+
+class _ArenaLinear(nn.Module):
+    """Parameter holder with nn.Linear's attribute names; the tensors are views into the plan arena."""
+
+    def __init__(self, weight, bias):
+        super().__init__()
+        self.weight = nn.Parameter(weight)
+        self.bias = nn.Parameter(bias)
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+    def forward(self, x):  # only used for the unused alpha_linear / debugging
+        return F.linear(x, self.weight, self.bias)
+
+
+class _FusedNet(nn.Module):
+    def _build(self, topk_model, D, W, skips, activation, output_ch, reference_order):
+        if activation != 'snake':
+            raise NotImplementedError("the B200 path implements activation='snake' (the reference default, "
+                                      "options/arg_config.py:29); relu is not built")
+        if output_ch != 3 or len(skips) != 1:
+            raise NotImplementedError("output_ch=3 and a single skip connection are required")
+        self.D, self.W, self.skips = D, W, skips
+        spec = _embedder.current_encoder_spec()
+        if (spec.topk > 1) != topk_model:
+            raise ValueError("number of registered proposals does not match the network class")
+        self._spec = spec
+        self._plan = Plan(spec, depth=D, width=W, skip_layer=skips[0], max_rows=1 << 15)
+        self._generation = 0
+        views = self._plan.param_views()
+        # Initialise exactly like the reference: construct nn.Linear modules in the reference's order
+        # (networks.py:42-49 / 127-138) so a given torch seed yields the same weights, then copy.
+        for name, (out_f, in_f) in reference_order:
+            lin = nn.Linear(in_f, out_f)
+            views[name + ".weight"].copy_(lin.weight.detach())
+            views[name + ".bias"].copy_(lin.bias.detach())
+        self._plan.sync_weights()
+
+        def holder(name):
+            return _ArenaLinear(views[name + ".weight"], views[name + ".bias"])
+
+        self.periodic_linears = nn.ModuleList([holder(f"periodic_linears.{i}") for i in range(D)])
+        if topk_model:
+            self.scale_linears = nn.ModuleList([holder("scale_linears.0")])
+        self.pos_linears = nn.ModuleList([holder("pos_linears.0")])
+        self.feature_linear1 = holder("feature_linear1")
+        self.feature_linear2 = holder("feature_linear2")
+        self.alpha_linear = holder("alpha_linear")
+        self.rgb_linear = holder("rgb_linear")
+        self.snakes = SnakeActivation()
+        named = dict(self.named_parameters())
+        self._param_names = list(named.keys())
+        self._params = [named[k] for k in self._param_names]
+        self._versions = None
+
+    # --------------------------------------------------------------------------------------------
+    def _plan_for(self, n):
+        if n > self._plan.max_rows:
+            old = self._plan
+            cap = 1 << (int(n) - 1).bit_length()
+            self._plan = Plan(self._spec, depth=self.D, width=self.W, skip_layer=self.skips[0], max_rows=cap,
+                              arenas=(old.params, old.grads, old.exp_avg, old.exp_avg_sq))
+            self._plan.adam_steps = old.adam_steps
+            self._plan.sync_weights()
+            old.close()
+        return self._plan
+
+    def _sync_if_dirty(self, params):
+        """Refresh the fp16 shadow weights if anyone but the fused optimiser wrote the fp32 parameters."""
+        versions = tuple(p._version for p in params)
+        if versions != self._versions:
+            self._plan.sync_weights()
+            self._versions = versions
+
+    def mark_clean(self):
+        self._versions = tuple(p._version for p in self._params)
+
+    def _apply(self, fn, *a, **k):
+        before = self._plan.params.data_ptr()
+        out = super()._apply(fn, *a, **k)
+        if any(p.device != self._plan.device or p.dtype != torch.float32 for p in self._params) or \
+                self._plan.params.data_ptr() != before:
+            raise RuntimeError("NPP_Net parameters live in a CUDA fp32 arena and cannot be moved or cast")
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._plan.sync_weights()
+        self.mark_clean()
+        return out
+
+    def forward(self, x, x_periodic):
+        """x is ignored (None) exactly like the reference; x_periodic is either [N,2] coordinates ('coords' embed
+        mode) or the materialised [N, K*462] encoding."""
+        if x_periodic.shape[1] not in (2, self._plan.encoding_width):
+            raise AssertionError(f"x_periodic has {x_periodic.shape[1]} columns; expected 2 (coordinates) or "
+                                 f"{self._plan.encoding_width} (materialised encoding)")
+        if x_periodic.shape[0] == 0:
+            return x_periodic.new_zeros((0, 3))
+        return _NppFunction.apply(x_periodic.float(), self, *self._params)
+
+
+class NPP_Net(_FusedNet):
+    def __init__(self, input_ch_periodic, input_ch_periodic_aux, freq_scales, freq_offsets, angle_offsets, D=8, W=256,
+                 freq_nerf=3, output_ch=3, skips=[4], activation='relu'):
+        super().__init__()
+        self.scale, self.offset, self.angle_offset = len(freq_scales), len(freq_offsets), len(angle_offsets)
+        ch = int(input_ch_periodic) * freq_nerf
+        aux = int(input_ch_periodic_aux) * freq_nerf
+        self.input_ch_periodic, self.input_ch_periodic_aux = ch, aux
+        order = [(f"periodic_linears.{i}", (W, ch if i == 0 else (W + ch if (i - 1) in skips else W))) for i in range(D)]
+        order += [("scale_linears.0", (W, aux + W)), ("pos_linears.0", (W // 2, 2 * W)),
+                  ("feature_linear1", (W, W)), ("feature_linear2", (W, W)), ("alpha_linear", (1, W)),
+                  ("rgb_linear", (output_ch, W // 2))]
+        self._build(True, D, W, list(skips), activation, output_ch, order)
+        assert self._plan.encoding_width == ch + aux, "embedder widths do not match input_ch_periodic(_aux)"
+
+
+class NPP_Net_top1(_FusedNet):
+    def __init__(self, input_ch_periodic, freq_scales, freq_offsets, angle_offsets, D=8, W=256, freq_nerf=3,
+                 output_ch=3, skips=[4], activation='relu'):
+        super().__init__()
+        self.scale, self.offset, self.angle_offset = len(freq_scales), len(freq_offsets), len(angle_offsets)
+        ch = int(input_ch_periodic) * freq_nerf
+        self.input_ch_periodic = ch
+        order = [(f"periodic_linears.{i}", (W, ch if i == 0 else (W + ch if (i - 1) in skips else W))) for i in range(D)]
+        order += [("pos_linears.0", (W // 2, W)), ("feature_linear1", (W, W)), ("feature_linear2", (W, W)),
+                  ("alpha_linear", (1, W)), ("rgb_linear", (output_ch, W // 2))]
+        self._build(False, D, W, list(skips), activation, output_ch, order)
+        assert self._plan.encoding_width == ch
+
+
+def __getattr__(name):
+    if name == "NPP_Net_light":      # periodicity search stays reference PyTorch
+        from ._reference import reference_module
+        return reference_module("networks").NPP_Net_light
+    raise AttributeError(name)

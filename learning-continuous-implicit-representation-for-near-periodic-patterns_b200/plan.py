@@ -89,7 +89,7 @@ class Plan:
     """One fused NPP-Net instance on the current CUDA device."""
 
     def __init__(self, enc: EncoderSpec, *, depth: int = 8, width: int = 512, skip_layer: int = 4,
-                 max_rows: int = 1 << 16, wgrad_splits: int = 0, training: bool = True):
+                 max_rows: int = 1 << 16, wgrad_splits: int = 0, training: bool = True, arenas=None):
         if not torch.cuda.is_available():
             raise nat.NppError("npp_b200 needs a CUDA device (B200, sm_100); there is no CPU fallback")
         self.lib = nat.lib()
@@ -125,10 +125,14 @@ class Plan:
             nat.check(self.lib.npp_plan_tensor_info(handle, i, C.byref(info)))
             shape = (info.cols,) if info.is_bias else (info.rows, info.cols)
             self.slots.append(TensorSlot(info.name.decode(), info.offset, shape, bool(info.trained)))
-        self.params = torch.zeros(self.arena_floats, device=self.device)
-        self.grads = torch.zeros(self.arena_floats, device=self.device) if training else None
-        self.exp_avg = torch.zeros(self.arena_floats, device=self.device) if training else None
-        self.exp_avg_sq = torch.zeros(self.arena_floats, device=self.device) if training else None
+        if arenas is not None:      # re-plan with a larger workspace around existing parameters / Adam state
+            self.params, self.grads, self.exp_avg, self.exp_avg_sq = arenas
+            assert self.params.numel() == self.arena_floats
+        else:
+            self.params = torch.zeros(self.arena_floats, device=self.device)
+            self.grads = torch.zeros(self.arena_floats, device=self.device) if training else None
+            self.exp_avg = torch.zeros(self.arena_floats, device=self.device) if training else None
+            self.exp_avg_sq = torch.zeros(self.arena_floats, device=self.device) if training else None
         nat.check(self.lib.npp_plan_bind(handle, nat.ptr(self.params), nat.ptr(self.grads),
                                          nat.ptr(self.exp_avg), nat.ptr(self.exp_avg_sq)))
         self.encoding_width = self.lib.npp_plan_encoding_width(handle)
@@ -214,6 +218,19 @@ class Plan:
         logits = torch.empty(c.shape[0], 3, device=self.device)
         if c.shape[0]:
             nat.check(self.lib.npp_forward(self.handle, c.data_ptr(), c.shape[0], logits.data_ptr(), nat.current_stream()))
+        return logits
+
+    def forward_encoded(self, enc: torch.Tensor) -> torch.Tensor:
+        """Forward on a materialised [N, K*462] fp32 encoding (reference layout)."""
+        e = enc.to(self.device, torch.float32).contiguous()
+        if e.dim() != 2 or e.shape[1] != self.encoding_width:
+            raise ValueError(f"encoding must be [N,{self.encoding_width}], got {tuple(e.shape)}")
+        if e.shape[0] > self.max_rows:
+            raise ValueError(f"{e.shape[0]} rows exceed the plan capacity max_rows={self.max_rows}")
+        logits = torch.empty(e.shape[0], 3, device=self.device)
+        if e.shape[0]:
+            nat.check(self.lib.npp_forward_encoded(self.handle, e.data_ptr(), e.shape[0], logits.data_ptr(),
+                                                   nat.current_stream()))
         return logits
 
     def backward(self, n: int, grad_logits: torch.Tensor):

@@ -1,0 +1,164 @@
+"""The reference's train-loop body (NPP_completion/train.py:93-105,164-195,253-263) run on the drop-in ``models``
+package and checked step by step against the CPU oracle started from the same weights."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import npp_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "learning-continuous-implicit-representation-for-near-periodic-patterns_b200")
+
+EXPECTED_KEYS_TOPK = sorted(
+    [f"periodic_linears.{i}.{s}" for i in range(8) for s in ("weight", "bias")] +
+    [f"{m}.{s}" for m in ("scale_linears.0", "pos_linears.0", "feature_linear1", "feature_linear2", "alpha_linear",
+                          "rgb_linear") for s in ("weight", "bias")])
+
+
+def _args(topk):
+    return argparse.Namespace(multires=10, i_embed=0, p_topk=topk, freq_scales=[1], freq_offsets=[0, -1, 1, 0.5, -0.5],
+                              angle_offsets=[0], netdepth=8, netwidth=512, activation='snake', netchunk=1024 * 4096,
+                              lrate=5e-4, lrate_decay=500, normalize_type=1, loss_type='l2')
+
+
+@pytest.mark.parametrize("topk", [3, 1])
+def test_train_loop_on_dropin_models(topk, monkeypatch):
+    monkeypatch.delenv("NPP_B200_EMBED", raising=False)
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net, render
+    from models.mse_calculator import img2mse
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    dev = torch.device("cuda")
+    res = (96, 128)
+    args = _args(topk)
+    angles = torch.Tensor([[83.0, 172.5], [90.0, 180.0], [41.3, 127.9]])[:topk]
+    periods = torch.Tensor([[17.2, 14.9], [8.6, 7.45], [34.4, 29.8]])[:topk]
+    kw, _, start, grad_vars, optimizer, embedder, embedder_periodic = create_npp_net(args, angles, periods, res, None)
+    model = kw['network_fn']
+    assert sorted(model.state_dict().keys()) == (EXPECTED_KEYS_TOPK if topk > 1 else
+                                                 [k for k in EXPECTED_KEYS_TOPK if not k.startswith("scale_linears")])
+    assert sum(p.numel() for p in model.parameters()) == (3836932 if topk > 1 else 2970116)
+
+    # oracle twin from the same initial weights and encoder constants
+    p = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    tabs = [(e.cos_t, e.sin_t, e.period) for e in embedder_periodic]
+    freqs = embedder.freqs
+
+    # "table build" exactly as the script does it -- in coords mode it is just the coordinates
+    img = torch.rand(1, res[0], res[1], 3, device=dev)
+    h, w = torch.meshgrid(torch.arange(0, res[0]), torch.arange(0, res[1]), indexing="ij")
+    i_all = torch.stack([h, w], dim=-1).reshape(-1, 2).float().to(dev)
+    i_train = i_all[torch.randperm(i_all.shape[0], device=dev)[:6000]]
+    embs = []
+    for i in range(args.p_topk):
+        embs.append(embedder.embed(embedder_periodic[i].embed(i_train.clone())))
+    i_train_emb = torch.cat(embs, 1)
+    assert i_train_emb.shape == (6000, 2)
+
+    N_rand = 2048
+    global_step = start
+    for it in range(1, 7):
+        select_inds = np.random.choice(i_train.shape[0], size=[N_rand], replace=False)
+        select_coords = i_train[select_inds].long()
+        gt_rgb = img[0, select_coords[:, 0], select_coords[:, 1], :]
+        gt_mask = torch.ones_like(gt_rgb[:, :1])
+        pred_rgb = render(None, i_train_emb[select_inds], args, **kw)
+        optimizer.zero_grad()
+        loss = img2mse(pred_rgb, gt_rgb, args.loss_type, None, gt_mask)
+        loss.backward()
+        optimizer.step()
+        new_lrate = args.lrate * (0.1 ** (global_step / (args.lrate_decay * 100)))
+        for g in optimizer.param_groups:
+            g['lr'] = new_lrate
+        global_step += 1
+        enc = O.encode(select_coords.float().cpu().numpy(), tabs, freqs, res)
+        ref_loss, _ = O.train_step(p, m, v, it, enc, gt_rgb.cpu().numpy(), gt_mask.cpu().numpy(), O.lr_schedule(it),
+                                   topk_model=topk > 1)
+        assert abs(loss.item() - ref_loss) < 1e-3 * ref_loss, (it, loss.item(), ref_loss)
+    sd = model.state_dict()
+    for k in p:
+        assert np.abs(sd[k].cpu().numpy() - p[k]).max() < 1e-3, k
+
+    # chunked no-grad inference like the i_testset branch (train.py:277-309)
+    with torch.no_grad():
+        out = torch.cat([render(None, i_all[j:j + 5000], args, **kw) for j in range(0, i_all.shape[0], 5000)])
+    assert out.shape == (res[0] * res[1], 3) and torch.isfinite(out).all()
+
+
+def test_table_mode_matches_coords_mode(monkeypatch):
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net, render
+    torch.manual_seed(0)
+    res = (64, 80)
+    args = _args(3)
+    angles = torch.Tensor([[83.0, 172.5], [90.0, 180.0], [41.3, 127.9]])
+    periods = torch.Tensor([[17.2, 14.9], [8.6, 7.45], [34.4, 29.8]])
+    kw, _, _, _, _, embedder, per = create_npp_net(args, angles, periods, res, None)
+    coords = torch.stack([torch.randint(0, res[0], (500,)), torch.randint(0, res[1], (500,))], 1).float().cuda()
+    monkeypatch.setenv("NPP_B200_EMBED", "coords")
+    with torch.no_grad():
+        a = render(None, torch.cat([embedder.embed(e.embed(coords.clone())) for e in per], 1), args, **kw)
+    monkeypatch.setenv("NPP_B200_EMBED", "table")
+    table = torch.cat([embedder.embed(e.embed(coords.clone())) for e in per], 1)
+    assert table.shape == (500, 1386)
+    tabs = [(e.cos_t, e.sin_t, e.period) for e in per]
+    np.testing.assert_allclose(table.cpu().numpy(), O.encode(coords.cpu().numpy(), tabs, embedder.freqs, res), atol=5e-5)
+    with torch.no_grad():
+        b = render(None, table, args, **kw)
+    assert (a - b).abs().max().item() < 2e-3
+
+
+def test_foreign_parameters_and_external_weight_edit():
+    """Adam over a mixed list (our arena + foreign tiny parameters, models/helpers.py:144-151) and shadow-weight
+    refresh after someone edits the fp32 parameters in place."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net, render
+
+    class Adaptive(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.latent = torch.nn.Parameter(torch.zeros(1, 3, device="cuda"))
+
+    class Percep:
+        adaptive_perceps = [Adaptive()]
+
+    torch.manual_seed(0)
+    args = _args(1)
+    args.use_adaptive_perceptual_loss = True
+    res = (64, 64)
+    kw, _, _, grad_vars, opt, embedder, per = create_npp_net(args, torch.Tensor([[90.0, 180.0]]),
+                                                            torch.Tensor([[12.0, 11.0]]), res, Percep())
+    foreign = Percep.adaptive_perceps[0].latent
+    assert any(g is foreign for g in grad_vars)
+    coords = torch.stack([torch.randint(0, 64, (256,)), torch.randint(0, 64, (256,))], 1).float().cuda()
+    pred = render(None, coords, args, **kw)
+    loss = ((pred - 0.5) ** 2).mean() + (foreign ** 2).sum() + foreign.sum()
+    opt.zero_grad()
+    loss.backward()
+    w_before = kw['network_fn'].rgb_linear.weight.detach().clone()
+    opt.step()
+    assert (foreign.detach().abs() > 0).all()                       # foreign parameter moved
+    assert not torch.equal(w_before, kw['network_fn'].rgb_linear.weight.detach())
+    # external in-place edit -> next forward must see it
+    with torch.no_grad():
+        out1 = render(None, coords, args, **kw)
+        kw['network_fn'].rgb_linear.bias.add_(1.0)
+        out2 = render(None, coords, args, **kw)
+    assert (out2 > out1).all()
+    # double forward then backward of the stale graph is rejected
+    a = render(None, coords, args, **kw)
+    _ = render(None, coords, args, **kw)
+    with pytest.raises(RuntimeError):
+        a.sum().backward()
