@@ -136,6 +136,8 @@ float npp_debug_grad_scale(NppPlan* plan, void* stream); /* synchronises */
  * C[m,n] = A[rows,m]^T . B[rows,n] summed over `splits` row ranges. Dimensions: m%128==0 not required
  * for the first (rows are masked), n%256==0, k%64==0. */
 int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, void* stream);
+int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, int m, int n, int k, int epi,
+                         int iters, float* ms_out);
 int npp_debug_wgrad(const void* a, const void* b, float* c_partials, int rows, int m, int n, int splits,
                     void* stream);
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "npp_debug_copy": (C.c_int, [_P, C.c_char_p, C.c_int64, _P, _P]),
     "npp_debug_grad_scale": (C.c_float, [_P, _P]),
     "npp_debug_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "npp_debug_gemm_bench": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "npp_debug_wgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 

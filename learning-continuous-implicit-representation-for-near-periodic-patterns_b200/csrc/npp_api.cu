@@ -995,6 +995,43 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   return 0;
 }
 
+// Times `iters` back-to-back launches of the K-major GEMM (epi 0 linear / 1 snake) with CUDA events.
+int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, int m, int n, int k, int epi, int iters,
+                         float* ms_out) {
+  if (n % BN != 0 || k % BK != 0) return fail("npp_debug_gemm_bench: n % 256 == 0 and k % 64 == 0 required");
+  KmajorParams kp;
+  memset(&kp, 0, sizeof(kp));
+  CKI(make_map(&kp.tmA[0], a, m, k, k, BM));
+  CKI(make_map(&kp.tmB[0], b, n, k, k, 256));
+  CKI(make_map(&kp.tmOut0, out0, m, n, n, 32));
+  if (out1) CKI(make_map(&kp.tmOut1, out1, m, n, n, 32));
+  kp.nseg = 1;
+  kp.kblocks[0] = k / BK;
+  kp.M = m;
+  kp.tiles_m = (m + BM - 1) / BM;
+  kp.tiles_n = n / BN;
+  kp.out0 = (__half*)out0;
+  kp.ld0 = n;
+  kp.out1 = (__half*)out1;
+  kp.ld1 = n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* e = getenv("NPP_DEBUG_GRID")) sms = atoi(e);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) CKI(launch_kmajor(kp, epi ? EPI_SNAKE : EPI_LINEAR, sms, 0));
+  CK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) CKI(launch_kmajor(kp, epi ? EPI_SNAKE : EPI_LINEAR, sms, 0));
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(ms_out, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
 int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int n, int splits, void* stream) {
   if (m % BM != 0 || n % BN != 0 || splits < 1) return fail("npp_debug_wgrad: m % 128 == 0, n % 256 == 0 required");
   CKI(set_smem_attrs());

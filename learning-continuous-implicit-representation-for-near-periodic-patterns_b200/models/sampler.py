@@ -1,0 +1,212 @@
+"""GridPatchSampler with the reference surface (models/sampler.py:8-354), rebuilt around integer index math.
+
+Behavioural contract kept from the reference (checked bit-exactly against it in tests/test_sampler_parity.py):
+  * numpy RNG consumption order: one np.random.uniform per sample_patches call, then one
+    np.random.choice(pool, N_samples, replace=False) for the fake-patch centroids (sampler.py:260-261,324),
+    plus one np.random.choice over the valid unfold patches when no_reg_sampling is set (sampler.py:229);
+  * candidate real centroids = fake centroid + i*shift1 + j*shift2, i,j in [-10,10), top-1 proposal only,
+    (x,y)->(row,col) swapped (sampler.py:32-35,89-94,149-153), filtered by image bounds and by the unknown-pixel
+    ratio, ranked by |i|+|j| with torch.topk on the same tensor the reference builds (same tie-breaking);
+  * crops are extract_glimpse(mode='nearest', normalized=False, centered=False), which for integer centroids is
+    img[c-ps/2 : c+ps/2] with zero padding (utils/extract_glimpse.py:7-79).
+
+What changed: the reference tiles the full image once per candidate (up to N_samples*400 copies,
+sampler.py:171-178) and materialises every stride-ps/10 unfold patch (sampler.py:66-84).  Here the unknown-pixel
+count of any window comes from a summed-area table in O(1) and only the patches that are returned are cropped.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F  # noqa: F401  (re-exported like the reference module)
+
+
+def extract_glimpse(input, size, offsets, centered=False, normalized=False, mode='nearest', padding_mode='zeros'):
+    """Nearest-neighbour glimpse for pixel offsets (x, y) = window centre; the only configuration the sampler uses
+    (utils/extract_glimpse.py with mode='nearest', normalized=False, centered=False, padding_mode='zeros')."""
+    if centered or normalized or mode != 'nearest' or padding_mode != 'zeros':
+        raise NotImplementedError("only the sampler's configuration is implemented")
+    h, w = size
+    # sample i of a window of even size s centred at c reads pixel nearbyint(c - s/2 + i)
+    c0 = torch.round(offsets[:, 0].float() - w / 2).long()
+    r0 = torch.round(offsets[:, 1].float() - h / 2).long()
+    if input.shape[0] not in (1, offsets.shape[0]):
+        raise ValueError("batch size must be 1 or match the number of offsets")
+    return _crop(input[:1], r0, c0, h, w)
+
+
+def _crop(img_nchw, r0, c0, h, w):
+    """img [1,C,H,W]; windows with top-left (r0[i], c0[i]) -> [M,C,h,w], zero padded outside the image."""
+    _, C, H, W = img_nchw.shape
+    dev = img_nchw.device
+    rows = r0.to(dev)[:, None] + torch.arange(h, device=dev)[None, :]          # [M,h]
+    cols = c0.to(dev)[:, None] + torch.arange(w, device=dev)[None, :]          # [M,w]
+    ok = ((rows >= 0) & (rows < H))[:, :, None] & ((cols >= 0) & (cols < W))[:, None, :]
+    out = img_nchw[0][:, rows.clamp(0, H - 1)[:, :, None], cols.clamp(0, W - 1)[:, None, :]]   # [C,M,h,w]
+    return (out * ok[None].to(out.dtype)).permute(1, 0, 2, 3).contiguous()
+
+
+class _UnknownCounter:
+    """Summed-area table of (mask < 0.5); pixels outside the image count as unknown (zero padding)."""
+
+    def __init__(self, mask_hw):
+        unk = (mask_hw < 0.5).to(torch.int64)
+        self.H, self.W = unk.shape
+        sat = torch.zeros(self.H + 1, self.W + 1, dtype=torch.int64, device=unk.device)
+        sat[1:, 1:] = unk.cumsum(0).cumsum(1)
+        self.sat = sat
+
+    def count(self, r0, c0, h, w):
+        ra, rb = r0.clamp(0, self.H), (r0 + h).clamp(0, self.H)
+        ca, cb = c0.clamp(0, self.W), (c0 + w).clamp(0, self.W)
+        inside = self.sat[rb, cb] - self.sat[ra, cb] - self.sat[rb, ca] + self.sat[ra, ca]
+        area = (rb - ra) * (cb - ca)
+        return inside + (h * w - area)
+
+
+class GridPatchSampler():
+    def __init__(self, img, mask, N_samples, patch_size, height, width, pool_train, pool_val, selected_shifts,
+                 no_reg_sampling):
+        self.N_samples = int(N_samples)
+        self.height, self.width = height, width
+        self.device = img.device
+        self.img, self.mask = img.permute(0, 3, 1, 2), mask.permute(0, 3, 1, 2)
+        self._mask_counter = _UnknownCounter(self.mask[0, 0])
+        # only the top-1 periodicity is used for sampling; first coordinate along the vertical direction
+        selected_shifts = selected_shifts[0]
+        self.selected_shifts = [torch.tensor([s[1], s[0]]) for s in selected_shifts]
+        self.no_reg_sampling = no_reg_sampling
+        self.coord_patches = None
+        self.reset_patchsize(img, mask, patch_size, N_samples)
+        self.reset_pool(pool_train, pool_val)
+
+    # ------------------------------------------------------------------------------------------
+    def reset_patchsize(self, img, mask, patch_size, N_samples, ratio=0.0):
+        self.N_samples = N_samples
+        self.patch_size_h_half, self.patch_size_w_half = patch_size // 2, patch_size // 2
+        self._patch_size = patch_size
+        # valid positions of the stride-(patch_size//10) unfold grid (random strategy, sampler.py:66-84)
+        self._unfold_img = img.permute(0, 3, 1, 2)
+        self._unfold_mask = mask.permute(0, 3, 1, 2)
+        stride = max(patch_size // 10, 1)
+        H, W = mask.shape[1], mask.shape[2]
+        ys = torch.arange(0, H - patch_size + 1, stride, device=self.device)
+        xs = torch.arange(0, W - patch_size + 1, stride, device=self.device)
+        if len(ys) and len(xs):
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            cnt = _UnknownCounter(self._unfold_mask[0, 0]).count(yy.reshape(-1), xx.reshape(-1), patch_size, patch_size)
+            keep = ~(cnt > (patch_size ** 2 * ratio))
+            self._unfold_r0, self._unfold_c0 = yy.reshape(-1)[keep], xx.reshape(-1)[keep]
+        else:
+            self._unfold_r0 = self._unfold_c0 = torch.zeros(0, dtype=torch.int64, device=self.device)
+        self.coord_patches = True
+
+        self.max_shifting_ind = 10
+        r = torch.arange(-self.max_shifting_ind, self.max_shifting_ind, device=self.device)
+        self.permutation1, self.permutation2 = torch.meshgrid(r, r, indexing="ij")
+        self.permute_distance = (abs(self.permutation1) + abs(self.permutation2)).reshape(-1).tile(self.N_samples)
+        n_perm = (2 * self.max_shifting_ind) ** 2
+        self.coord_batch_indicator = torch.arange(self.N_samples, device=self.device).repeat_interleave(n_perm)
+
+    def reset_pool(self, pool_train, pool_val):
+        def _get_valid_centroid(pool):
+            pool = pool.to(self.device)
+            valid = (pool[:, 0] > self.patch_size_h_half) & (pool[:, 0] < self.height - (self.patch_size_h_half + 1)) & \
+                    (pool[:, 1] > self.patch_size_w_half) & (pool[:, 1] < self.width - (self.patch_size_w_half + 1))
+            return pool[valid]
+
+        self.pool_train = _get_valid_centroid(pool_train)
+        self.pool_val = _get_valid_centroid(pool_val)
+
+    # ------------------------------------------------------------------------------------------
+    def sample_patch_real(self, fake_coords=None, topk=5, invalid_ratio=0.3):
+        hh, wh = self.patch_size_h_half, self.patch_size_w_half
+        if fake_coords is not None and not self.no_reg_sampling:
+            N = fake_coords.shape[0]
+            cent = fake_coords[:, hh, wh, :].to(self.device)                                  # [N,2] (row, col)
+            s1, s2 = (s.to(self.device) for s in self.selected_shifts)
+            total = s1[None, None, :] * self.permutation1[..., None] + s2[None, None, :] * self.permutation2[..., None]
+            pool = (cent[:, None, None, :] + total[None]).reshape(-1, 2)                       # (sample, i, j) order
+            in_bound = (pool[:, 0] > 0) & (pool[:, 0] < self.height - 1) & (pool[:, 1] > 0) & (pool[:, 1] < self.width - 1)
+            pool = pool[in_bound]
+            indicator = self.coord_batch_indicator[:N * total.shape[0] * total.shape[1]][in_bound]
+            distance_all = self.permute_distance[:N * total.shape[0] * total.shape[1]][in_bound]
+            r0 = torch.round(pool[:, 0].float() - hh).long()
+            c0 = torch.round(pool[:, 1].float() - wh).long()
+            unknown = self._mask_counter.count(r0, c0, 2 * hh, 2 * wh)
+            keep = ~(unknown > (hh * wh * 4 * invalid_ratio))
+            r0, c0, indicator, distance_all = r0[keep], c0[keep], indicator[keep], distance_all[keep]
+
+            sel_r0, sel_c0, weight_topks = [], [], []
+            topk_min = topk
+            for i in range(self.N_samples):
+                inds = indicator == i
+                distance = distance_all[inds]
+                distance[distance == 0] = 10000            # the patch itself is never its own reference
+                if min(len(distance) - 1, topk) < topk_min:
+                    topk_min = min(len(distance) - 1, topk)
+                    if topk_min <= 0:
+                        return None, None, None, 0
+                distance_topk, inds_topk = torch.topk(distance, k=topk_min, largest=False)
+                distance_topk = 1 / distance_topk
+                weight_topks.append(distance_topk / torch.sum(distance_topk))
+                sel_r0.append(r0[inds][inds_topk])
+                sel_c0.append(c0[inds][inds_topk])
+            if topk_min < topk:
+                weight_topks = [w[:topk_min] for w in weight_topks]
+                sel_r0 = [r[:topk_min] for r in sel_r0]
+                sel_c0 = [c[:topk_min] for c in sel_c0]
+            weight_topks = torch.cat(weight_topks)
+            r0s, c0s = torch.cat(sel_r0), torch.cat(sel_c0)
+            select_img_patches = _crop(self.img, r0s, c0s, 2 * hh, 2 * wh).reshape(self.N_samples, topk_min, 3, 2 * hh, 2 * wh)
+            select_mask_patches = _crop(self.mask, r0s, c0s, 2 * hh, 2 * wh).reshape(self.N_samples, topk_min, 1, 2 * hh, 2 * wh)
+        else:
+            ps = self._patch_size
+            select_inds = np.random.choice(self._unfold_r0.shape[0], size=[self.N_samples * topk], replace=False)
+            sel = torch.as_tensor(select_inds, device=self.device)
+            r0s, c0s = self._unfold_r0[sel], self._unfold_c0[sel]
+            select_img_patches = _crop(self._unfold_img, r0s, c0s, ps, ps).reshape(self.N_samples, topk, 3, ps, ps)
+            select_mask_patches = _crop(self._unfold_mask, r0s, c0s, ps, ps).reshape(self.N_samples, topk, 1, ps, ps)
+            weight_topks, topk_min = None, topk
+
+        select_img_patches = select_img_patches.permute(0, 1, 3, 4, 2)
+        select_mask_patches = select_mask_patches.permute(0, 1, 3, 4, 2)
+        return select_img_patches, select_mask_patches, weight_topks, topk_min
+
+    def sample_patch_fake(self, mode):
+        pool = self.pool_train if mode == 'train' else self.pool_val
+        hh, wh = self.patch_size_h_half, self.patch_size_w_half
+        select_inds = np.random.choice(pool.shape[0], size=[self.N_samples], replace=False)
+        select_centroid = pool[torch.as_tensor(select_inds, device=pool.device)]
+        cent = select_centroid.long()                       # int(left_h) of the reference truncates the same way
+        r0, c0 = cent[:, 0] - hh, cent[:, 1] - wh
+        rows = r0[:, None] + torch.arange(2 * hh, device=self.device)[None, :]
+        cols = c0[:, None] + torch.arange(2 * wh, device=self.device)[None, :]
+        select_patch_grids = torch.stack([rows[:, :, None].expand(-1, -1, 2 * wh),
+                                          cols[:, None, :].expand(-1, 2 * hh, -1)], dim=-1)
+        # glimpses are taken at the (possibly fractional) centroid like the reference does
+        off = select_centroid.flip((1,))
+        select_patch = extract_glimpse(self.img, (2 * hh, 2 * wh), off)
+        select_patch_mask = extract_glimpse(self.mask, (2 * hh, 2 * wh), off)
+        return select_patch, select_patch_mask, select_patch_grids
+
+    def sample_patches(self, topk, invalid_ratio):
+        prob = np.random.uniform(0, 1)
+        if prob < 0.5:
+            patch_source = 'val'
+            fake, fake_mask, coords = self.sample_patch_fake('val')
+            real, real_mask, weight_topk, topk = self.sample_patch_real(coords, topk=topk, invalid_ratio=invalid_ratio)
+        elif prob > 0.5 and prob < 0.8:
+            patch_source = 'train'
+            fake, fake_mask, coords = self.sample_patch_fake('train')
+            real, real_mask, weight_topk, topk = self.sample_patch_real(coords, topk=topk, invalid_ratio=invalid_ratio)
+        else:
+            fake, fake_mask, coords = self.sample_patch_fake('train')
+            real, real_mask = fake.clone().permute(0, 2, 3, 1)[:, None], fake_mask.clone().permute(0, 2, 3, 1)[:, None]
+            patch_source = 'same'
+            topk = 1
+            weight_topk = torch.ones(self.N_samples, dtype=torch.float32, device=self.device)
+        if topk == 0:
+            return None, None, None, None, None, None, topk, None
+        if fake_mask is not None:
+            fake = fake[:, None].tile([1, topk, 1, 1, 1])
+            fake_mask = fake_mask[:, None].tile([1, topk, 1, 1, 1])
+        return real, real_mask, fake, fake_mask, coords, patch_source, topk, weight_topk
