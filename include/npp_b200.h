@@ -114,6 +114,10 @@ int npp_train_step(NppPlan* plan, const float* coords, const float* target, cons
                    int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
                    void* stream);
 
+/* By default npp_train_step goes straight from the split-K slabs to the Adam update and never writes the
+ * gradient arena; turn this on to have it written as well (tests, gradient inspection). */
+int npp_set_keep_grads(NppPlan* plan, int on);
+
 /* Number of kernels the last npp_train_step / forward / backward call launched. */
 int npp_last_launch_count(const NppPlan* plan);
 

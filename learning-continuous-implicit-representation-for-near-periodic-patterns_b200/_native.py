@@ -65,6 +65,7 @@ SIGNATURES = {
     "npp_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "npp_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, _P, _P]),
+    "npp_set_keep_grads": (C.c_int, [_P, C.c_int]),
     "npp_last_launch_count": (C.c_int, [_P]),
     "npp_profile_enable": (C.c_int, [_P, C.c_int]),
     "npp_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -134,11 +134,13 @@ struct NppPlan {
   float* logits_buf = nullptr;  // [max_rows,3] (fused path)
   FinalizeLayer* d_fin = nullptr;
   ShadowLayer* d_shadow = nullptr;
+  UpdateLayer* d_update = nullptr;
   WgUnit* d_units = nullptr;
   int n_units = 0;
   int splits_max = 0;
   int num_sms = 148;
 
+  bool keep_grads = false;  // fused train step also writes the gradient arena (tests)
   // bound arenas
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
 
@@ -429,6 +431,21 @@ static int alloc_plan_memory(NppPlan* p) {
   }
   CK(cudaMalloc(&p->d_fin, fin.size() * sizeof(FinalizeLayer)));
   CK(cudaMemcpy(p->d_fin, fin.data(), fin.size() * sizeof(FinalizeLayer), cudaMemcpyHostToDevice));
+  {
+    std::vector<UpdateLayer> up;
+    for (size_t i = 0; i < fin.size(); ++i) {
+      UpdateLayer u;
+      u.w_off = fin[i].w_off; u.b_off = fin[i].b_off; u.pg_off = fin[i].pg_off; u.bg_off = fin[i].bg_off;
+      u.out = fin[i].out; u.in_ref = fin[i].in_ref; u.kpad = fin[i].kpad;
+      u.split_col = fin[i].split_col; u.off0 = fin[i].off0; u.off1 = fin[i].off1;
+      u.wf = sh[i].wf; u.wt = sh[i].wt;
+      u.t_lo = sh[i].t_lo; u.t_hi = sh[i].t_hi; u.t_row0 = sh[i].t_row0;
+      u.t_lo2 = sh[i].t_lo2; u.t_hi2 = sh[i].t_hi2; u.t_row02 = sh[i].t_row02;
+      up.push_back(u);
+    }
+    CK(cudaMalloc(&p->d_update, up.size() * sizeof(UpdateLayer)));
+    CK(cudaMemcpy(p->d_update, up.data(), up.size() * sizeof(UpdateLayer), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
   CK(cudaMemcpy(p->d_shadow, sh.data(), sh.size() * sizeof(ShadowLayer), cudaMemcpyHostToDevice));
 
@@ -607,7 +624,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     const int width = p->E;
     dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
-    npp_encode_kernel<<<grid, 512, ENC_ROWS * width * sizeof(__half), st>>>(
+    npp_encode_kernel<<<grid, 512, ((ENC_ROWS * width * 2 + 15) / 16) * 16 + ENC_ROWS * (width / (1 + 2 * p->cfg.n_freq)) * sizeof(float), st>>>(
         coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
     CK(cudaGetLastError());
     ++p->launches;
@@ -631,7 +648,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
 }
 
 // grad_logits must already be reflected in acc[amax] (loss kernel or amax kernel).
-static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st) {
+static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st, bool finalize = true) {
   if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
   CKI(prepare(p, n));
   CKI(set_smem_attrs());
@@ -660,7 +677,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
     CK(cudaGetLastError());
     ++p->launches;
   }
-  {
+  if (finalize) {
     ProfScope ps(p, st, PROF_FINALIZE, 3);
     dim3 grid(128, (unsigned)p->layers.size());
     npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin, p->partial, p->wg_params.n_splits, p->slab_stride, p->acc,
@@ -775,6 +792,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->logits_buf);
   cudaFree(p->d_fin);
   cudaFree(p->d_shadow);
+  cudaFree(p->d_update);
   cudaFree(p->d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -883,12 +901,39 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     CK(cudaGetLastError());
     ++p->launches;
   }
-  CKI(run_backward(p, n, p->g_buf, st));
-  CKI(run_adam(p, lr, beta1, beta2, eps, step, st));
-  return run_shadow(p, st);
+  CKI(run_backward(p, n, p->g_buf, st, /*finalize=*/false));
+  {
+    if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
+    if (step < 1) return fail("Adam step must be >= 1");
+    ProfScope ps(p, st, PROF_ADAM, 1);
+    AdamScalars ad;
+    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    ad.beta1 = beta1;
+    ad.beta2 = beta2;
+    ad.step_size = (float)((double)lr / bc1);
+    ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    ad.eps = eps;
+    const int nl = (int)p->layers.size();
+    dim3 grid(96, (unsigned)nl + 1);
+    npp_fused_update_kernel<<<grid, 256, 0, st>>>(p->d_update, nl, p->partial, p->wg_params.n_splits, p->slab_stride,
+                                                  p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,
+                                                  p->head_width,
+                                                  reinterpret_cast<unsigned int*>(p->acc + p->amax_off), p->params,
+                                                  p->keep_grads ? p->grads : nullptr, p->m, p->v, ad);
+    CK(cudaGetLastError());
+    ++p->launches;
+  }
+  return 0;
 }
 
 int npp_last_launch_count(const NppPlan* p) { return p ? p->launches : 0; }
+
+int npp_set_keep_grads(NppPlan* p, int on) {
+  if (!p) return fail("null plan");
+  p->keep_grads = on != 0;
+  return 0;
+}
 
 int npp_profile_enable(NppPlan* p, int on) {
   if (!p) return fail("null plan");

@@ -64,26 +64,34 @@ constexpr int ENC_ROWS = 16;
 __global__ void __launch_bounds__(512) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
                                                          __half* __restrict__ enc1, int ld1,
                                                          __half* __restrict__ enca, int lda) {
-  extern __shared__ __half enc_tile[];  // [ENC_ROWS][width]
+  extern __shared__ __align__(16) unsigned char enc_smem[];
   const int B = 2 * (t.include_input + 2 * t.n_aug);
   const int F = 1 + 2 * t.n_freq;
   const int width = B * F;
+  __half* enc_tile = reinterpret_cast<__half*>(enc_smem);                         // [ENC_ROWS][width]
+  float* base = reinterpret_cast<float*>(enc_smem + ((ENC_ROWS * width * 2 + 15) / 16) * 16);  // [ENC_ROWS][B]
   const int j = blockIdx.y;
   const int row0 = blockIdx.x * ENC_ROWS;
+  // phase 1: the B base features per row in full fp32 accuracy (they are the arguments of phase 2)
   for (int idx = threadIdx.x; idx < ENC_ROWS * B; idx += blockDim.x) {
     const int r = idx / B, c = idx - r * B;
     const int row = row0 + r;
-    if (row < n) {
-      const float y = coords[2 * row], x = coords[2 * row + 1];
-      const float u = npp_base_feature(t, j, c, y, x);
-      __half* o = enc_tile + r * width + c;
-      o[0] = __float2half_rn(u);
-      for (int k = 0; k < t.n_freq; ++k) {
-        const float a = __fmul_rn(u, t.freq[k]);  // p_fn(x * freq), embedder.py:43
-        o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
-        o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
-      }
-    }
+    float u = 0.f;
+    if (row < n) u = npp_base_feature(t, j, c, coords[2 * row], coords[2 * row + 1]);
+    base[idx] = u;
+    enc_tile[r * width + c] = __float2half_rn(u);
+  }
+  __syncthreads();
+  // phase 2: Fourier expansion, one (row, feature, frequency) item per thread-iteration
+  const int items = ENC_ROWS * B * t.n_freq;
+  for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+    const int k = idx / (ENC_ROWS * B);
+    const int rc = idx - k * (ENC_ROWS * B);
+    const int r = rc / B, c = rc - r * B;
+    const float a = __fmul_rn(base[rc], t.freq[k]);  // p_fn(x * freq), embedder.py:43
+    __half* o = enc_tile + r * width + c;
+    o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
+    o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
   }
   __syncthreads();
   __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
@@ -238,18 +246,38 @@ __global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __rest
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   float lsum = 0.f, lmax = 0.f;
+  // width == 256: lane owns columns [8*lane, 8*lane+8); their 3x8 head weights stay in registers
+  float wr[3][8];
+  const bool fast = width == 256;
+  if (fast) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[c][i] = w[c * width + lane * 8 + i];
+  }
   for (int row = blockIdx.x * 8 + wib; row < n; row += gridDim.x * 8) {
     const __half* h = hp + (size_t)row * ld;
     float a[3] = {0.f, 0.f, 0.f};
-    for (int k = lane * 8; k < width; k += 256) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
+    if (fast) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(h + lane * 8);
       const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h2[i]);
-        const int kk = k + 2 * i;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, w[c * width + kk], fmaf(f.y, w[c * width + kk + 1], a[c]));
+        for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, wr[c][2 * i], fmaf(f.y, wr[c][2 * i + 1], a[c]));
+      }
+    } else {
+      for (int k = lane * 8; k < width; k += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h2[i]);
+          const int kk = k + 2 * i;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, w[c * width + kk], fmaf(f.y, w[c * width + kk + 1], a[c]));
+        }
       }
     }
 #pragma unroll
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__
 // Backward of the RGB head: delta_P = (g . W_rgb) * snake'(z_P) * scale (fp16), plus
 // dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
 // Block = 256 threads: thread -> (column pair, row group); rows of a block are split in two groups.
-constexpr int HEAD_BWD_ROWS = 32;
+constexpr int HEAD_BWD_ROWS = 128;   // few blocks -> few atomics per accumulator address
 __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
                                                            const __half* __restrict__ dp, int ld, int width, int n,
                                                            const float* __restrict__ w,
@@ -401,6 +429,93 @@ __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLa
   }
   if (blockIdx.x == 0)
     for (int o = threadIdx.x; o < L.out; o += blockDim.x) grads[L.b_off + o] = bias_acc[L.bg_off + o] * inv;
+}
+
+// Single pass for the fused train step: split-K slabs -> gradient -> Adam -> fp32 master + fp16 shadows.
+// Replaces grad_finalize + adam + shadow (3 kernels, ~2x the bytes) when nobody needs the gradient arena.
+struct UpdateLayer {
+  long long w_off, b_off, pg_off, bg_off;
+  int out, in_ref, kpad;
+  int split_col, off0, off1;
+  __half* wf;
+  __half* wt;
+  int t_lo, t_hi, t_row0;
+  int t_lo2, t_hi2, t_row02;
+};
+struct AdamScalars {
+  float beta1, beta2, step_size, inv_sqrt_bc2, eps;
+};
+__device__ __forceinline__ float npp_adam1(float p, float g, float& m, float& v, const AdamScalars a) {
+  m = m + (g - m) * (1.0f - a.beta1);
+  v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+  return p - a.step_size * (m / (sqrtf(v) * a.inv_sqrt_bc2 + a.eps));
+}
+__global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer* __restrict__ layers, int n_layers,
+                                                               const float* __restrict__ partial, int n_splits,
+                                                               long long slab_stride, const float* __restrict__ bias_acc,
+                                                               const float* __restrict__ head_acc, long long rgb_w_off,
+                                                               long long rgb_b_off, int head_width,
+                                                               const unsigned int* __restrict__ amax_bits,
+                                                               float* __restrict__ params, float* __restrict__ grads,
+                                                               float* __restrict__ m, float* __restrict__ v,
+                                                               AdamScalars ad) {
+  __shared__ float tile[32][33];
+  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
+  if ((int)blockIdx.y == n_layers) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
+    const int total = 3 * head_width + 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const long long idx = i < 3 * head_width ? rgb_w_off + i : rgb_b_off + (i - 3 * head_width);
+      const float g = head_acc[i];
+      if (grads) grads[idx] = g;
+      params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
+    }
+    return;
+  }
+  const UpdateLayer L = layers[blockIdx.y];
+  const int tiles_c = (L.in_ref + 31) / 32;
+  const int tiles_r = L.out / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      float pnew = 0.f;
+      if (c < L.in_ref) {
+        const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
+        const float* pp = partial + L.pg_off + (long long)r * L.kpad + pc;
+        float g = 0.f;
+        for (int k = 0; k < n_splits; ++k) g += pp[k * slab_stride];
+        g *= inv;
+        const long long idx = L.w_off + (long long)r * L.in_ref + c;
+        if (grads) grads[idx] = g;
+        pnew = npp_adam1(params[idx], g, m[idx], v[idx], ad);
+        params[idx] = pnew;
+        L.wf[(long long)r * L.kpad + pc] = __float2half_rn(pnew);
+      }
+      tile[ty + 8 * i][tx] = pnew;
+    }
+    __syncthreads();
+    if (L.wt != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        int trow = -1;
+        if (c >= L.t_lo && c < L.t_hi) trow = L.t_row0 + (c - L.t_lo);
+        else if (c >= L.t_lo2 && c < L.t_hi2) trow = L.t_row02 + (c - L.t_lo2);
+        if (trow >= 0) L.wt[(long long)trow * L.out + r] = __float2half_rn(tile[tx][ty + 8 * i]);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
+      const long long idx = L.b_off + o;
+      const float g = bias_acc[L.bg_off + o] * inv;
+      if (grads) grads[idx] = g;
+      params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
+    }
+  }
 }
 
 __global__ void npp_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {

@@ -19,29 +19,49 @@ import torch
 import torch.nn.functional as F  # noqa: F401  (re-exported like the reference module)
 
 
+def _nearest_index(center, size, dim):
+    """Pixel index read by sample i of a glimpse of `size` centred at `center` (float pixels) along an axis of
+    length `dim`: the fp32 arithmetic of utils/extract_glimpse.py:62-79 followed by grid_sample's
+    unnormalise + nearbyint (align_corners=False, mode='nearest').  Returns [M,size] int64 (may be out of range)."""
+    c = center.to(torch.float32)
+    k = torch.arange(0, size, dtype=torch.float32, device=c.device) - (size - 1) / 2.0
+    x = c[:, None] + k[None, :]
+    half = c.new_tensor(dim / 2)
+    g = (x - half) / half
+    ix = ((g + 1) * dim - 1) / 2
+    return torch.round(ix).long()                 # torch.round is round-half-even, like nearbyint
+
+
+def _is_integral(t):
+    return (not t.is_floating_point()) or bool((t == torch.floor(t)).all())
+
+
+def _gather_window(img_nchw, rows, cols):
+    """img [1,C,H,W]; rows [M,h], cols [M,w] int64 index tables -> [M,C,h,w], zeros outside the image."""
+    _, C, H, W = img_nchw.shape
+    ok = ((rows >= 0) & (rows < H))[:, :, None] & ((cols >= 0) & (cols < W))[:, None, :]
+    out = img_nchw[0][:, rows.clamp(0, H - 1)[:, :, None], cols.clamp(0, W - 1)[:, None, :]]   # [C,M,h,w]
+    return (out * ok[None].to(out.dtype)).permute(1, 0, 2, 3).contiguous()
+
+
 def extract_glimpse(input, size, offsets, centered=False, normalized=False, mode='nearest', padding_mode='zeros'):
     """Nearest-neighbour glimpse for pixel offsets (x, y) = window centre; the only configuration the sampler uses
     (utils/extract_glimpse.py with mode='nearest', normalized=False, centered=False, padding_mode='zeros')."""
     if centered or normalized or mode != 'nearest' or padding_mode != 'zeros':
         raise NotImplementedError("only the sampler's configuration is implemented")
     h, w = size
-    # sample i of a window of even size s centred at c reads pixel nearbyint(c - s/2 + i)
-    c0 = torch.round(offsets[:, 0].float() - w / 2).long()
-    r0 = torch.round(offsets[:, 1].float() - h / 2).long()
     if input.shape[0] not in (1, offsets.shape[0]):
         raise ValueError("batch size must be 1 or match the number of offsets")
-    return _crop(input[:1], r0, c0, h, w)
+    W, H = input.size(-1), input.size(-2)
+    return _gather_window(input[:1], _nearest_index(offsets[:, 1], h, H), _nearest_index(offsets[:, 0], w, W))
 
 
 def _crop(img_nchw, r0, c0, h, w):
     """img [1,C,H,W]; windows with top-left (r0[i], c0[i]) -> [M,C,h,w], zero padded outside the image."""
-    _, C, H, W = img_nchw.shape
     dev = img_nchw.device
     rows = r0.to(dev)[:, None] + torch.arange(h, device=dev)[None, :]          # [M,h]
     cols = c0.to(dev)[:, None] + torch.arange(w, device=dev)[None, :]          # [M,w]
-    ok = ((rows >= 0) & (rows < H))[:, :, None] & ((cols >= 0) & (cols < W))[:, None, :]
-    out = img_nchw[0][:, rows.clamp(0, H - 1)[:, :, None], cols.clamp(0, W - 1)[:, None, :]]   # [C,M,h,w]
-    return (out * ok[None].to(out.dtype)).permute(1, 0, 2, 3).contiguous()
+    return _gather_window(img_nchw, rows, cols)
 
 
 class _UnknownCounter:
@@ -129,13 +149,19 @@ class GridPatchSampler():
             pool = pool[in_bound]
             indicator = self.coord_batch_indicator[:N * total.shape[0] * total.shape[1]][in_bound]
             distance_all = self.permute_distance[:N * total.shape[0] * total.shape[1]][in_bound]
-            r0 = torch.round(pool[:, 0].float() - hh).long()
-            c0 = torch.round(pool[:, 1].float() - wh).long()
-            unknown = self._mask_counter.count(r0, c0, 2 * hh, 2 * wh)
+            integral = _is_integral(pool)
+            if integral:      # windows are contiguous: O(1) unknown-pixel counts from the summed-area table
+                r0 = pool[:, 0].long() - hh
+                c0 = pool[:, 1].long() - wh
+                unknown = self._mask_counter.count(r0, c0, 2 * hh, 2 * wh)
+            else:             # fractional shifts: reproduce grid_sample's per-sample nearest rounding exactly
+                rows = _nearest_index(pool[:, 0], 2 * hh, self.height)
+                cols = _nearest_index(pool[:, 1], 2 * wh, self.width)
+                unknown = (_gather_window(self.mask, rows, cols) < 0.5).sum(dim=[1, 2, 3])
             keep = ~(unknown > (hh * wh * 4 * invalid_ratio))
-            r0, c0, indicator, distance_all = r0[keep], c0[keep], indicator[keep], distance_all[keep]
+            pool, indicator, distance_all = pool[keep], indicator[keep], distance_all[keep]
 
-            sel_r0, sel_c0, weight_topks = [], [], []
+            sel_cent, weight_topks = [], []
             topk_min = topk
             for i in range(self.N_samples):
                 inds = indicator == i
@@ -148,16 +174,20 @@ class GridPatchSampler():
                 distance_topk, inds_topk = torch.topk(distance, k=topk_min, largest=False)
                 distance_topk = 1 / distance_topk
                 weight_topks.append(distance_topk / torch.sum(distance_topk))
-                sel_r0.append(r0[inds][inds_topk])
-                sel_c0.append(c0[inds][inds_topk])
+                sel_cent.append(pool[inds][inds_topk])
             if topk_min < topk:
                 weight_topks = [w[:topk_min] for w in weight_topks]
-                sel_r0 = [r[:topk_min] for r in sel_r0]
-                sel_c0 = [c[:topk_min] for c in sel_c0]
+                sel_cent = [c[:topk_min] for c in sel_cent]
             weight_topks = torch.cat(weight_topks)
-            r0s, c0s = torch.cat(sel_r0), torch.cat(sel_c0)
-            select_img_patches = _crop(self.img, r0s, c0s, 2 * hh, 2 * wh).reshape(self.N_samples, topk_min, 3, 2 * hh, 2 * wh)
-            select_mask_patches = _crop(self.mask, r0s, c0s, 2 * hh, 2 * wh).reshape(self.N_samples, topk_min, 1, 2 * hh, 2 * wh)
+            cents = torch.cat(sel_cent)
+            if integral:
+                rows = (cents[:, 0].long() - hh)[:, None] + torch.arange(2 * hh, device=self.device)[None, :]
+                cols = (cents[:, 1].long() - wh)[:, None] + torch.arange(2 * wh, device=self.device)[None, :]
+            else:
+                rows = _nearest_index(cents[:, 0], 2 * hh, self.height)
+                cols = _nearest_index(cents[:, 1], 2 * wh, self.width)
+            select_img_patches = _gather_window(self.img, rows, cols).reshape(self.N_samples, topk_min, 3, 2 * hh, 2 * wh)
+            select_mask_patches = _gather_window(self.mask, rows, cols).reshape(self.N_samples, topk_min, 1, 2 * hh, 2 * wh)
         else:
             ps = self._patch_size
             select_inds = np.random.choice(self._unfold_r0.shape[0], size=[self.N_samples * topk], replace=False)

@@ -207,7 +207,7 @@ class Plan:
         return c
 
     def encode(self, coords: torch.Tensor) -> torch.Tensor:
-        c = self._coords(coords)
+        c = coords.to(self.device, torch.float32).contiguous()      # no workspace involved: any row count
         out = torch.empty(c.shape[0], self.encoding_width, device=self.device)
         if c.shape[0]:
             nat.check(self.lib.npp_encode(self.handle, c.data_ptr(), c.shape[0], out.data_ptr(), nat.current_stream()))
@@ -265,6 +265,9 @@ class Plan:
         nat.check(self.lib.npp_train_step(self.handle, coords.data_ptr(), target.data_ptr(), nat.ptr(mask), n,
                                           n if n_norm is None else int(n_norm), lr, betas[0], betas[1], eps, step,
                                           loss_out.data_ptr(), nat.current_stream()))
+
+    def keep_grads(self, on: bool = True):
+        nat.check(self.lib.npp_set_keep_grads(self.handle, int(on)))
 
     def launch_count(self) -> int:
         return self.lib.npp_last_launch_count(self.handle)
