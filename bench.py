@@ -155,7 +155,7 @@ def cpu_reference(topk, rows, steps, warmup, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2-top1", "cfg4"])
@@ -246,8 +246,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    # W warm-up steps, and keep going until the SM clock has had ~0.5 s of load to settle
+    t_w = time.time()
+    i = 0
+    while i < args.warmup or time.time() - t_w < 0.5:
         step_resident(i)
+        i += 1
+        if i % 50 == 0:
+            torch.cuda.synchronize()
     launches_per_step = plan.launch_count() if not dp else None
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None

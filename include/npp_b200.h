@@ -36,7 +36,7 @@ typedef struct NppConfig {
   int32_t model;          /* NPP_MODEL_* */
   int32_t topk;           /* number of periodicity proposals K (create_npp_net, models/helpers.py:108-116) */
   int32_t depth;          /* netdepth D (options/arg_config.py:55-74), default 8 */
-  int32_t width;          /* netwidth W, default 512; this build requires W % 512 == 0 */
+  int32_t width;          /* netwidth W; this build requires W == 512 (the reference default) */
   int32_t skip_layer;     /* skips=[4] (models/helpers.py:90); -1 = none */
   int32_t n_aug;          /* len(freq_scales)*len(freq_offsets)*len(angle_offsets), embedder.py:117-120 */
   int32_t n_freq;         /* multires, number of Gaussian Fourier frequencies (embedder.py:25-26) */

@@ -40,6 +40,7 @@ enum : int {
   EPI_DGRAD = 3,      // out0 = acc; colsum += out0
 };
 
+// One dense layer (forward) or one dgrad GEMM of the chain; lives in GLOBAL memory (array of ops).
 struct alignas(64) KmajorParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];
@@ -53,6 +54,7 @@ struct alignas(64) KmajorParams {
   int b_row0[2];   // first row of B (weight shadow) for output column 0
   int M;           // valid rows
   int tiles_m, tiles_n;
+  int epi;         // EPI_*
   const float* bias;
   __half* out0;
   int ld0;
@@ -65,6 +67,15 @@ struct alignas(64) KmajorParams {
   int ldf;
   unsigned long long desc_hi;  // UMMA smem descriptor bits [16,64) (0 = default K-major SW128)
   int k_adv;                   // byte advance per UMMA_K slice (0 = default 32)
+};
+
+// A chain = ops executed in order for every 128-row stripe; op i may read what ops < i wrote for the
+// same rows (rows are independent in forward and dgrad), so a CTA that owns a stripe needs no grid sync.
+struct ChainParams {
+  const KmajorParams* ops;  // device array
+  int n_ops;
+  int M;
+  int tiles_m;
 };
 
 struct WgUnit {
@@ -111,6 +122,7 @@ struct GemmSmem {
   uint64_t* tfull;
   uint64_t* tempty;
   uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
+  uint64_t* op_done;  // all stores of (stripe, op) have completed -> the next op may load them
   uint32_t* tmem_ptr;
 };
 
@@ -126,7 +138,8 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   s.tfull = s.empty + STAGES;
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
+  s.op_done = s.epi_bar + 4;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.op_done + 1);
   return s;
 }
 
@@ -141,6 +154,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
       mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
+    mbar_init(s.op_done, 4);  // one arrive per epilogue warp
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
@@ -183,229 +197,283 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 }
 
 // ---------------------------------------------------------------------------------
+// Epilogue of one 128x256 accumulator tile.  Each warp owns 32 accumulator rows (its TMEM lane quadrant).
+// Results are staged in a per-warp 128B-swizzled 32x64 smem box and written with TMA stores (full 128-byte
+// lines); the dgrad multiplier (stored snake derivative) arrives the same way through a TMA load.
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ KmajorParams p) {
+__device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
+                                              int n0, int M, int warp, int lane, uint32_t& ld_phase,
+                                              uint64_t* tfull, uint32_t acc_phase) {
+  const int lane_base = (warp & 3) * 32;
+  uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
+  uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
+  uint64_t* ebar = &s.epi_bar[warp & 3];
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+  const int row0 = m0 + lane_base;
+  const int row = row0 + lane;
+  const bool row_ok = row < M;
+  const bool warp_ok = row0 < M;
+  const float* bias = p.bias;
+  float* colsum = p.colsum;
+  float* out_f32 = p.out_f32;
+  if (EPI == EPI_DGRAD_MUL) {
+    if (lane == 0) {  // multiplier sub-tile 0, overlapped with the wait for the accumulator
+      mbar_expect_tx(ebar, EPI_BUF_BYTES);
+      tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
+    }
+  }
+  mbar_wait(tfull, acc_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int sub = 0; sub < BN / EPI_COLS; ++sub) {
+    const int col = n0 + sub * EPI_COLS;
+    if (EPI == EPI_DGRAD_MUL) {
+      mbar_wait(ebar, ld_phase);
+      ld_phase ^= 1;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS + half * 32, raw);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      const int hcol = col + half * 32;
+
+      if ((EPI == EPI_LINEAR || EPI == EPI_SNAKE) && bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hcol + i));
+          v[i] += b4.x;
+          v[i + 1] += b4.y;
+          v[i + 2] += b4.z;
+          v[i + 3] += b4.w;
+        }
+      }
+      if (out_f32 != nullptr && row_ok) {
+        float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)row * p.ldf + hcol);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      uint32_t hd[16], dd[16];
+      if (EPI == EPI_SNAKE) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float h2[2], d2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float z = v[i + e];
+            const float w = z + z;
+            const float sn = __sinf(w);
+            const float cs = __cosf(w);
+            h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
+            d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+          }
+          hd[i >> 1] = pack_h2(h2[0], h2[1]);
+          dd[i >> 1] = pack_h2(d2[0], d2[1]);
+        }
+      } else {
+        if (EPI == EPI_DGRAD_MUL) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+            const uint4 m4 = *reinterpret_cast<const uint4*>(buf0 + row_off + ((c ^ sw) << 4));
+            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 m2 = unpack_h2(mw[q]);
+              v[8 * j + 2 * q] *= m2.x;
+              v[8 * j + 2 * q + 1] *= m2.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+      }
+      if (half == 0) {
+        // the previous sub-tile's TMA stores must have finished reading the staging buffers
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+      uint8_t* obuf = (EPI == EPI_DGRAD_MUL) ? buf1 : buf0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+        *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
+            make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+        if (EPI == EPI_SNAKE)
+          *reinterpret_cast<uint4*>(buf1 + row_off + ((c ^ sw) << 4)) =
+              make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+      }
+      if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
+        // bias gradient of the layer that produced this delta: column sums of the
+        // fp16-rounded values, so it matches what the wgrad GEMM consumes.
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 r = unpack_h2(hd[i]);
+          v[2 * i] = row_ok ? r.x : 0.f;
+          v[2 * i + 1] = row_ok ? r.y : 0.f;
+        }
+        const float cs = warp_colsum32(v, lane);
+        if (warp_ok) atomicAdd(colsum + hcol + lane, cs);
+      }
+    }
+    if (EPI == EPI_DGRAD_MUL) {
+      __syncwarp();  // every lane has consumed buf0
+      if (lane == 0 && sub + 1 < BN / EPI_COLS) {
+        mbar_expect_tx(ebar, EPI_BUF_BYTES);
+        tma_load_2d(buf0, &p.tmMul, ebar, col + EPI_COLS, row0);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && warp_ok) {
+      tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
+      if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
+      bulk_commit();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ ChainParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const GemmSmem s = carve_smem(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nseg; ++i) {
-      tma_prefetch_desc(&p.tmA[i]);
-      tma_prefetch_desc(&p.tmB[i]);
-    }
-    tma_prefetch_desc(&p.tmOut0);
-    if (EPI == EPI_SNAKE) tma_prefetch_desc(&p.tmOut1);
-    if (EPI == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
-  }
   const uint32_t tmem_base = gemm_prologue(s, warp);
-  const int total_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     PipeState ps;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * BM;
-      const int n0 = (tile % p.tiles_n) * BN;
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
-          mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
-          if (lane == 0) {
-            mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], p.a_k0[seg] + kb * BK,
-                        m0);
-            tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], p.b_k0[seg] + kb * BK,
-                        p.b_row0[seg] + n0);
+    uint32_t done_phase = 0;
+    bool first = true;
+    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
+      const int m0 = mt * BM;
+      for (int oi = 0; oi < cp.n_ops; ++oi) {
+        const KmajorParams& p = cp.ops[oi];
+        if (lane == 0) {
+          for (int i = 0; i < p.nseg; ++i) {
+            tma_prefetch_desc(&p.tmA[i]);
+            tma_prefetch_desc(&p.tmB[i]);
           }
-          __syncwarp();
-          ps.advance();
+        }
+        if (!first) {
+          // everything the previous op stored for this CTA has landed in global memory
+          mbar_wait(s.op_done, done_phase);
+          done_phase ^= 1;
+          fence_proxy_async_all();
+        }
+        first = false;
+        const int nseg = p.nseg;
+        for (int nt = 0; nt < p.tiles_n; ++nt) {
+          const int n0 = nt * BN;
+          for (int seg = 0; seg < nseg; ++seg) {
+            const int kbs = p.kblocks[seg], ak0 = p.a_k0[seg], bk0 = p.b_k0[seg], br0 = p.b_row0[seg];
+            for (int kb = 0; kb < kbs; ++kb) {
+              mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+              if (lane == 0) {
+                mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
+                tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+              }
+              __syncwarp();
+              ps.advance();
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-    const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
-    const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
     PipeState ps;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&s.tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      int it = 0;
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        for (int kb = 0; kb < p.kblocks[seg]; ++kb, ++it) {
-          mbar_wait(&s.full[ps.stage], ps.phase);
+    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
+      for (int oi = 0; oi < cp.n_ops; ++oi) {
+        const KmajorParams& p = cp.ops[oi];
+        const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
+        const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
+        int total_kb = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
+        for (int nt = 0; nt < p.tiles_n; ++nt) {
+          mbar_wait(&s.tempty[acc], acc_phase ^ 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
-            const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int it = 0; it < total_kb; ++it) {
+            mbar_wait(&s.full[ps.stage], ps.phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+              const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi),
-                       idesc, (it | k) != 0);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                         (it | k) != 0);
+              }
+              umma_commit(&s.empty[ps.stage]);
             }
-            umma_commit(&s.empty[ps.stage]);
+            __syncwarp();
+            ps.advance();
           }
+          if (lane == 0) umma_commit(&s.tfull[acc]);
           __syncwarp();
-          ps.advance();
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&s.tfull[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------ epilogue
-    // Each warp owns 32 accumulator rows (its TMEM lane quadrant).  Results are staged in a per-warp
-    // 128B-swizzled 32x64 smem box and written with TMA stores (full 128-byte lines); the dgrad
-    // multiplier (stored snake derivative) arrives the same way through a TMA load.
-    const int lane_base = (warp & 3) * 32;    // TMEM lane quadrant this warp may access
-    uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
-    uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
-    uint64_t* ebar = &s.epi_bar[warp & 3];
-    const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+    // ------------------------------------------------------------ epilogue warps
     uint32_t ld_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * BM;
-      const int n0 = (tile % p.tiles_n) * BN;
-      const int row0 = m0 + lane_base;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
-      const bool warp_ok = row0 < p.M;
-      if (EPI == EPI_DGRAD_MUL) {
-        if (lane == 0) {  // multiplier sub-tile 0, overlapped with the wait for the accumulator
-          mbar_expect_tx(ebar, EPI_BUF_BYTES);
-          tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
+    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
+      const int m0 = mt * BM;
+      for (int oi = 0; oi < cp.n_ops; ++oi) {
+        const KmajorParams& p = cp.ops[oi];
+        if (lane == 0) {
+          tma_prefetch_desc(&p.tmOut0);
+          if (p.epi == EPI_SNAKE) tma_prefetch_desc(&p.tmOut1);
+          if (p.epi == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
         }
-      }
-      mbar_wait(&s.tfull[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < BN / EPI_COLS; ++sub) {
-        const int col = n0 + sub * EPI_COLS;
-        if (EPI == EPI_DGRAD_MUL) {
-          mbar_wait(ebar, ld_phase);
-          ld_phase ^= 1;
+        const int epi = p.epi;
+        for (int nt = 0; nt < p.tiles_n; ++nt) {
+          const uint32_t tacc = tmem_base + acc * BN;
+          const int n0 = nt * BN;
+          switch (epi) {
+            case EPI_LINEAR:
+              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              break;
+            case EPI_SNAKE:
+              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              break;
+            case EPI_DGRAD_MUL:
+              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              break;
+            default:
+              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              break;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.tempty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + sub * EPI_COLS + half * 32,
-                        raw);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          const int hcol = col + half * 32;
-
-          if ((EPI == EPI_LINEAR || EPI == EPI_SNAKE) && p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + hcol + i));
-              v[i] += b4.x;
-              v[i + 1] += b4.y;
-              v[i + 2] += b4.z;
-              v[i + 3] += b4.w;
-            }
-          }
-          if (p.out_f32 != nullptr && row_ok) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldf + hcol);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          uint32_t hd[16], dd[16];
-          if (EPI == EPI_SNAKE) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float h2[2], d2[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float z = v[i + e];
-                const float w = z + z;
-                const float sn = __sinf(w);
-                const float cs = __cosf(w);
-                h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
-                d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
-              }
-              hd[i >> 1] = pack_h2(h2[0], h2[1]);
-              dd[i >> 1] = pack_h2(d2[0], d2[1]);
-            }
-          } else {
-            if (EPI == EPI_DGRAD_MUL) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t c = static_cast<uint32_t>(half * 4 + j);
-                const uint4 m4 = *reinterpret_cast<const uint4*>(buf0 + row_off + ((c ^ sw) << 4));
-                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 m2 = unpack_h2(mw[q]);
-                  v[8 * j + 2 * q] *= m2.x;
-                  v[8 * j + 2 * q + 1] *= m2.y;
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
-          }
-          if (half == 0) {
-            // the previous sub-tile's TMA stores must have finished reading the staging buffers
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-          }
-          uint8_t* obuf = (EPI == EPI_DGRAD_MUL) ? buf1 : buf0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t c = static_cast<uint32_t>(half * 4 + j);
-            *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
-                make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
-            if (EPI == EPI_SNAKE)
-              *reinterpret_cast<uint4*>(buf1 + row_off + ((c ^ sw) << 4)) =
-                  make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
-          }
-          if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && p.colsum != nullptr) {
-            // bias gradient of the layer that produced this delta: column sums of the
-            // fp16-rounded values, so it matches what the wgrad GEMM consumes.
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 r = unpack_h2(hd[i]);
-              v[2 * i] = row_ok ? r.x : 0.f;
-              v[2 * i + 1] = row_ok ? r.y : 0.f;
-            }
-            const float cs = warp_colsum32(v, lane);
-            if (warp_ok) atomicAdd(p.colsum + hcol + lane, cs);
-          }
+        // (stripe, op) finished: make its TMA stores globally visible before the next op loads them
+        if (lane == 0) {
+          bulk_wait0();
+          fence_proxy_async_all();
+          __threadfence();
+          mbar_arrive(s.op_done);
         }
-        if (EPI == EPI_DGRAD_MUL) {
-          __syncwarp();  // every lane has consumed buf0
-          if (lane == 0 && sub + 1 < BN / EPI_COLS) {
-            mbar_expect_tx(ebar, EPI_BUF_BYTES);
-            tma_load_2d(buf0, &p.tmMul, ebar, col + EPI_COLS, row0);
-          }
-        }
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && warp_ok) {
-          tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
-          if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
-          bulk_commit();
-        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) bulk_wait0();
-    __syncwarp();
   }
   gemm_teardown(tmem_base, warp);
 }

@@ -135,6 +135,8 @@ struct NppPlan {
   FinalizeLayer* d_fin = nullptr;
   ShadowLayer* d_shadow = nullptr;
   UpdateLayer* d_update = nullptr;
+  KmajorParams* d_fwd_ops = nullptr;    // forward chain (one op per dense layer)
+  KmajorParams* d_dgrad_ops = nullptr;  // dgrad chain
   WgUnit* d_units = nullptr;
   int n_units = 0;
   int splits_max = 0;
@@ -373,6 +375,7 @@ static int alloc_plan_memory(NppPlan* p) {
       }
     }
   }
+  if (S > NPP_MAX_SPLITS) S = NPP_MAX_SPLITS;
   p->splits_max = S;
   CK(cudaMalloc(&p->partial, (size_t)S * p->slab_stride * sizeof(float)));
 
@@ -446,6 +449,8 @@ static int alloc_plan_memory(NppPlan* p) {
     CK(cudaMalloc(&p->d_update, up.size() * sizeof(UpdateLayer)));
     CK(cudaMemcpy(p->d_update, up.data(), up.size() * sizeof(UpdateLayer), cudaMemcpyHostToDevice));
   }
+  CK(cudaMalloc(&p->d_fwd_ops, p->layers.size() * sizeof(KmajorParams)));
+  CK(cudaMalloc(&p->d_dgrad_ops, (p->dgrads.size() + 1) * sizeof(KmajorParams)));
   CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
   CK(cudaMemcpy(p->d_shadow, sh.data(), sh.size() * sizeof(ShadowLayer), cudaMemcpyHostToDevice));
 
@@ -527,6 +532,7 @@ static int prepare(NppPlan* p, long long n) {
     k.tiles_m = tiles_m;
     k.tiles_n = L.out / BN;
     k.bias = p->params + L.b_off;
+    k.epi = L.act ? EPI_SNAKE : EPI_LINEAR;
     k.out0 = p->bufs[L.buf_h].ptr;
     k.ld0 = L.out;
     k.tmOut0 = p->map_ep[L.buf_h];
@@ -564,8 +570,12 @@ static int prepare(NppPlan* p, long long n) {
       k.tmMul = p->map_ep[P.buf_d];
     }
     k.colsum = p->acc + P.bg_off;
+    k.epi = P.act ? EPI_DGRAD_MUL : EPI_DGRAD;
     p->dgrad_params.push_back(k);
   }
+  CK(cudaMemcpy(p->d_fwd_ops, p->fwd_params.data(), p->fwd_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_dgrad_ops, p->dgrad_params.data(), p->dgrad_params.size() * sizeof(KmajorParams),
+                cudaMemcpyHostToDevice));
   WgradParams& w = p->wg_params;
   const int nl = (int)p->layers.size();
   for (int i = 0; i < nl; ++i) w.maps[i] = p->map_mn[p->layers[i].buf_delta];
@@ -585,25 +595,22 @@ static int prepare(NppPlan* p, long long n) {
 static int g_smem_attr_done = 0;
 static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_DGRAD_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   g_smem_attr_done = 1;
   return 0;
 }
 
-static int launch_kmajor(const KmajorParams& k, int epi, int num_sms, cudaStream_t st) {
+// Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
+static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st) {
   CKI(set_smem_attrs());
-  const int tiles = k.tiles_m * k.tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  switch (epi) {
-    case EPI_LINEAR: npp_gemm_kmajor<EPI_LINEAR><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
-    case EPI_SNAKE: npp_gemm_kmajor<EPI_SNAKE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
-    case EPI_DGRAD_MUL: npp_gemm_kmajor<EPI_DGRAD_MUL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
-    default: npp_gemm_kmajor<EPI_DGRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(k); break;
-  }
+  ChainParams cp;
+  cp.ops = d_ops;
+  cp.n_ops = n_ops;
+  cp.M = M;
+  cp.tiles_m = (M + BM - 1) / BM;
+  const int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
+  npp_gemm_kmajor<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
   CK(cudaGetLastError());
   return 0;
 }
@@ -624,17 +631,15 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     const int width = p->E;
     dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
-    npp_encode_kernel<<<grid, 512, ((ENC_ROWS * width * 2 + 15) / 16) * 16 + ENC_ROWS * (width / (1 + 2 * p->cfg.n_freq)) * sizeof(float), st>>>(
+    npp_encode_kernel<<<grid, 512, ENC_ROWS * width * sizeof(__half), st>>>(
         coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
     CK(cudaGetLastError());
     ++p->launches;
   }
   {
-    ProfScope ps(p, st, PROF_GEMM_FWD, (int)p->layers.size());
-    for (size_t i = 0; i < p->layers.size(); ++i) {
-      CKI(launch_kmajor(p->fwd_params[i], p->layers[i].act ? EPI_SNAKE : EPI_LINEAR, p->num_sms, st));
-      ++p->launches;
-    }
+    ProfScope ps(p, st, PROF_GEMM_FWD, 1);
+    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st));
+    ++p->launches;
   }
   if (!with_head) return 0;
   const Layer& last = p->layers.back();
@@ -663,12 +668,9 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   ++p->launches;
   }
   {
-    ProfScope ps(p, st, PROF_GEMM_DGRAD, (int)p->dgrads.size());
-    for (size_t i = 0; i < p->dgrads.size(); ++i) {
-      const Layer& P = p->layers[p->dgrads[i].producer];
-      CKI(launch_kmajor(p->dgrad_params[i], P.act ? EPI_DGRAD_MUL : EPI_DGRAD, p->num_sms, st));
-      ++p->launches;
-    }
+    ProfScope ps(p, st, PROF_GEMM_DGRAD, 1);
+    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st));
+    ++p->launches;
   }
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
@@ -737,7 +739,7 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   if (cfg->model == NPP_MODEL_TOPK && cfg->topk < 2) return fail("NPP_Net (top-K) needs topk >= 2");
   if (cfg->model == NPP_MODEL_TOP1 && cfg->topk != 1) return fail("NPP_Net_top1 needs topk == 1");
   if (cfg->topk > MAX_TOPK) return fail("topk exceeds MAX_TOPK=8");
-  if (cfg->width <= 0 || cfg->width % 512 != 0) return fail("this build supports netwidth % 512 == 0 only");
+  if (cfg->width != 512) return fail("this build supports netwidth == 512 only (the reference default)");
   if (cfg->depth < 2 || cfg->depth > 16) return fail("netdepth must be in [2,16]");
   if (cfg->skip_layer >= cfg->depth - 1) return fail("skip layer must be < depth-1");
   if (cfg->n_aug < 1 || cfg->n_aug > MAX_AUG) return fail("n_aug out of range");
@@ -793,6 +795,8 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_fin);
   cudaFree(p->d_shadow);
   cudaFree(p->d_update);
+  cudaFree(p->d_fwd_ops);
+  cudaFree(p->d_dgrad_ops);
   cudaFree(p->d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -915,7 +919,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     ad.eps = eps;
     const int nl = (int)p->layers.size();
-    dim3 grid(96, (unsigned)nl + 1);
+    dim3 grid(296, (unsigned)nl + 1);
     npp_fused_update_kernel<<<grid, 256, 0, st>>>(p->d_update, nl, p->partial, p->wg_params.n_splits, p->slab_stride,
                                                   p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,
                                                   p->head_width,
@@ -1032,9 +1036,14 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int r = launch_kmajor(kp, EPI_LINEAR, sms, (cudaStream_t)stream);
+  kp.epi = EPI_LINEAR;
+  KmajorParams* d_op = nullptr;
+  CK(cudaMalloc(&d_op, sizeof(KmajorParams)));
+  CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(scratch);
+  cudaFree(d_op);
   if (r) return r;
   CK(e);
   return 0;
@@ -1066,14 +1075,23 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 3; ++i) CKI(launch_kmajor(kp, epi ? EPI_SNAKE : EPI_LINEAR, sms, 0));
+  kp.epi = epi ? EPI_SNAKE : EPI_LINEAR;
+  int chain = 1;
+  if (const char* e = getenv("NPP_DEBUG_CHAIN")) chain = atoi(e);   // same op repeated `chain` times in one launch
+  std::vector<KmajorParams> ops((size_t)chain, kp);
+  KmajorParams* d_op = nullptr;
+  CK(cudaMalloc(&d_op, ops.size() * sizeof(KmajorParams)));
+  CK(cudaMemcpy(d_op, ops.data(), ops.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0));
   CK(cudaEventRecord(e0, 0));
-  for (int i = 0; i < iters; ++i) CKI(launch_kmajor(kp, epi ? EPI_SNAKE : EPI_LINEAR, sms, 0));
+  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0));
   CK(cudaEventRecord(e1, 0));
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(ms_out, e0, e1));
+  *ms_out /= (float)chain;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  cudaFree(d_op);
   return 0;
 }
 

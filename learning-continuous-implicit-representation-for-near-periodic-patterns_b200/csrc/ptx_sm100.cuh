@@ -85,6 +85,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// orders async-proxy accesses (TMA loads/stores) of ANY state space against generic-proxy accesses
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

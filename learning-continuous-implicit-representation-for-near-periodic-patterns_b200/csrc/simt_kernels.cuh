@@ -64,34 +64,26 @@ constexpr int ENC_ROWS = 16;
 __global__ void __launch_bounds__(512) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
                                                          __half* __restrict__ enc1, int ld1,
                                                          __half* __restrict__ enca, int lda) {
-  extern __shared__ __align__(16) unsigned char enc_smem[];
+  extern __shared__ __half enc_tile[];  // [ENC_ROWS][width]
   const int B = 2 * (t.include_input + 2 * t.n_aug);
   const int F = 1 + 2 * t.n_freq;
   const int width = B * F;
-  __half* enc_tile = reinterpret_cast<__half*>(enc_smem);                         // [ENC_ROWS][width]
-  float* base = reinterpret_cast<float*>(enc_smem + ((ENC_ROWS * width * 2 + 15) / 16) * 16);  // [ENC_ROWS][B]
   const int j = blockIdx.y;
   const int row0 = blockIdx.x * ENC_ROWS;
-  // phase 1: the B base features per row in full fp32 accuracy (they are the arguments of phase 2)
   for (int idx = threadIdx.x; idx < ENC_ROWS * B; idx += blockDim.x) {
     const int r = idx / B, c = idx - r * B;
     const int row = row0 + r;
-    float u = 0.f;
-    if (row < n) u = npp_base_feature(t, j, c, coords[2 * row], coords[2 * row + 1]);
-    base[idx] = u;
-    enc_tile[r * width + c] = __float2half_rn(u);
-  }
-  __syncthreads();
-  // phase 2: Fourier expansion, one (row, feature, frequency) item per thread-iteration
-  const int items = ENC_ROWS * B * t.n_freq;
-  for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
-    const int k = idx / (ENC_ROWS * B);
-    const int rc = idx - k * (ENC_ROWS * B);
-    const int r = rc / B, c = rc - r * B;
-    const float a = __fmul_rn(base[rc], t.freq[k]);  // p_fn(x * freq), embedder.py:43
-    __half* o = enc_tile + r * width + c;
-    o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
-    o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
+    if (row < n) {
+      const float y = coords[2 * row], x = coords[2 * row + 1];
+      const float u = npp_base_feature(t, j, c, y, x);
+      __half* o = enc_tile + r * width + c;
+      o[0] = __float2half_rn(u);
+      for (int k = 0; k < t.n_freq; ++k) {
+        const float a = __fmul_rn(u, t.freq[k]);  // p_fn(x * freq), embedder.py:43
+        o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
+        o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
+      }
+    }
   }
   __syncthreads();
   __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
@@ -334,8 +326,9 @@ __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__
 
 // Backward of the RGB head: delta_P = (g . W_rgb) * snake'(z_P) * scale (fp16), plus
 // dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
-// Block = 256 threads: thread -> (column pair, row group); rows of a block are split in two groups.
-constexpr int HEAD_BWD_ROWS = 128;   // few blocks -> few atomics per accumulator address
+// One warp per row, lane owns 8 consecutive columns (16-byte loads/stores); per-lane partial sums are reduced
+// across the block's warps in shared memory, then one atomic per column per block.
+constexpr int HEAD_BWD_ROWS = 128;  // rows per block (kept for the launch geometry)
 __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
                                                            const __half* __restrict__ dp, int ld, int width, int n,
                                                            const float* __restrict__ w,
@@ -343,62 +336,101 @@ __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restri
                                                            __half* __restrict__ delta, int ldd,
                                                            float* __restrict__ head_acc /*[3*width+3]*/,
                                                            float* __restrict__ bias_acc /*[width]*/) {
-  __shared__ float sg[HEAD_BWD_ROWS * 3];
+  __shared__ float red[8][4 * 256 + 4];
   const float scale = npp_grad_scale(__uint_as_float(*amax_bits));
-  const int row0 = blockIdx.x * HEAD_BWD_ROWS;
-  const int rows = min(HEAD_BWD_ROWS, n - row0);
-  for (int i = threadIdx.x; i < HEAD_BWD_ROWS * 3; i += blockDim.x) sg[i] = i < rows * 3 ? g[(size_t)row0 * 3 + i] : 0.f;
-  __syncthreads();
-  const int pairs = width >> 1;            // column pairs
-  const int groups = blockDim.x / 128;     // 2 row groups of 128 threads
-  const int grp = threadIdx.x / 128;
-  const int rper = HEAD_BWD_ROWS / groups;
-  for (int cp = threadIdx.x % 128; cp < pairs; cp += 128) {
-    const int k = 2 * cp;
-    const float2 w0 = make_float2(w[k], w[k + 1]);
-    const float2 w1 = make_float2(w[width + k], w[width + k + 1]);
-    const float2 w2 = make_float2(w[2 * width + k], w[2 * width + k + 1]);
-    float2 aw0 = make_float2(0.f, 0.f), aw1 = aw0, aw2 = aw0, ab = aw0;
-#pragma unroll 8
-    for (int rr = 0; rr < rper; ++rr) {
-      const int r = grp * rper + rr;
-      if (r < rows) {
-        const float g0 = sg[3 * r], g1 = sg[3 * r + 1], g2 = sg[3 * r + 2];
-        const size_t off = (size_t)(row0 + r) * ld + k;
-        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(hp + off));
-        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(dp + off));
-        const float dax = fmaf(g0, w0.x, fmaf(g1, w1.x, g2 * w2.x));
-        const float day = fmaf(g0, w0.y, fmaf(g1, w1.y, g2 * w2.y));
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int row_begin = blockIdx.x * HEAD_BWD_ROWS;
+  const int row_end = min(row_begin + HEAD_BWD_ROWS, n);
+  float gsum[3] = {0.f, 0.f, 0.f};
+  for (int k0 = lane * 8; k0 < width; k0 += 256) {   // one pass for width == 256
+    float wr[3][8], aw[3][8], ab[8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        wr[c][i] = w[c * width + k0 + i];
+        aw[c][i] = 0.f;
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ab[i] = 0.f;
+#pragma unroll 4
+    for (int row = row_begin + wib; row < row_end; row += 8) {
+      const float g0 = g[3 * (size_t)row], g1 = g[3 * (size_t)row + 1], g2 = g[3 * (size_t)row + 2];
+      const uint4 hraw = *reinterpret_cast<const uint4*>(hp + (size_t)row * ld + k0);
+      const uint4 draw = *reinterpret_cast<const uint4*>(dp + (size_t)row * ld + k0);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hraw);
+      const __half2* d2 = reinterpret_cast<const __half2*>(&draw);
+      uint4 outv;
+      __half2* o2 = reinterpret_cast<__half2*>(&outv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 h = __half22float2(h2[i]);
+        const float2 d = __half22float2(d2[i]);
+        const float dax = fmaf(g0, wr[0][2 * i], fmaf(g1, wr[1][2 * i], g2 * wr[2][2 * i]));
+        const float day = fmaf(g0, wr[0][2 * i + 1], fmaf(g1, wr[1][2 * i + 1], g2 * wr[2][2 * i + 1]));
         const __half2 dh = __floats2half2_rn(dax * d.x * scale, day * d.y * scale);
-        *reinterpret_cast<__half2*>(delta + (size_t)(row0 + r) * ldd + k) = dh;
+        o2[i] = dh;
         const float2 df = __half22float2(dh);
-        ab.x += df.x;
-        ab.y += df.y;
-        aw0.x = fmaf(g0, h.x, aw0.x);
-        aw0.y = fmaf(g0, h.y, aw0.y);
-        aw1.x = fmaf(g1, h.x, aw1.x);
-        aw1.y = fmaf(g1, h.y, aw1.y);
-        aw2.x = fmaf(g2, h.x, aw2.x);
-        aw2.y = fmaf(g2, h.y, aw2.y);
+        ab[2 * i] += df.x;
+        ab[2 * i + 1] += df.y;
+        aw[0][2 * i] = fmaf(g0, h.x, aw[0][2 * i]);
+        aw[0][2 * i + 1] = fmaf(g0, h.y, aw[0][2 * i + 1]);
+        aw[1][2 * i] = fmaf(g1, h.x, aw[1][2 * i]);
+        aw[1][2 * i + 1] = fmaf(g1, h.y, aw[1][2 * i + 1]);
+        aw[2][2 * i] = fmaf(g2, h.x, aw[2][2 * i]);
+        aw[2][2 * i + 1] = fmaf(g2, h.y, aw[2][2 * i + 1]);
+      }
+      *reinterpret_cast<uint4*>(delta + (size_t)row * ldd + k0) = outv;
+      if (k0 == lane * 8 && lane == 0) {
+        gsum[0] += g0;
+        gsum[1] += g1;
+        gsum[2] += g2;
       }
     }
-    atomicAdd(head_acc + k, aw0.x);
-    atomicAdd(head_acc + k + 1, aw0.y);
-    atomicAdd(head_acc + width + k, aw1.x);
-    atomicAdd(head_acc + width + k + 1, aw1.y);
-    atomicAdd(head_acc + 2 * width + k, aw2.x);
-    atomicAdd(head_acc + 2 * width + k + 1, aw2.y);
-    atomicAdd(bias_acc + k, ab.x);
-    atomicAdd(bias_acc + k + 1, ab.y);
-  }
-  if (threadIdx.x < 3) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += sg[3 * r + threadIdx.x];
-    atomicAdd(head_acc + 3 * width + threadIdx.x, s);
+    // block reduction over the 8 warps (column k0+i of accumulator a lives at red[warp][a*256 + ...])
+    if (k0 < 256) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        red[wib][0 * 256 + lane * 8 + i] = aw[0][i];
+        red[wib][1 * 256 + lane * 8 + i] = aw[1][i];
+        red[wib][2 * 256 + lane * 8 + i] = aw[2][i];
+        red[wib][3 * 256 + lane * 8 + i] = ab[i];
+      }
+      if (lane == 0) {
+        red[wib][1024] = gsum[0];
+        red[wib][1025] = gsum[1];
+        red[wib][1026] = gsum[2];
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 1027; idx += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][idx];
+        const int a = idx >> 8, col = idx & 255;
+        if (idx >= 1024) atomicAdd(head_acc + 3 * width + (idx - 1024), t);
+        else if (col < width) {
+          if (a < 3) atomicAdd(head_acc + a * width + col, t);
+          else atomicAdd(bias_acc + col, t);
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
 // ------------------------------------------------------------- gradients / Adam
+// Sum of the split-K partials of one element in a fixed order; all loads are issued before the adds.
+constexpr int NPP_MAX_SPLITS = 12;
+__device__ __forceinline__ float npp_sum_splits(const float* __restrict__ p, int n_splits, long long stride) {
+  float v[NPP_MAX_SPLITS];
+#pragma unroll
+  for (int k = 0; k < NPP_MAX_SPLITS; ++k) v[k] = k < n_splits ? __ldg(p + k * stride) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NPP_MAX_SPLITS; ++k) s += v[k];
+  return s;
+}
+
 struct FinalizeLayer {
   long long w_off, b_off;    // arena offsets (floats) of weight [out, in_ref] and bias [out]
   long long pg_off;          // offset of this layer's [out, kpad] block inside a partial slab
@@ -422,9 +454,7 @@ __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLa
     float* grow = grads + L.w_off + (long long)o * L.in_ref;
     for (int c = threadIdx.x; c < L.in_ref; c += blockDim.x) {
       const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
-      float s = 0.f;
-      for (int k = 0; k < n_splits; ++k) s += prow[k * slab_stride + pc];
-      grow[c] = s * inv;
+      grow[c] = npp_sum_splits(prow + pc, n_splits, slab_stride) * inv;
     }
   }
   if (blockIdx.x == 0)
@@ -485,9 +515,7 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer
       if (c < L.in_ref) {
         const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
         const float* pp = partial + L.pg_off + (long long)r * L.kpad + pc;
-        float g = 0.f;
-        for (int k = 0; k < n_splits; ++k) g += pp[k * slab_stride];
-        g *= inv;
+        const float g = npp_sum_splits(pp, n_splits, slab_stride) * inv;
         const long long idx = L.w_off + (long long)r * L.in_ref + c;
         if (grads) grads[idx] = g;
         pnew = npp_adam1(params[idx], g, m[idx], v[idx], ad);

@@ -162,6 +162,7 @@ class GridPatchSampler():
             pool, indicator, distance_all = pool[keep], indicator[keep], distance_all[keep]
 
             sel_cent, weight_topks = [], []
+            self.last_topk_distance = []
             topk_min = topk
             for i in range(self.N_samples):
                 inds = indicator == i
@@ -171,7 +172,11 @@ class GridPatchSampler():
                     topk_min = min(len(distance) - 1, topk)
                     if topk_min <= 0:
                         return None, None, None, 0
+                # the reference's own call on the reference's own tensor: many candidates tie on |i|+|j| and torch.topk's
+                # tie order is implementation defined (it differs between CPU and CUDA), so only the identical call
+                # reproduces the reference on a given device
                 distance_topk, inds_topk = torch.topk(distance, k=topk_min, largest=False)
+                self.last_topk_distance.append(distance_topk.clone())
                 distance_topk = 1 / distance_topk
                 weight_topks.append(distance_topk / torch.sum(distance_topk))
                 sel_cent.append(pool[inds][inds_topk])
