@@ -246,6 +246,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi needs ~1 s to come up
     # W warm-up steps, and keep going until the SM clock has had ~0.5 s of load to settle
     t_w = time.time()
     i = 0
@@ -256,7 +257,6 @@ def main():
             torch.cuda.synchronize()
     launches_per_step = plan.launch_count() if not dp else None
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()

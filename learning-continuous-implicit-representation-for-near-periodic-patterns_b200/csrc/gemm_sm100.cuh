@@ -31,7 +31,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
 constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;  // 4 epilogue warps x 2 buffers = 32 KB
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + 256 + 1024;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 
 enum : int {
   EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
@@ -117,6 +117,7 @@ struct GemmSmem {
   uint8_t* a;
   uint8_t* b;
   uint8_t* epi;  // 4 warps x 2 x 4 KB staging, 1024-B aligned
+  float* bias;   // BN floats: bias slice of the current tile, shared by the 4 epilogue warps
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tfull;
@@ -133,7 +134,8 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   s.a = base;
   s.b = base + STAGES * A_STAGE_BYTES;
   s.epi = s.b + STAGES * B_STAGE_BYTES;
-  s.full = reinterpret_cast<uint64_t*>(s.epi + EPI_STAGE_BYTES);
+  s.bias = reinterpret_cast<float*>(s.epi + EPI_STAGE_BYTES);
+  s.full = reinterpret_cast<uint64_t*>(s.bias + BN);
   s.empty = s.full + STAGES;
   s.tfull = s.empty + STAGES;
   s.tempty = s.tfull + 2;
@@ -223,6 +225,16 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
       tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
     }
   }
+  if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+    // bias slice of this tile -> smem once (its load latency hides behind the accumulator wait); the two named
+    // barriers order the refill against the other epilogue warps' reads of the previous tile's slice
+    const int et = (warp & 3) * 32 + lane;
+    float2 bv = make_float2(0.f, 0.f);
+    if (bias != nullptr) bv = __ldg(reinterpret_cast<const float2*>(bias + n0) + et);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    reinterpret_cast<float2*>(s.bias)[et] = bv;
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+  }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
 #pragma unroll 1
@@ -232,20 +244,22 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
       mbar_wait(ebar, ld_phase);
       ld_phase ^= 1;
     }
+    // both 32-column halves of the sub-tile are fetched from TMEM before either is consumed
+    uint32_t raw0[32], raw1[32];
+    tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS, raw0);
+    tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS + 32, raw1);
+    tmem_ld_wait();
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS + half * 32, raw);
-      tmem_ld_wait();
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(half == 0 ? raw0[i] : raw1[i]);
       const int hcol = col + half * 32;
 
-      if ((EPI == EPI_LINEAR || EPI == EPI_SNAKE) && bias != nullptr) {
+      if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hcol + i));
+          const float4 b4 = *reinterpret_cast<const float4*>(s.bias + sub * EPI_COLS + half * 32 + i);
           v[i] += b4.x;
           v[i + 1] += b4.y;
           v[i + 2] += b4.z;

@@ -249,7 +249,7 @@ def test_train_steps_follow_oracle(topk):
         plan.train_step(cd, td, md, lr, loss_d, step=step)
         ref_loss, _ = O.train_step(p, m, v, step, enc, target, mask, lr, topk_model=topk > 1)
         assert abs(loss_d.item() - ref_loss) < 1e-3 * ref_loss, (step, loss_d.item(), ref_loss)
-    assert plan.launch_count() > 20
+    assert plan.launch_count() >= 5          # encode, fwd chain, head+loss, head bwd, dgrad chain, wgrad, update
     # after 8 Adam steps of size ~5e-4 the weights agree to a fraction of one step
     got = plan.state()
     for k in plan.grad_views():
