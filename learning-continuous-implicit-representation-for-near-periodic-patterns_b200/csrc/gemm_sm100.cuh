@@ -52,6 +52,8 @@ struct alignas(64) KmajorParams {
   int a_k0[2];     // first K element of the segment inside A's tensor
   int b_k0[2];     // first K element inside B's tensor
   int b_row0[2];   // first row of B (weight shadow) for output column 0
+  int a_src[2];    // index of the op of this chain that writes the segment's A tensor, -1 = produced earlier
+  int sub_base;    // 64-column output sub-tiles written per stripe by the ops before this one
   int M;           // valid rows
   int tiles_m, tiles_n;
   int epi;         // EPI_*
@@ -76,6 +78,7 @@ struct ChainParams {
   int n_ops;
   int M;
   int tiles_m;
+  int subs_per_stripe;  // output sub-tiles all ops write per stripe
 };
 
 struct WgUnit {
@@ -123,7 +126,7 @@ struct GemmSmem {
   uint64_t* tfull;
   uint64_t* tempty;
   uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
-  uint64_t* op_done;  // all stores of (stripe, op) have completed -> the next op may load them
+  uint32_t* prog;     // [4] per epilogue warp: output sub-tiles (cumulative) whose TMA stores have completed
   uint32_t* tmem_ptr;
 };
 
@@ -140,8 +143,8 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   s.tfull = s.empty + STAGES;
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
-  s.op_done = s.epi_bar + 4;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.op_done + 1);
+  s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
+  s.tmem_ptr = s.prog + 4;
   return s;
 }
 
@@ -156,7 +159,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
       mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
-    mbar_init(s.op_done, 4);  // one arrive per epilogue warp
+    for (int i = 0; i < 4; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
@@ -198,6 +201,20 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+// Progress counters between the epilogue warps (writers of an op's output) and the TMA producer (reader of it
+// as the next op's A operand).  The value is the cumulative number of 64-column sub-tiles whose bulk stores have
+// COMPLETED; release/acquire at CTA scope plus an async-proxy fence on both sides order TMA store -> TMA load.
+__device__ __forceinline__ void publish_progress(uint32_t* slot, uint32_t value) {
+  fence_proxy_async_all();
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(value) : "memory");
+}
+__device__ __forceinline__ void wait_progress(const uint32_t* slot, uint32_t need) {
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(slot)) : "memory");
+  } while (static_cast<int32_t>(v - need) < 0);
+}
+
 // ---------------------------------------------------------------------------------
 // Epilogue of one 128x256 accumulator tile.  Each warp owns 32 accumulator rows (its TMEM lane quadrant).
 // Results are staged in a per-warp 128B-swizzled 32x64 smem box and written with TMA stores (full 128-byte
@@ -205,7 +222,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
-                                              uint64_t* tfull, uint32_t acc_phase) {
+                                              uint64_t* tfull, uint32_t acc_phase, uint32_t& seq) {
   const int lane_base = (warp & 3) * 32;
   uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
   uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
@@ -343,10 +360,17 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && warp_ok) {
-      tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
-      if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
-      bulk_commit();
+    ++seq;  // cumulative number of sub-tiles this warp has handed to the TMA store engine
+    if (lane == 0) {
+      if (warp_ok) {
+        tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
+        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
+        bulk_commit();
+        bulk_wait1();                    // every group but the one just committed has fully completed
+        publish_progress(&s.prog[warp & 3], seq - 1);
+      } else {
+        publish_progress(&s.prog[warp & 3], seq);
+      }
     }
   }
 }
@@ -362,10 +386,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     PipeState ps;
-    uint32_t done_phase = 0;
-    bool first = true;
-    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
+    uint32_t stripe_iter = 0;
+    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x, ++stripe_iter) {
       const int m0 = mt * BM;
+      const uint32_t stripe_base = stripe_iter * static_cast<uint32_t>(cp.subs_per_stripe);
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
@@ -374,24 +398,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             tma_prefetch_desc(&p.tmB[i]);
           }
         }
-        if (!first) {
-          // everything the previous op stored for this CTA has landed in global memory
-          mbar_wait(s.op_done, done_phase);
-          done_phase ^= 1;
-          fence_proxy_async_all();
-        }
-        first = false;
         const int nseg = p.nseg;
         for (int nt = 0; nt < p.tiles_n; ++nt) {
           const int n0 = nt * BN;
           for (int seg = 0; seg < nseg; ++seg) {
             const int kbs = p.kblocks[seg], ak0 = p.a_k0[seg], bk0 = p.b_k0[seg], br0 = p.b_row0[seg];
+            const int src = p.a_src[seg];
+            // K block kb of this segment is the 64-column sub-tile (ak0/64 + kb) written by op `src`
+            const uint32_t need0 = src >= 0 ? stripe_base + cp.ops[src].sub_base + ak0 / BK + 1 : 0u;
             for (int kb = 0; kb < kbs; ++kb) {
               mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
-              if (lane == 0) {
+              if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
                 mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
                 tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+              }
+              if (src >= 0) {
+                if (lane < 4) wait_progress(&s.prog[lane], need0 + kb);
+                __syncwarp();
+              }
+              if (lane == 0) {
+                if (src >= 0) fence_proxy_async_all();
+                tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
               }
               __syncwarp();
               ps.advance();
@@ -443,6 +470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   } else {
     // ------------------------------------------------------------ epilogue warps
     uint32_t ld_phase = 0;
+    uint32_t seq = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
@@ -460,16 +488,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           const int n0 = nt * BN;
           switch (epi) {
             case EPI_LINEAR:
-              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
               break;
             case EPI_SNAKE:
-              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
               break;
             case EPI_DGRAD_MUL:
-              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
               break;
             default:
-              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase);
+              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
               break;
           }
           tc_fence_before();
@@ -478,12 +506,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-        // (stripe, op) finished: make its TMA stores globally visible before the next op loads them
+        // (stripe, op) finished: its last sub-tile must not wait for a later commit to be published
         if (lane == 0) {
           bulk_wait0();
-          fence_proxy_async_all();
-          __threadfence();
-          mbar_arrive(s.op_done);
+          publish_progress(&s.prog[warp & 3], seq);
         }
         __syncwarp();
       }

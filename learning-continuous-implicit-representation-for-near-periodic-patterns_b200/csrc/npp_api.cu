@@ -155,6 +155,7 @@ struct NppPlan {
   WgradParams wg_params;
   std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
   int launches = 0;
+  int fwd_subs = 0, dgrad_subs = 0;  // output sub-tiles per stripe of each chain
 
   // optional per-kernel-class timing (CUDA events on the launching stream)
   bool profiling = false;
@@ -516,6 +517,7 @@ static int prepare(NppPlan* p, long long n) {
   }
   const int tiles_m = (int)((n + BM - 1) / BM);
   p->fwd_params.clear();
+  int fwd_subs = 0;
   for (auto& L : p->layers) {
     KmajorParams k;
     memset(&k, 0, sizeof(k));
@@ -527,7 +529,10 @@ static int prepare(NppPlan* p, long long n) {
       k.a_k0[s] = 0;
       k.b_k0[s] = L.segs[s].pad_off;
       k.b_row0[s] = 0;
+      k.a_src[s] = L.segs[s].producer;   // forward op index == layer index
     }
+    k.sub_base = fwd_subs;
+    fwd_subs += (L.out / BN) * (BN / EPI_COLS);
     k.M = (int)n;
     k.tiles_m = tiles_m;
     k.tiles_n = L.out / BN;
@@ -544,6 +549,7 @@ static int prepare(NppPlan* p, long long n) {
     p->fwd_params.push_back(k);
   }
   p->dgrad_params.clear();
+  int dg_subs = 0;
   for (auto& op : p->dgrads) {
     const Layer& P = p->layers[op.producer];
     KmajorParams k;
@@ -557,7 +563,14 @@ static int prepare(NppPlan* p, long long n) {
       k.a_k0[s] = 0;
       k.b_k0[s] = 0;
       k.b_row0[s] = C.segs[op.src[s].seg].wt_row0;
+      // the delta of consumer layer C is written by the dgrad op whose producer == C (none for the last layer,
+      // whose delta comes from the head-backward kernel)
+      k.a_src[s] = -1;
+      for (size_t q = 0; q < p->dgrads.size(); ++q)
+        if (p->dgrads[q].producer == op.src[s].layer) k.a_src[s] = (int)q;
     }
+    k.sub_base = dg_subs;
+    dg_subs += (P.out / BN) * (BN / EPI_COLS);
     k.M = (int)n;
     k.tiles_m = tiles_m;
     k.tiles_n = P.out / BN;
@@ -573,6 +586,8 @@ static int prepare(NppPlan* p, long long n) {
     k.epi = P.act ? EPI_DGRAD_MUL : EPI_DGRAD;
     p->dgrad_params.push_back(k);
   }
+  p->fwd_subs = fwd_subs;
+  p->dgrad_subs = dg_subs;
   CK(cudaMemcpy(p->d_fwd_ops, p->fwd_params.data(), p->fwd_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_dgrad_ops, p->dgrad_params.data(), p->dgrad_params.size() * sizeof(KmajorParams),
                 cudaMemcpyHostToDevice));
@@ -602,13 +617,14 @@ static int set_smem_attrs() {
 }
 
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
-static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st) {
+static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st, int subs_per_stripe) {
   CKI(set_smem_attrs());
   ChainParams cp;
   cp.ops = d_ops;
   cp.n_ops = n_ops;
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
+  cp.subs_per_stripe = subs_per_stripe;
   const int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
   npp_gemm_kmajor<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
   CK(cudaGetLastError());
@@ -638,7 +654,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
   }
   {
     ProfScope ps(p, st, PROF_GEMM_FWD, 1);
-    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st));
+    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs));
     ++p->launches;
   }
   if (!with_head) return 0;
@@ -669,7 +685,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_GEMM_DGRAD, 1);
-    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st));
+    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st, p->dgrad_subs));
     ++p->launches;
   }
   {
@@ -1040,7 +1056,9 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   KmajorParams* d_op = nullptr;
   CK(cudaMalloc(&d_op, sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
-  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream);
+  kp.a_src[0] = kp.a_src[1] = -1;
+  CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / EPI_COLS));
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(scratch);
   cudaFree(d_op);
@@ -1078,13 +1096,22 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   kp.epi = epi ? EPI_SNAKE : EPI_LINEAR;
   int chain = 1;
   if (const char* e = getenv("NPP_DEBUG_CHAIN")) chain = atoi(e);   // same op repeated `chain` times in one launch
+  kp.a_src[0] = kp.a_src[1] = -1;
   std::vector<KmajorParams> ops((size_t)chain, kp);
+  const int subs_op = (n / BN) * (BN / EPI_COLS);
+  if (getenv("NPP_DEBUG_CHAIN_DEP") && n == k)   // op i reads op i-1's output (ping-pong between out0 and out1 buffers)
+    for (int i = 0; i < chain; ++i) {
+      ops[i].sub_base = i * subs_op;
+      if (i > 0) ops[i].a_src[0] = i - 1;
+    }
+  else
+    for (int i = 0; i < chain; ++i) ops[i].sub_base = i * subs_op;
   KmajorParams* d_op = nullptr;
   CK(cudaMalloc(&d_op, ops.size() * sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, ops.data(), ops.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
-  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0));
+  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op));
   CK(cudaEventRecord(e0, 0));
-  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0));
+  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op));
   CK(cudaEventRecord(e1, 0));
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(ms_out, e0, e1));

@@ -12,7 +12,7 @@ nat = npp_b200._native
 lib = nat.lib()
 torch.manual_seed(0)
 CHAIN = int(os.environ.get('NPP_DEBUG_CHAIN', '1'))
-print('chain length per launch:', CHAIN)
+print('chain length per launch:', CHAIN, 'dependent' if os.environ.get('NPP_DEBUG_CHAIN_DEP') else 'independent')
 for (m, n, k) in [(16384, 512, 512), (16384, 512, 1024), (131072, 512, 512)]:
     a = torch.randn(m, k, device="cuda").half()
     b = (torch.randn(n, k, device="cuda") * 0.05).half()
