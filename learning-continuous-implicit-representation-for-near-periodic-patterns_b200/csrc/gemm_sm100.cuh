@@ -366,13 +366,21 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
         tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
         if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
         bulk_commit();
-        bulk_wait1();                    // every group but the one just committed has fully completed
-        publish_progress(&s.prog[warp & 3], seq - 1);
-      } else {
-        publish_progress(&s.prog[warp & 3], seq);
+        if (sub >= 2) {
+          // lazily publish stores that are two sub-tiles old: by now they have completed, so this does not stall
+          bulk_wait2();
+          publish_progress(&s.prog[warp & 3], seq - 2);
+        }
       }
     }
   }
+  // tile end: drain this warp's stores and publish the whole tile.  The warp would otherwise just wait for the
+  // next accumulator, so the store-completion latency (~1 us) is hidden.
+  if (lane == 0) {
+    bulk_wait0();
+    publish_progress(&s.prog[warp & 3], seq);
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------
@@ -506,12 +514,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-        // (stripe, op) finished: its last sub-tile must not wait for a later commit to be published
-        if (lane == 0) {
-          bulk_wait0();
-          publish_progress(&s.prog[warp & 3], seq);
-        }
-        __syncwarp();
+
       }
     }
   }

@@ -80,6 +80,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // all committed bulk stores of this thread have finished READING their smem source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recently committed bulk group of this thread have completed (writes performed)
+__device__ __forceinline__ void bulk_wait2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes -> visible to the async proxy (UMMA / TMA reads of smem)
