@@ -205,14 +205,14 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 // as the next op's A operand).  The value is the cumulative number of 64-column sub-tiles whose bulk stores have
 // COMPLETED; release/acquire at CTA scope plus an async-proxy fence on both sides order TMA store -> TMA load.
 __device__ __forceinline__ void publish_progress(uint32_t* slot, uint32_t value) {
-  fence_proxy_async_all();
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(value) : "memory");
 }
-__device__ __forceinline__ void wait_progress(const uint32_t* slot, uint32_t need) {
+__device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t need) {
   uint32_t v;
   do {
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(slot)) : "memory");
   } while (static_cast<int32_t>(v - need) < 0);
+  return v;
 }
 
 // ---------------------------------------------------------------------------------
@@ -366,11 +366,6 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
         tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
         if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
         bulk_commit();
-        if (sub >= 2) {
-          // lazily publish stores that are two sub-tiles old: by now they have completed, so this does not stall
-          bulk_wait2();
-          publish_progress(&s.prog[warp & 3], seq - 2);
-        }
       }
     }
   }
@@ -395,6 +390,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     // ------------------------------------------------------------ TMA producer
     PipeState ps;
     uint32_t stripe_iter = 0;
+    uint32_t seen = 0;  // cumulative output sub-tiles known to be complete (minimum over the epilogue warps)
     for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x, ++stripe_iter) {
       const int m0 = mt * BM;
       const uint32_t stripe_base = stripe_iter * static_cast<uint32_t>(cp.subs_per_stripe);
@@ -420,12 +416,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
                 tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
               }
-              if (src >= 0) {
-                if (lane < 4) wait_progress(&s.prog[lane], need0 + kb);
+              if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
+                // wait until all four epilogue warps have published this sub-tile, remember how far they are
+                // (later K blocks usually need no second look) and order the coming TMA loads after the acquire
+                const uint32_t need = need0 + kb;
+                uint32_t ahead = 0x7fffffffu;
+                if (lane < 4) ahead = wait_progress(&s.prog[lane], need) - need;
+#pragma unroll
+                for (int o = 2; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
+                seen = need + __shfl_sync(0xffffffffu, ahead, 0);
+                if (lane == 0) fence_proxy_async_all();
                 __syncwarp();
               }
               if (lane == 0) {
-                if (src >= 0) fence_proxy_async_all();
                 tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
               }
               __syncwarp();
