@@ -286,3 +286,51 @@ def test_rejects_bad_input():
         plan.forward(torch.zeros(300, 2, device="cuda"))
     with pytest.raises(npp_b200._native.NppError):
         npp_b200._native.check(plan.lib.npp_forward(plan.handle, None, 10, None, None))
+
+
+def test_psnr_after_training_matches_oracle():
+    """Fit a small synthetic near-periodic image for 120 steps with the CUDA path and with the fp32 CPU oracle from the
+    same weights / coordinates / LR schedule; the final full-image reconstruction PSNR must agree within 0.1 dB
+    (BASELINE.json north_star)."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(3)
+    H, W = 48, 64
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    img = np.stack([0.5 + 0.4 * np.sin(2 * np.pi * xx / 16.0) * np.cos(2 * np.pi * yy / 12.0),
+                    0.5 + 0.4 * np.cos(2 * np.pi * (xx + yy) / 16.0),
+                    0.5 + 0.3 * np.sin(2 * np.pi * yy / 12.0)], -1).astype(np.float32)
+    img = np.clip(img + rng.normal(0, 0.01, img.shape).astype(np.float32), 0, 1)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    angles, periods = [[90.0, 180.0]], [[16.0, 12.0]]
+    enc = EncoderSpec.from_proposals((H, W), angles, periods, freqs)
+    n = 1024
+    plan = Plan(enc, max_rows=H * W)
+    params = O.init_params(rng, topk=1)
+    plan.load_state(params)
+    tabs = [(enc.cos_t[0], enc.sin_t[0], enc.period[0])]
+    all_coords = np.stack([yy.reshape(-1), xx.reshape(-1)], 1).astype(np.float32)
+    table = O.encode(all_coords, tabs, freqs, (H, W))
+    target_all = img.reshape(-1, 3)
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    mask = np.ones((n, 1), np.float32)
+    loss_d = torch.zeros((), device="cuda")
+    md = torch.from_numpy(mask).cuda()
+    for step in range(1, 121):
+        sel = rng.choice(H * W, n, replace=False)
+        lr = O.lr_schedule(step)
+        plan.train_step(torch.from_numpy(all_coords[sel]).cuda(), torch.from_numpy(target_all[sel]).cuda(), md, lr,
+                        loss_d, step=step)
+        O.train_step(p, m, v, step, table[sel], target_all[sel], mask, lr, topk_model=False)
+
+    def psnr(pred):
+        return -10.0 * np.log10(np.mean((pred - target_all) ** 2))
+
+    ours = torch.sigmoid(plan.forward(torch.from_numpy(all_coords).cuda())).cpu().numpy()
+    ref = O.sigmoid(O.forward(p, table, topk_model=False)[0])
+    a, b = psnr(ours), psnr(ref)
+    _report("psnr", {"psnr_cuda_db": float(a), "psnr_oracle_db": float(b), "steps": 120, "rows_per_step": n})
+    assert b > 15.0, b                     # the fit actually learned something
+    assert abs(a - b) < 0.1, (a, b)
