@@ -28,11 +28,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_COLS = 32;                         // epilogue sub-tile: 32 rows x 32 halves = one 2 KB SW64 box per warp
-constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 2 KB
-constexpr int EPI_BUFS = 4;                          // per warp: 2 tensors x double buffering
-constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 32 KB
-constexpr int DEP_COLS = 64;                         // dependency granularity between ops = one K block
+constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
+constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
+constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;  // 4 epilogue warps x 2 buffers = 32 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 
 enum : int {
@@ -127,7 +125,7 @@ struct GemmSmem {
   uint64_t* empty;
   uint64_t* tfull;
   uint64_t* tempty;
-  uint64_t* epi_bar;  // two per epilogue warp (double-buffered TMA loads of the dgrad multiplier)
+  uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
   uint32_t* prog;     // [4] per epilogue warp: output sub-tiles (cumulative) whose TMA stores have completed
   uint32_t* tmem_ptr;
 };
@@ -145,7 +143,7 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   s.tfull = s.empty + STAGES;
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
-  s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 8);
+  s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
   s.tmem_ptr = s.prog + 4;
   return s;
 }
@@ -160,7 +158,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
       mbar_init(&s.tfull[i], 1);
       mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&s.epi_bar[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
     for (int i = 0; i < 4; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
@@ -225,14 +223,12 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq) {
-  constexpr int NSUB = BN / EPI_COLS;  // 8 sub-tiles of 32 columns
   const int lane_base = (warp & 3) * 32;
-  // per-warp staging: [0],[1] = out0 (h / delta) double buffer; [2],[3] = out1 (snake derivative) or the dgrad multiplier
-  uint8_t* wbuf = s.epi + (warp & 3) * EPI_BUFS * EPI_BUF_BYTES;
-  uint64_t* ebar = &s.epi_bar[(warp & 3) * 2];
-  // SWIZZLE_64B: 16-byte chunk c (0..3) of row r sits at chunk c ^ ((r >> 1) & 3)
-  const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
-  const uint32_t row_off = static_cast<uint32_t>(lane) * 64u;
+  uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
+  uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
+  uint64_t* ebar = &s.epi_bar[warp & 3];
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const int row0 = m0 + lane_base;
   const int row = row0 + lane;
   const bool row_ok = row < M;
@@ -241,12 +237,9 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   float* colsum = p.colsum;
   float* out_f32 = p.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
-    if (lane == 0) {  // multiplier sub-tiles 0 and 1, overlapped with the wait for the accumulator
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        mbar_expect_tx(&ebar[b], EPI_BUF_BYTES);
-        tma_load_2d(wbuf + (2 + b) * EPI_BUF_BYTES, &p.tmMul, &ebar[b], n0 + b * EPI_COLS, row0);
-      }
+    if (lane == 0) {  // multiplier sub-tile 0, overlapped with the wait for the accumulator
+      mbar_expect_tx(ebar, EPI_BUF_BYTES);
+      tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
     }
   }
   if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
@@ -261,109 +254,121 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
-  const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(lane_base) << 16);
-  uint32_t raw[2][32];
-  tmem_ld_32x32(tbase, raw[0]);
-#pragma unroll
-  for (int sub = 0; sub < NSUB; ++sub) {
-    const int b = sub & 1;
+#pragma unroll 1
+  for (int sub = 0; sub < BN / EPI_COLS; ++sub) {
     const int col = n0 + sub * EPI_COLS;
-    tmem_ld_wait();                                                   // accumulators of this sub-tile
-    if (sub + 1 < NSUB) tmem_ld_32x32(tbase + (sub + 1) * EPI_COLS, raw[b ^ 1]);   // next one in flight
-    float v[32];
+    if (EPI == EPI_DGRAD_MUL) {
+      mbar_wait(ebar, ld_phase);
+      ld_phase ^= 1;
+    }
+    // both 32-column halves of the sub-tile are fetched from TMEM before either is consumed
+    uint32_t raw0[32], raw1[32];
+    tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS, raw0);
+    tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS + 32, raw1);
+    tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[b][i]);
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(half == 0 ? raw0[i] : raw1[i]);
+      const int hcol = col + half * 32;
 
-    if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+      if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(s.bias + sub * EPI_COLS + i);
-        v[i] += b4.x;
-        v[i + 1] += b4.y;
-        v[i + 2] += b4.z;
-        v[i + 3] += b4.w;
-      }
-    }
-    if (out_f32 != nullptr && row_ok) {
-      float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)row * p.ldf + col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-    uint32_t hd[16], dd[16];
-    if (EPI == EPI_SNAKE) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float h2[2], d2[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float z = v[i + e];
-          const float w = z + z;
-          const float sn = __sinf(w);
-          const float cs = __cosf(w);
-          h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
-          d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s.bias + sub * EPI_COLS + half * 32 + i);
+          v[i] += b4.x;
+          v[i + 1] += b4.y;
+          v[i + 2] += b4.z;
+          v[i + 3] += b4.w;
         }
-        hd[i >> 1] = pack_h2(h2[0], h2[1]);
-        dd[i >> 1] = pack_h2(d2[0], d2[1]);
       }
-    } else {
-      if (EPI == EPI_DGRAD_MUL) {
-        mbar_wait(&ebar[b], ld_phase);       // multiplier sub-tile `sub` has landed in buffer 2+b
-        const uint8_t* mbuf = wbuf + (2 + b) * EPI_BUF_BYTES;
+      if (out_f32 != nullptr && row_ok) {
+        float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)row * p.ldf + hcol);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 m4 = *reinterpret_cast<const uint4*>(mbuf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4));
-          const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      uint32_t hd[16], dd[16];
+      if (EPI == EPI_SNAKE) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 m2 = unpack_h2(mw[q]);
-            v[8 * j + 2 * q] *= m2.x;
-            v[8 * j + 2 * q + 1] *= m2.y;
+        for (int i = 0; i < 32; i += 2) {
+          float h2[2], d2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float z = v[i + e];
+            const float w = z + z;
+            const float sn = __sinf(w);
+            const float cs = __cosf(w);
+            h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
+            d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+          }
+          hd[i >> 1] = pack_h2(h2[0], h2[1]);
+          dd[i >> 1] = pack_h2(d2[0], d2[1]);
+        }
+      } else {
+        if (EPI == EPI_DGRAD_MUL) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+            const uint4 m4 = *reinterpret_cast<const uint4*>(buf0 + row_off + ((c ^ sw) << 4));
+            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 m2 = unpack_h2(mw[q]);
+              v[8 * j + 2 * q] *= m2.x;
+              v[8 * j + 2 * q + 1] *= m2.y;
+            }
           }
         }
-        if (b == 1) ld_phase ^= 1;           // both barriers have completed one more phase
-        __syncwarp();                        // every lane has consumed the multiplier buffer
-        if (lane == 0 && sub + 2 < NSUB) {
-          mbar_expect_tx(&ebar[b], EPI_BUF_BYTES);
-          tma_load_2d(wbuf + (2 + b) * EPI_BUF_BYTES, &p.tmMul, &ebar[b], col + 2 * EPI_COLS, row0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+      }
+      if (half == 0) {
+        // the previous sub-tile's TMA stores must have finished reading the staging buffers
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+      uint8_t* obuf = (EPI == EPI_DGRAD_MUL) ? buf1 : buf0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+        *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
+            make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
+        if (EPI == EPI_SNAKE)
+          *reinterpret_cast<uint4*>(buf1 + row_off + ((c ^ sw) << 4)) =
+              make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+      }
+      if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
+        // bias gradient of the layer that produced this delta: column sums of the
+        // fp16-rounded values, so it matches what the wgrad GEMM consumes.
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 r = unpack_h2(hd[i]);
+          v[2 * i] = row_ok ? r.x : 0.f;
+          v[2 * i + 1] = row_ok ? r.y : 0.f;
         }
+        const float cs = warp_colsum32(v, lane);
+        if (warp_ok) atomicAdd(colsum + hcol + lane, cs);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
     }
-    // the TMA store issued two sub-tiles ago (same buffers) must have finished reading them
-    if (lane == 0) bulk_wait_read1();
-    __syncwarp();
-    uint8_t* obuf = wbuf + b * EPI_BUF_BYTES;
-    uint8_t* dbuf = wbuf + (2 + b) * EPI_BUF_BYTES;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
-      *reinterpret_cast<uint4*>(obuf + off) = make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
-      if (EPI == EPI_SNAKE)
-        *reinterpret_cast<uint4*>(dbuf + off) = make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
-    }
-    if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
-      // bias gradient of the layer that produced this delta: column sums of the fp16-rounded values, so it
-      // matches what the wgrad GEMM consumes.
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float2 r = unpack_h2(hd[i]);
-        v[2 * i] = row_ok ? r.x : 0.f;
-        v[2 * i + 1] = row_ok ? r.y : 0.f;
+    if (EPI == EPI_DGRAD_MUL) {
+      __syncwarp();  // every lane has consumed buf0
+      if (lane == 0 && sub + 1 < BN / EPI_COLS) {
+        mbar_expect_tx(ebar, EPI_BUF_BYTES);
+        tma_load_2d(buf0, &p.tmMul, ebar, col + EPI_COLS, row0);
       }
-      const float cs = warp_colsum32(v, lane);
-      if (warp_ok) atomicAdd(colsum + col + lane, cs);
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && warp_ok) {
-      tma_store_2d(&p.tmOut0, obuf, col, row0);
-      if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
-      bulk_commit();
+    ++seq;  // cumulative number of sub-tiles this warp has handed to the TMA store engine
+    if (lane == 0) {
+      if (warp_ok) {
+        tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
+        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
+        bulk_commit();
+      }
     }
   }
-  seq += BN / DEP_COLS;  // cumulative number of 64-column blocks this warp has handed to the TMA store engine
   // tile end: drain this warp's stores and publish the whole tile.  The warp would otherwise just wait for the
   // next accumulator, so the store-completion latency (~1 us) is hidden.
   if (lane == 0) {

@@ -54,16 +54,14 @@ static int load_encode_fn() {
 }
 
 // fp16 row-major [rows, cols] tensor with pitch `ld` elements; box = {64 cols, box_rows}, 128B swizzle.
-static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
-                    int box_cols = 64) {
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   CKI(load_encode_fn());
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (rows=" +
@@ -515,7 +513,7 @@ static int prepare(NppPlan* p, long long n) {
     // row-contraction of the weight-gradient GEMM.
     CKI(make_map(&p->map_a[i], b.ptr, n, b.width, b.width, BM));
     CKI(make_map(&p->map_mn[i], b.ptr, n, b.width, b.width, 64));
-    CKI(make_map(&p->map_ep[i], b.ptr, n, b.width, b.width, 32, EPI_COLS));
+    CKI(make_map(&p->map_ep[i], b.ptr, n, b.width, b.width, 32));
   }
   const int tiles_m = (int)((n + BM - 1) / BM);
   p->fwd_params.clear();
@@ -534,7 +532,7 @@ static int prepare(NppPlan* p, long long n) {
       k.a_src[s] = L.segs[s].producer;   // forward op index == layer index
     }
     k.sub_base = fwd_subs;
-    fwd_subs += (L.out / BN) * (BN / DEP_COLS);
+    fwd_subs += (L.out / BN) * (BN / EPI_COLS);
     k.M = (int)n;
     k.tiles_m = tiles_m;
     k.tiles_n = L.out / BN;
@@ -572,7 +570,7 @@ static int prepare(NppPlan* p, long long n) {
         if (p->dgrads[q].producer == op.src[s].layer) k.a_src[s] = (int)q;
     }
     k.sub_base = dg_subs;
-    dg_subs += (P.out / BN) * (BN / DEP_COLS);
+    dg_subs += (P.out / BN) * (BN / EPI_COLS);
     k.M = (int)n;
     k.tiles_m = tiles_m;
     k.tiles_n = P.out / BN;
@@ -1050,7 +1048,7 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   CK(cudaMalloc(&scratch, (size_t)m * n * sizeof(__half)));
   kp.out0 = scratch;
   kp.ld0 = n;
-  CKI(make_map(&kp.tmOut0, scratch, m, n, n, 32, EPI_COLS));
+  CKI(make_map(&kp.tmOut0, scratch, m, n, n, 32));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1060,7 +1058,7 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
   kp.a_src[0] = kp.a_src[1] = -1;
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
-  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / DEP_COLS));
+  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / EPI_COLS));
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(scratch);
   cudaFree(d_op);
@@ -1077,8 +1075,8 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   memset(&kp, 0, sizeof(kp));
   CKI(make_map(&kp.tmA[0], a, m, k, k, BM));
   CKI(make_map(&kp.tmB[0], b, n, k, k, 256));
-  CKI(make_map(&kp.tmOut0, out0, m, n, n, 32, EPI_COLS));
-  if (out1) CKI(make_map(&kp.tmOut1, out1, m, n, n, 32, EPI_COLS));
+  CKI(make_map(&kp.tmOut0, out0, m, n, n, 32));
+  if (out1) CKI(make_map(&kp.tmOut1, out1, m, n, n, 32));
   kp.nseg = 1;
   kp.kblocks[0] = k / BK;
   kp.M = m;
@@ -1100,7 +1098,7 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   if (const char* e = getenv("NPP_DEBUG_CHAIN")) chain = atoi(e);   // same op repeated `chain` times in one launch
   kp.a_src[0] = kp.a_src[1] = -1;
   std::vector<KmajorParams> ops((size_t)chain, kp);
-  const int subs_op = (n / BN) * (BN / DEP_COLS);
+  const int subs_op = (n / BN) * (BN / EPI_COLS);
   if (getenv("NPP_DEBUG_CHAIN_DEP") && n == k)   // op i reads op i-1's output (ping-pong between out0 and out1 buffers)
     for (int i = 0; i < chain; ++i) {
       ops[i].sub_base = i * subs_op;
