@@ -23,14 +23,15 @@ constexpr int BM = 128;      // UMMA M  (rows of the coordinate batch / out-feat
 constexpr int BN = 256;      // UMMA N
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle atom of halves
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
 constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
-constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;  // 4 epilogue warps x 2 buffers = 32 KB
+constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
+constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 
 enum : int {
@@ -119,7 +120,7 @@ struct PipeState {
 struct GemmSmem {
   uint8_t* a;
   uint8_t* b;
-  uint8_t* epi;  // 4 warps x 2 x 4 KB staging, 1024-B aligned
+  uint8_t* epi;  // 4 warps x 4 x 4 KB staging, 1024-B aligned
   float* bias;   // BN floats: bias slice of the current tile, shared by the 4 epilogue warps
   uint64_t* full;
   uint64_t* empty;
@@ -223,9 +224,13 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq) {
+  constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
   const int lane_base = (warp & 3) * 32;
-  uint8_t* buf0 = s.epi + (warp & 3) * 2 * EPI_BUF_BYTES;
-  uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
+  // per-warp staging (4 x 4 KB, 128B-swizzled 32x64 boxes):
+  //   forward : [0],[1] out0 double buffer, [2],[3] out1 (snake derivative) double buffer
+  //   dgrad   : [0..3] the multiplier of the WHOLE tile (fetched during the accumulator wait); each sub-tile's
+  //             result overwrites its multiplier in place and is stored from there
+  uint8_t* wbuf = s.epi + (warp & 3) * EPI_BUFS * EPI_BUF_BYTES;
   uint64_t* ebar = &s.epi_bar[warp & 3];
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
@@ -237,9 +242,11 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   float* colsum = p.colsum;
   float* out_f32 = p.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
-    if (lane == 0) {  // multiplier sub-tile 0, overlapped with the wait for the accumulator
-      mbar_expect_tx(ebar, EPI_BUF_BYTES);
-      tma_load_2d(buf0, &p.tmMul, ebar, n0, row0);
+    // all stores of the previous tile were drained at its end, so the four buffers are free
+    if (lane == 0) {
+      mbar_expect_tx(ebar, NSUB * EPI_BUF_BYTES);
+#pragma unroll
+      for (int q = 0; q < NSUB; ++q) tma_load_2d(wbuf + q * EPI_BUF_BYTES, &p.tmMul, ebar, n0 + q * EPI_COLS, row0);
     }
   }
   if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
@@ -254,13 +261,15 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
+  if (EPI == EPI_DGRAD_MUL) {
+    mbar_wait(ebar, ld_phase);
+    ld_phase ^= 1;
+  }
 #pragma unroll 1
-  for (int sub = 0; sub < BN / EPI_COLS; ++sub) {
+  for (int sub = 0; sub < NSUB; ++sub) {
     const int col = n0 + sub * EPI_COLS;
-    if (EPI == EPI_DGRAD_MUL) {
-      mbar_wait(ebar, ld_phase);
-      ld_phase ^= 1;
-    }
+    uint8_t* obuf = wbuf + ((EPI == EPI_DGRAD_MUL) ? sub : (sub & 1)) * EPI_BUF_BYTES;
+    uint8_t* dbuf = wbuf + (2 + (sub & 1)) * EPI_BUF_BYTES;
     // both 32-column halves of the sub-tile are fetched from TMEM before either is consumed
     uint32_t raw0[32], raw1[32];
     tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS, raw0);
@@ -310,7 +319,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t c = static_cast<uint32_t>(half * 4 + j);
-            const uint4 m4 = *reinterpret_cast<const uint4*>(buf0 + row_off + ((c ^ sw) << 4));
+            const uint4 m4 = *reinterpret_cast<const uint4*>(obuf + row_off + ((c ^ sw) << 4));
             const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -323,19 +332,19 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
 #pragma unroll
         for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
       }
-      if (half == 0) {
-        // the previous sub-tile's TMA stores must have finished reading the staging buffers
-        if (lane == 0) bulk_wait_read0();
+      if (EPI != EPI_DGRAD_MUL && half == 0) {
+        // the TMA store issued two sub-tiles ago (same buffers) must have finished reading them
+        if (lane == 0) bulk_wait_read1();
         __syncwarp();
       }
-      uint8_t* obuf = (EPI == EPI_DGRAD_MUL) ? buf1 : buf0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+        // dgrad: in place over this thread's own multiplier chunks (already consumed above)
         *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
             make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
         if (EPI == EPI_SNAKE)
-          *reinterpret_cast<uint4*>(buf1 + row_off + ((c ^ sw) << 4)) =
+          *reinterpret_cast<uint4*>(dbuf + row_off + ((c ^ sw) << 4)) =
               make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
       }
       if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
@@ -351,22 +360,13 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
         if (warp_ok) atomicAdd(colsum + hcol + lane, cs);
       }
     }
-    if (EPI == EPI_DGRAD_MUL) {
-      __syncwarp();  // every lane has consumed buf0
-      if (lane == 0 && sub + 1 < BN / EPI_COLS) {
-        mbar_expect_tx(ebar, EPI_BUF_BYTES);
-        tma_load_2d(buf0, &p.tmMul, ebar, col + EPI_COLS, row0);
-      }
-    }
     fence_proxy_async_smem();
     __syncwarp();
     ++seq;  // cumulative number of sub-tiles this warp has handed to the TMA store engine
-    if (lane == 0) {
-      if (warp_ok) {
-        tma_store_2d(&p.tmOut0, (EPI == EPI_DGRAD_MUL) ? buf1 : buf0, col, row0);
-        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, buf1, col, row0);
-        bulk_commit();
-      }
+    if (lane == 0 && warp_ok) {
+      tma_store_2d(&p.tmOut0, obuf, col, row0);
+      if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
+      bulk_commit();
     }
   }
   // tile end: drain this warp's stores and publish the whole tile.  The warp would otherwise just wait for the

@@ -912,7 +912,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   {
     ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
     const Layer& last = p->layers.back();
-    int blocks = (int)((n + 7) / 8);
+    int blocks = (int)((n + 31) / 32);   // 8 warps x 4 rows in flight each
     if (blocks > p->num_sms * 8) blocks = p->num_sms * 8;
     npp_head_loss_kernel<<<blocks, 256, 0, st>>>(p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)n,
                                                  p->params + p->rgb_w_off, p->params + p->rgb_b_off, target, mask,
@@ -935,7 +935,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     ad.eps = eps;
     const int nl = (int)p->layers.size();
-    dim3 grid(296, (unsigned)nl + 1);
+    dim3 grid(192, (unsigned)nl + 1);
     npp_fused_update_kernel<<<grid, 256, 0, st>>>(p->d_update, nl, p->partial, p->wg_params.n_splits, p->slab_stride,
                                                   p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,
                                                   p->head_width,

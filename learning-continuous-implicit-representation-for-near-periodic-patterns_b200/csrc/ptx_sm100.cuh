@@ -78,6 +78,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING their smem source
+// all but the most recent committed bulk store of this thread have finished READING their smem source
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recently committed bulk group of this thread have completed (writes performed)
 __device__ __forceinline__ void bulk_wait2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }

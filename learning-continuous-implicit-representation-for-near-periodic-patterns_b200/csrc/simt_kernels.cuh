@@ -89,12 +89,13 @@ __global__ void __launch_bounds__(512) npp_encode_kernel(const float* __restrict
   __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
   const int ld = j == 0 ? ld1 : lda;
   const int w2 = width >> 1;  // width is even (B is even)
-  for (int idx = threadIdx.x; idx < ENC_ROWS * w2; idx += blockDim.x) {
-    const int r = idx / w2, c2 = idx - r * w2;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = wib; r < ENC_ROWS; r += nw) {  // one warp per row: coalesced 128-byte stores, no division
     const int row = row0 + r;
-    if (row < n)
-      *reinterpret_cast<__half2*>(dst + (size_t)row * ld + 2 * c2) =
-          *reinterpret_cast<const __half2*>(enc_tile + r * width + 2 * c2);
+    if (row >= n) break;
+    const __half2* src = reinterpret_cast<const __half2*>(enc_tile + r * width);
+    __half2* d2 = reinterpret_cast<__half2*>(dst + (size_t)row * ld);
+    for (int c2 = lane; c2 < w2; c2 += 32) d2[c2] = src[c2];
   }
 }
 
@@ -247,48 +248,76 @@ __global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __rest
 #pragma unroll
       for (int i = 0; i < 8; ++i) wr[c][i] = w[c * width + lane * 8 + i];
   }
-  for (int row = blockIdx.x * 8 + wib; row < n; row += gridDim.x * 8) {
-    const __half* h = hp + (size_t)row * ld;
-    float a[3] = {0.f, 0.f, 0.f};
-    if (fast) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(h + lane * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  const int wstride = gridDim.x * 8;
+  for (int row_base = blockIdx.x * 8 + wib; row_base < n; row_base += 4 * wstride) {
+    // up to 4 rows per iteration so that four 512-byte row loads are in flight per warp
+    float a[4][3];
+    uint4 raw[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h2[i]);
+    for (int u = 0; u < 4; ++u) {
+      const int row = row_base + u * wstride;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (fast && row < n) raw[u] = *reinterpret_cast<const uint4*>(hp + (size_t)row * ld + lane * 8);
+    }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, wr[c][2 * i], fmaf(f.y, wr[c][2 * i + 1], a[c]));
-      }
-    } else {
-      for (int k = lane * 8; k < width; k += 256) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    for (int u = 0; u < 4; ++u) {
+      const int row = row_base + u * wstride;
+      a[u][0] = a[u][1] = a[u][2] = 0.f;
+      if (row >= n) continue;
+      if (fast) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 f = __half22float2(h2[i]);
-          const int kk = k + 2 * i;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) a[c] = fmaf(f.x, w[c * width + kk], fmaf(f.y, w[c * width + kk + 1], a[c]));
+          for (int c = 0; c < 3; ++c) a[u][c] = fmaf(f.x, wr[c][2 * i], fmaf(f.y, wr[c][2 * i + 1], a[u][c]));
+        }
+      } else {
+        const __half* h = hp + (size_t)row * ld;
+        for (int k = lane * 8; k < width; k += 256) {
+          const uint4 rw = *reinterpret_cast<const uint4*>(h + k);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&rw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            const int kk = k + 2 * i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              a[u][c] = fmaf(f.x, w[c * width + kk], fmaf(f.y, w[c * width + kk + 1], a[u][c]));
+          }
         }
       }
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a[c] += __shfl_xor_sync(0xffffffffu, a[c], s);
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[u][c] += __shfl_xor_sync(0xffffffffu, a[u][c], s);
     }
-    if (lane < 3) {
-      const float z = (lane == 0 ? a[0] : (lane == 1 ? a[1] : a[2])) + b[lane];
-      const size_t idx = 3 * (size_t)row + lane;
-      const float yh = 1.0f / (1.0f + expf(-z));
-      const float m = mask ? mask[row] : 1.0f;
-      const float wgt = m + (1.0f - m) * 0.3f;
-      const float d = (yh - target[idx]) * wgt;
-      lsum += d * d;
-      const float gi = 2.0f * d * wgt * inv_count * yh * (1.0f - yh);
-      if (logits) logits[idx] = z;
-      g[idx] = gi;
-      lmax = fmaxf(lmax, fabsf(gi));
+    // lanes 0..11: (row u = lane / 3, channel c = lane % 3)
+    if (lane < 12) {
+      const int u = lane / 3, c = lane - 3 * u;
+      const int row = row_base + u * wstride;
+      if (row < n) {
+        float acc = 0.f;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            if (uu == u && cc == c) acc = a[uu][cc];
+        const float z = acc + b[c];
+        const size_t idx = 3 * (size_t)row + c;
+        const float yh = 1.0f / (1.0f + expf(-z));
+        const float m = mask ? mask[row] : 1.0f;
+        const float wgt = m + (1.0f - m) * 0.3f;
+        const float d = (yh - target[idx]) * wgt;
+        lsum += d * d;
+        const float gi = 2.0f * d * wgt * inv_count * yh * (1.0f - yh);
+        if (logits) logits[idx] = z;
+        g[idx] = gi;
+        lmax = fmaxf(lmax, fabsf(gi));
+      }
     }
   }
   __shared__ float ssum[8], smax[8];
@@ -328,7 +357,7 @@ __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__
 // dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
 // One warp per row, lane owns 8 consecutive columns (16-byte loads/stores); per-lane partial sums are reduced
 // across the block's warps in shared memory, then one atomic per column per block.
-constexpr int HEAD_BWD_ROWS = 128;  // rows per block (kept for the launch geometry)
+constexpr int HEAD_BWD_ROWS = 32;   // rows per block: ~3.5 blocks per SM at 16 k rows
 __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
                                                            const __half* __restrict__ dp, int ld, int width, int n,
                                                            const float* __restrict__ w,
@@ -489,7 +518,10 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer
                                                                float* __restrict__ params, float* __restrict__ grads,
                                                                float* __restrict__ m, float* __restrict__ v,
                                                                AdamScalars ad) {
-  __shared__ float tile[32][33];
+  // Tile = 32 weight rows x 128 PADDED columns; a thread owns 4 consecutive padded columns of one row per pass, so
+  // the split-K slabs are read with aligned float4 loads.  Padded columns map back to reference columns per segment
+  // (segment boundaries are multiples of 64, so the four columns never straddle one).
+  __shared__ float tile[32][129];
   const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
   if ((int)blockIdx.y == n_layers) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
     const int total = 3 * head_width + 3;
@@ -502,37 +534,84 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer
     return;
   }
   const UpdateLayer L = layers[blockIdx.y];
-  const int tiles_c = (L.in_ref + 31) / 32;
-  const int tiles_r = L.out / 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tiles_c = (L.kpad + 127) >> 7;
+  const int tiles_r = L.out >> 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 column groups x 8 rows per pass
+  const bool two_seg = L.in_ref > L.split_col;
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
-    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    const int r0 = (t / tiles_c) << 5, pc0 = (t % tiles_c) << 7;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty + 8 * i, c = c0 + tx;
-      float pnew = 0.f;
-      if (c < L.in_ref) {
-        const int pc = c < L.split_col ? L.off0 + c : L.off1 + (c - L.split_col);
-        const float* pp = partial + L.pg_off + (long long)r * L.kpad + pc;
-        const float g = npp_sum_splits(pp, n_splits, slab_stride) * inv;
-        const long long idx = L.w_off + (long long)r * L.in_ref + c;
-        if (grads) grads[idx] = g;
-        pnew = npp_adam1(params[idx], g, m[idx], v[idx], ad);
-        params[idx] = pnew;
-        L.wf[(long long)r * L.kpad + pc] = __float2half_rn(pnew);
+      const int r = r0 + ty + 8 * i;
+      const int pc = pc0 + 4 * tx;
+      float pn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pc < L.kpad) {
+        int c, lim;
+        if (two_seg && pc >= L.off1) {
+          c = pc - L.off1 + L.split_col;
+          lim = L.in_ref;
+        } else {
+          c = pc - L.off0;
+          lim = L.split_col;
+        }
+        if (c < lim) {
+          const float4* pp = reinterpret_cast<const float4*>(partial + L.pg_off + (long long)r * L.kpad + pc);
+          const long long s4 = slab_stride >> 2;
+          float4 acc[NPP_MAX_SPLITS];
+#pragma unroll
+          for (int k = 0; k < NPP_MAX_SPLITS; ++k)
+            acc[k] = k < n_splits ? __ldg(pp + k * s4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float g4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < NPP_MAX_SPLITS; ++k) {
+            g4[0] += acc[k].x;
+            g4[1] += acc[k].y;
+            g4[2] += acc[k].z;
+            g4[3] += acc[k].w;
+          }
+          const long long base = L.w_off + (long long)r * L.in_ref + c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c + j < lim) {
+              const float g = g4[j] * inv;
+              if (grads) grads[base + j] = g;
+              pn[j] = npp_adam1(params[base + j], g, m[base + j], v[base + j], ad);
+              params[base + j] = pn[j];
+            }
+          }
+        }
+        // forward shadow: four halves (padding columns are written as the zeros they must stay)
+        const __half2 lo = __floats2half2_rn(pn[0], pn[1]), hi = __floats2half2_rn(pn[2], pn[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+        pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+        *reinterpret_cast<uint2*>(L.wf + (long long)r * L.kpad + pc) = pk;
       }
-      tile[ty + 8 * i][tx] = pnew;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tile[ty + 8 * i][4 * tx + j] = pn[j];
     }
     __syncthreads();
     if (L.wt != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i, r = r0 + tx;
+      // transposed shadow for dgrad: row = reference input column (within the ranges that need a gradient)
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int pcl = ty + 8 * i;
+        const int pc = pc0 + pcl;
+        if (pc >= L.kpad) break;
+        int c, lim;
+        if (two_seg && pc >= L.off1) {
+          c = pc - L.off1 + L.split_col;
+          lim = L.in_ref;
+        } else {
+          c = pc - L.off0;
+          lim = L.split_col;
+        }
+        if (c >= lim) continue;
         int trow = -1;
         if (c >= L.t_lo && c < L.t_hi) trow = L.t_row0 + (c - L.t_lo);
         else if (c >= L.t_lo2 && c < L.t_hi2) trow = L.t_row02 + (c - L.t_lo2);
-        if (trow >= 0) L.wt[(long long)trow * L.out + r] = __float2half_rn(tile[tx][ty + 8 * i]);
+        if (trow >= 0) L.wt[(long long)trow * L.out + r0 + tx] = __float2half_rn(tile[tx][pcl]);
       }
     }
   }
