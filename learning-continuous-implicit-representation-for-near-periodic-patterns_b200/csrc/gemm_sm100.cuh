@@ -23,7 +23,8 @@ constexpr int BM = 128;      // UMMA M  (rows of the coordinate batch / out-feat
 constexpr int BN = 256;      // UMMA N
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle atom of halves
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;     // chain kernel: 3 x 48 KB ring + 64 KB epilogue staging
+constexpr int WG_STAGES = 4;  // wgrad kernel: no staging, deeper ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 192;
@@ -33,6 +34,7 @@ constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
 constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
+constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
 
 enum : int {
   EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
@@ -44,7 +46,7 @@ enum : int {
 // One dense layer (forward) or one dgrad GEMM of the chain; lives in GLOBAL memory (array of ops).
 struct alignas(64) KmajorParams {
   CUtensorMap tmA[2];
-  CUtensorMap tmB[2];
+  CUtensorMap tmB[2];   // weight tiles: box {64, 256/cluster} rows
   CUtensorMap tmOut0;  // box {64, 32} store maps of out0 / out1, load map of mul
   CUtensorMap tmOut1;
   CUtensorMap tmMul;
@@ -106,16 +108,18 @@ struct alignas(64) WgradParams {
   int k_adv;                   // 0 = default 2048
 };
 
-struct PipeState {
+template <int NSTAGES>
+struct PipeStateT {
   int stage = 0;
   uint32_t phase = 0;
   __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) {
+    if (++stage == NSTAGES) {
       stage = 0;
       phase ^= 1;
     }
   }
 };
+using PipeState = PipeStateT<STAGES>;
 
 struct GemmSmem {
   uint8_t* a;
@@ -131,17 +135,18 @@ struct GemmSmem {
   uint32_t* tmem_ptr;
 };
 
-__device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
+template <int NSTAGES, int EPI_BYTES>
+__device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   uint32_t addr = smem_u32(raw);
   uint8_t* base = raw + ((1024u - (addr & 1023u)) & 1023u);
   GemmSmem s;
   s.a = base;
-  s.b = base + STAGES * A_STAGE_BYTES;
-  s.epi = s.b + STAGES * B_STAGE_BYTES;
-  s.bias = reinterpret_cast<float*>(s.epi + EPI_STAGE_BYTES);
-  s.full = reinterpret_cast<uint64_t*>(s.bias + BN);
-  s.empty = s.full + STAGES;
-  s.tfull = s.empty + STAGES;
+  s.b = base + NSTAGES * A_STAGE_BYTES;
+  s.epi = s.b + NSTAGES * B_STAGE_BYTES;
+  s.bias = reinterpret_cast<float*>(s.epi + EPI_BYTES);
+  s.full = reinterpret_cast<uint64_t*>(s.bias + (EPI_BYTES ? BN : 0));
+  s.empty = s.full + NSTAGES;
+  s.tfull = s.empty + NSTAGES;
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
   s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
@@ -149,11 +154,12 @@ __device__ __forceinline__ GemmSmem carve_smem(uint8_t* raw) {
   return s;
 }
 
-__device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
+template <int NSTAGES, int CLUSTER = 1>
+__device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.empty[i], CLUSTER);  // every CTA of the cluster releases the stage (multicast writes into all)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tfull[i], 1);
@@ -166,13 +172,16 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmSmem& s, int warp) {
   if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // peers' barriers exist before anyone multicasts into them
   tc_fence_after();
   return *s.tmem_ptr;
 }
 
+template <int CLUSTER = 1>
 __device__ __forceinline__ void gemm_teardown(uint32_t tmem_base, int warp) {
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers / write its smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -379,20 +388,25 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
 }
 
 // ---------------------------------------------------------------------------------
+template <int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ ChainParams cp) {
   extern __shared__ uint8_t smem_raw[];
-  const GemmSmem s = carve_smem(smem_raw);
+  const GemmSmem s = carve_smem_t<STAGES, EPI_STAGE_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue(s, warp);
+  const uint32_t tmem_base = gemm_prologue_t<STAGES, CLUSTER>(s, warp);
+  // every CTA of a cluster runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
+  const int stripe_iters = (cp.tiles_m + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = static_cast<uint16_t>((1u << CLUSTER) - 1u);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     PipeState ps;
     uint32_t stripe_iter = 0;
     uint32_t seen = 0;  // cumulative output sub-tiles known to be complete (minimum over the epilogue warps)
-    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x, ++stripe_iter) {
-      const int m0 = mt * BM;
+    for (int si = 0; si < stripe_iters; ++si, ++stripe_iter) {
+      const int m0 = (si * (int)gridDim.x + (int)blockIdx.x) * BM;
       const uint32_t stripe_base = stripe_iter * static_cast<uint32_t>(cp.subs_per_stripe);
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
@@ -414,7 +428,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
               mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
               if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
                 mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+                if (CLUSTER == 1)
+                  tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+                else  // this CTA fetches 1/CLUSTER of the weight tile and multicasts it to the whole cluster
+                  tma_load_2d_mc(s.b + ps.stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / CLUSTER), &p.tmB[seg],
+                                 &s.full[ps.stage], bk0 + kb * BK, br0 + n0 + (int)crank * (BN / CLUSTER), cmask);
               }
               if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
                 // wait until all four epilogue warps have published this sub-tile, remember how far they are
@@ -444,7 +462,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     PipeState ps;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
+    for (int si = 0; si < stripe_iters; ++si) {
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
@@ -466,7 +484,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
                          (it | k) != 0);
               }
-              umma_commit(&s.empty[ps.stage]);
+              if (CLUSTER == 1) umma_commit(&s.empty[ps.stage]);
+              else umma_commit_mc(&s.empty[ps.stage], cmask);
             }
             __syncwarp();
             ps.advance();
@@ -484,8 +503,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     uint32_t seq = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int mt = blockIdx.x; mt < cp.tiles_m; mt += gridDim.x) {
-      const int m0 = mt * BM;
+    for (int si = 0; si < stripe_iters; ++si) {
+      const int m0 = (si * (int)gridDim.x + (int)blockIdx.x) * BM;
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
@@ -521,20 +540,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       }
     }
   }
-  gemm_teardown(tmem_base, warp);
+  gemm_teardown<CLUSTER>(tmem_base, warp);
 }
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const GemmSmem s = carve_smem(smem_raw);
+  const GemmSmem s = carve_smem_t<WG_STAGES, 0>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue(s, warp);
+  const uint32_t tmem_base = gemm_prologue_t<WG_STAGES>(s, warp);
   const int kb_total = (p.rows + BK - 1) / BK;
 
   if (warp == 0) {
-    PipeState ps;
+    PipeStateT<WG_STAGES> ps;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
@@ -561,7 +580,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_wgrad(const __grid_c
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 1, 1);
     const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(8192, 1024);
     const int kadv = p.k_adv ? p.k_adv : 2048;
-    PipeState ps;
+    PipeStateT<WG_STAGES> ps;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {

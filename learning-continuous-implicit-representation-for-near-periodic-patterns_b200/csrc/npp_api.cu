@@ -141,6 +141,7 @@ struct NppPlan {
   int n_units = 0;
   int splits_max = 0;
   int num_sms = 148;
+  int cluster = 2;   // CTAs per cluster in the chain kernel (weight tiles are TMA-multicast across it); 1 = off
 
   bool keep_grads = false;  // fused train step also writes the gradient arena (tests)
   // bound arenas
@@ -352,8 +353,8 @@ static int alloc_plan_memory(NppPlan* p) {
     Layer& L = p->layers[i];
     L.wf = reinterpret_cast<__half*>((char*)p->shadow_mem + wf_off[i]);
     L.wt = L.wt_rows ? reinterpret_cast<__half*>((char*)p->shadow_mem + wt_off[i]) : nullptr;
-    CKI(make_map(&L.map_wf, L.wf, L.out, L.kpad, L.kpad, 256));
-    if (L.wt) CKI(make_map(&L.map_wt, L.wt, L.wt_rows, L.out, L.out, 256));
+    CKI(make_map(&L.map_wf, L.wf, L.out, L.kpad, L.kpad, BN / p->cluster));
+    if (L.wt) CKI(make_map(&L.map_wt, L.wt, L.wt_rows, L.out, L.out, BN / p->cluster));
     L.pg_off = pg;
     pg += (long long)L.out * L.kpad;
     L.bg_off = bg;
@@ -610,14 +611,17 @@ static int prepare(NppPlan* p, long long n) {
 static int g_smem_attr_done = 0;
 static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
   g_smem_attr_done = 1;
   return 0;
 }
 
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
-static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st, int subs_per_stripe) {
+// cluster == 2: CTA pairs (thread-block clusters) share every weight tile through TMA multicast.
+static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st, int subs_per_stripe,
+                        int cluster = 1) {
   CKI(set_smem_attrs());
   ChainParams cp;
   cp.ops = d_ops;
@@ -625,9 +629,28 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
   cp.subs_per_stripe = subs_per_stripe;
-  const int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
-  npp_gemm_kmajor<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
-  CK(cudaGetLastError());
+  int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
+  if (cluster == 1) {
+    npp_gemm_kmajor<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  grid = (grid + cluster - 1) / cluster * cluster;
+  if (grid > num_sms) grid = num_sms / cluster * cluster;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
   return 0;
 }
 
@@ -654,7 +677,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
   }
   {
     ProfScope ps(p, st, PROF_GEMM_FWD, 1);
-    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs));
+    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs, p->cluster));
     ++p->launches;
   }
   if (!with_head) return 0;
@@ -685,13 +708,13 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_GEMM_DGRAD, 1);
-    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st, p->dgrad_subs));
+    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st, p->dgrad_subs, p->cluster));
     ++p->launches;
   }
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
     const int grid = p->n_units < p->num_sms ? p->n_units : p->num_sms;
-    npp_gemm_wgrad<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p->wg_params);
+    npp_gemm_wgrad<<<grid, GEMM_THREADS, WGRAD_SMEM_BYTES, st>>>(p->wg_params);
     CK(cudaGetLastError());
     ++p->launches;
   }
@@ -773,6 +796,7 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   NppPlan* p = new NppPlan();
   p->cfg = *cfg;
   p->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("NPP_CLUSTER")) p->cluster = atoi(e) == 1 ? 1 : 2;
   memset(&p->enc, 0, sizeof(p->enc));
   p->enc.topk = cfg->topk;
   p->enc.n_aug = cfg->n_aug;
@@ -1074,7 +1098,9 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   KmajorParams kp;
   memset(&kp, 0, sizeof(kp));
   CKI(make_map(&kp.tmA[0], a, m, k, k, BM));
-  CKI(make_map(&kp.tmB[0], b, n, k, k, 256));
+  int cluster = 1;
+  if (const char* e = getenv("NPP_CLUSTER")) cluster = atoi(e) == 2 ? 2 : 1;
+  CKI(make_map(&kp.tmB[0], b, n, k, k, 256 / cluster));
   CKI(make_map(&kp.tmOut0, out0, m, n, n, 32));
   if (out1) CKI(make_map(&kp.tmOut1, out1, m, n, n, 32));
   kp.nseg = 1;
@@ -1109,9 +1135,9 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   KmajorParams* d_op = nullptr;
   CK(cudaMalloc(&d_op, ops.size() * sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, ops.data(), ops.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
-  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op));
+  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e0, 0));
-  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op));
+  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e1, 0));
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(ms_out, e0, e1));
@@ -1165,7 +1191,7 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = w.n_units < sms ? w.n_units : sms;
-  npp_gemm_wgrad<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(w);
+  npp_gemm_wgrad<<<grid, GEMM_THREADS, WGRAD_SMEM_BYTES, (cudaStream_t)stream>>>(w);
   cudaError_t e1 = cudaGetLastError();
   cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d_units);
