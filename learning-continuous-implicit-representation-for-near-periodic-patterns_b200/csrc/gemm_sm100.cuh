@@ -27,7 +27,9 @@ constexpr int STAGES = 3;     // chain kernel: 3 x 48 KB ring + 64 KB epilogue s
 constexpr int WG_STAGES = 4;  // wgrad kernel: no staging, deeper ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;    // chain kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int WGRAD_THREADS = 192;   // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
 constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
@@ -131,7 +133,7 @@ struct GemmSmem {
   uint64_t* tfull;
   uint64_t* tempty;
   uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
-  uint32_t* prog;     // [4] per epilogue warp: output sub-tiles (cumulative) whose TMA stores have completed
+  uint32_t* prog;     // [8] per epilogue warp: output sub-tiles (cumulative) whose TMA stores have completed
   uint32_t* tmem_ptr;
 };
 
@@ -150,11 +152,11 @@ __device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
   s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
-  s.tmem_ptr = s.prog + 4;
+  s.tmem_ptr = s.prog + 8;
   return s;
 }
 
-template <int NSTAGES, int CLUSTER = 1>
+template <int NSTAGES, int CLUSTER = 1, int NEPI = 4>
 __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
@@ -163,10 +165,10 @@ __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tfull[i], 1);
-      mbar_init(&s.tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&s.tempty[i], NEPI);  // one arrive per epilogue warp
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
-    for (int i = 0; i < 4; ++i) s.prog[i] = 0;
+    for (int i = 0; i < 8; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
@@ -234,13 +236,19 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq) {
   constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
-  const int lane_base = (warp & 3) * 32;
-  // per-warp staging (4 x 4 KB, 128B-swizzled 32x64 boxes):
-  //   forward : [0],[1] out0 double buffer, [2],[3] out1 (snake derivative) double buffer
-  //   dgrad   : [0..3] the multiplier of the WHOLE tile (fetched during the accumulator wait); each sub-tile's
-  //             result overwrites its multiplier in place and is stored from there
-  uint8_t* wbuf = s.epi + (warp & 3) * EPI_BUFS * EPI_BUF_BYTES;
-  uint64_t* ebar = &s.epi_bar[warp & 3];
+  // Two warps share each TMEM lane quadrant (warps 2..5 take sub-tiles 0 and 1, warps 6..9 take 2 and 3), so the
+  // latency chain of one sub-tile (TMEM load -> math -> fence -> TMA store) overlaps the other warp's work.
+  // Warp e ALWAYS owns staging buffers 2e and 2e+1 of its quadrant, whatever the epilogue type.
+  const int q = warp & 3;
+  const int e = (warp - 2) >> 2;
+  const int lane_base = q * 32;
+  // per-quadrant staging (4 x 4 KB, 128B-swizzled 32x64 boxes):
+  //   snake        : warp e stages out0 in [2e] and out1 (snake derivative) in [2e+1], single-buffered
+  //   linear/dgrad : warp e stages its two sub-tiles in [2e] and [2e+1]
+  //   dgrad * d    : [sub] holds the multiplier of sub-tile `sub` (whole tile fetched during the accumulator wait);
+  //                  the result overwrites it in place and is stored from there
+  uint8_t* qbuf = s.epi + q * EPI_BUFS * EPI_BUF_BYTES;
+  uint64_t* ebar = &s.epi_bar[q];
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const int row0 = m0 + lane_base;
@@ -251,22 +259,24 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   float* colsum = p.colsum;
   float* out_f32 = p.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
-    // all stores of the previous tile were drained at its end, so the four buffers are free
-    if (lane == 0) {
+    // both warps of the quadrant drained their stores at the end of the previous tile; after this barrier the four
+    // buffers are free and the even warp refills them with this tile's multiplier
+    asm volatile("bar.sync %0, 64;" ::"r"(3 + q) : "memory");
+    if (e == 0 && lane == 0) {
       mbar_expect_tx(ebar, NSUB * EPI_BUF_BYTES);
 #pragma unroll
-      for (int q = 0; q < NSUB; ++q) tma_load_2d(wbuf + q * EPI_BUF_BYTES, &p.tmMul, ebar, n0 + q * EPI_COLS, row0);
+      for (int t = 0; t < NSUB; ++t) tma_load_2d(qbuf + t * EPI_BUF_BYTES, &p.tmMul, ebar, n0 + t * EPI_COLS, row0);
     }
   }
   if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
     // bias slice of this tile -> smem once (its load latency hides behind the accumulator wait); the two named
     // barriers order the refill against the other epilogue warps' reads of the previous tile's slice
-    const int et = (warp & 3) * 32 + lane;
-    float2 bv = make_float2(0.f, 0.f);
-    if (bias != nullptr) bv = __ldg(reinterpret_cast<const float2*>(bias + n0) + et);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    reinterpret_cast<float2*>(s.bias)[et] = bv;
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    const int et = (warp - 2) * 32 + lane;  // 0..255
+    float bv = 0.f;
+    if (bias != nullptr) bv = __ldg(bias + n0 + et);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    s.bias[et] = bv;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
   }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
@@ -275,10 +285,10 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
     ld_phase ^= 1;
   }
 #pragma unroll 1
-  for (int sub = 0; sub < NSUB; ++sub) {
+  for (int sub = 2 * e; sub < 2 * e + 2; ++sub) {
     const int col = n0 + sub * EPI_COLS;
-    uint8_t* obuf = wbuf + ((EPI == EPI_DGRAD_MUL) ? sub : (sub & 1)) * EPI_BUF_BYTES;
-    uint8_t* dbuf = wbuf + (2 + (sub & 1)) * EPI_BUF_BYTES;
+    uint8_t* obuf = qbuf + ((EPI == EPI_SNAKE) ? 2 * e : sub) * EPI_BUF_BYTES;
+    uint8_t* dbuf = qbuf + (2 * e + 1) * EPI_BUF_BYTES;
     // both 32-column halves of the sub-tile are fetched from TMEM before either is consumed
     uint32_t raw0[32], raw1[32];
     tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS, raw0);
@@ -312,13 +322,13 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
         for (int i = 0; i < 32; i += 2) {
           float h2[2], d2[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float z = v[i + e];
+          for (int k = 0; k < 2; ++k) {
+            const float z = v[i + k];
             const float w = z + z;
             const float sn = __sinf(w);
             const float cs = __cosf(w);
-            h2[e] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
-            d2[e] = 1.0f + sn;                  // d/dz = 1 + sin 2z
+            h2[k] = fmaf(-0.5f, cs, z + 0.5f);  // z + sin^2 z = z + (1 - cos 2z)/2
+            d2[k] = 1.0f + sn;                  // d/dz = 1 + sin 2z
           }
           hd[i >> 1] = pack_h2(h2[0], h2[1]);
           dd[i >> 1] = pack_h2(d2[0], d2[1]);
@@ -331,19 +341,20 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
             const uint4 m4 = *reinterpret_cast<const uint4*>(obuf + row_off + ((c ^ sw) << 4));
             const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 m2 = unpack_h2(mw[q]);
-              v[8 * j + 2 * q] *= m2.x;
-              v[8 * j + 2 * q + 1] *= m2.y;
+            for (int t = 0; t < 4; ++t) {
+              const float2 m2 = unpack_h2(mw[t]);
+              v[8 * j + 2 * t] *= m2.x;
+              v[8 * j + 2 * t + 1] *= m2.y;
             }
           }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
       }
-      if (EPI != EPI_DGRAD_MUL && half == 0) {
-        // the TMA store issued two sub-tiles ago (same buffers) must have finished reading them
-        if (lane == 0) bulk_wait_read1();
+      if (EPI == EPI_SNAKE && half == 0 && sub == 2 * e + 1) {
+        // snake stages two tensors per sub-tile, so its second sub-tile reuses the buffers of the first: that
+        // store must have finished reading them (all other cases use each buffer once per tile; tiles end drained)
+        if (lane == 0) bulk_wait_read0();
         __syncwarp();
       }
 #pragma unroll
@@ -371,18 +382,18 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
     }
     fence_proxy_async_smem();
     __syncwarp();
-    ++seq;  // cumulative number of sub-tiles this warp has handed to the TMA store engine
     if (lane == 0 && warp_ok) {
       tma_store_2d(&p.tmOut0, obuf, col, row0);
       if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
       bulk_commit();
     }
   }
-  // tile end: drain this warp's stores and publish the whole tile.  The warp would otherwise just wait for the
-  // next accumulator, so the store-completion latency (~1 us) is hidden.
+  seq += NSUB;  // progress is published per tile: all sub-tiles (of both warps of the quadrant) up to here
+  // tile end: drain this warp's stores and publish.  The warp would otherwise just wait for the next accumulator,
+  // so the store-completion latency (~1 us) is mostly hidden.
   if (lane == 0) {
     bulk_wait0();
-    publish_progress(&s.prog[warp & 3], seq);
+    publish_progress(&s.prog[warp - 2], seq);
   }
   __syncwarp();
 }
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   const GemmSmem s = carve_smem_t<STAGES, EPI_STAGE_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue_t<STAGES, CLUSTER>(s, warp);
+  const uint32_t tmem_base = gemm_prologue_t<STAGES, CLUSTER, EPI_WARPS>(s, warp);
   // every CTA of a cluster runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
   const int stripe_iters = (cp.tiles_m + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
@@ -435,13 +446,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                                  &s.full[ps.stage], bk0 + kb * BK, br0 + n0 + (int)crank * (BN / CLUSTER), cmask);
               }
               if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
-                // wait until all four epilogue warps have published this sub-tile, remember how far they are
+                // wait until all eight epilogue warps have published this sub-tile, remember how far they are
                 // (later K blocks usually need no second look) and order the coming TMA loads after the acquire
                 const uint32_t need = need0 + kb;
                 uint32_t ahead = 0x7fffffffu;
-                if (lane < 4) ahead = wait_progress(&s.prog[lane], need) - need;
+                if (lane < EPI_WARPS) ahead = wait_progress(&s.prog[lane], need) - need;
 #pragma unroll
-                for (int o = 2; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
+                for (int o = 4; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
                 seen = need + __shfl_sync(0xffffffffu, ahead, 0);
                 if (lane == 0) fence_proxy_async_all();
                 __syncwarp();
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 }
 
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const GemmSmem s = carve_smem_t<WG_STAGES, 0>(smem_raw);
   const int warp = threadIdx.x >> 5;

@@ -714,7 +714,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
     const int grid = p->n_units < p->num_sms ? p->n_units : p->num_sms;
-    npp_gemm_wgrad<<<grid, GEMM_THREADS, WGRAD_SMEM_BYTES, st>>>(p->wg_params);
+    npp_gemm_wgrad<<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, st>>>(p->wg_params);
     CK(cudaGetLastError());
     ++p->launches;
   }
@@ -1191,7 +1191,7 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = w.n_units < sms ? w.n_units : sms;
-  npp_gemm_wgrad<<<grid, GEMM_THREADS, WGRAD_SMEM_BYTES, (cudaStream_t)stream>>>(w);
+  npp_gemm_wgrad<<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, (cudaStream_t)stream>>>(w);
   cudaError_t e1 = cudaGetLastError();
   cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d_units);
