@@ -137,8 +137,8 @@ int npp_debug_copy(NppPlan* plan, const char* name, int64_t n, float* out, void*
 float npp_debug_grad_scale(NppPlan* plan, void* stream); /* synchronises */
 
 /* Stand-alone tcgen05 GEMM checks (no plan): C[m,n] = A[m,k] . B[n,k]^T (fp16 in, fp32 out) and
- * C[m,n] = A[rows,m]^T . B[rows,n] summed over `splits` row ranges. Dimensions: first: any m (rows are masked), n%256==0,
- * k%64==0; second: m%256==0, n%256==0. */
+ * C[m,n] = A[rows,m]^T . B[rows,n] summed over `splits` row ranges. Dimensions: m%128==0 not required
+ * for the first (rows are masked), n%256==0, k%64==0. */
 int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, void* stream);
 int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, int m, int n, int k, int epi,
                          int iters, float* ms_out);

@@ -24,8 +24,7 @@ constexpr int BN = 256;      // UMMA N
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle atom of halves
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 3;     // chain kernel: 3 x 48 KB ring + 64 KB epilogue staging
-constexpr int WG_STAGES = 3;  // wgrad kernel: 3 x 64 KB ring (256x64 A + 256x64 B per stage)
-constexpr int WG_BM = 256;    // wgrad tile: 256 out-features (two M=128 MMAs sharing B) x 256 in-features
+constexpr int WG_STAGES = 4;  // wgrad kernel: no staging, deeper ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int GEMM_THREADS = 320;    // chain kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
@@ -37,8 +36,7 @@ constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
 constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
-constexpr int WG_A_STAGE_BYTES = WG_BM * BK * 2;  // 32 KB
-constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (WG_A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
 
 enum : int {
   EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
@@ -139,13 +137,13 @@ struct GemmSmem {
   uint32_t* tmem_ptr;
 };
 
-template <int NSTAGES, int EPI_BYTES, int A_BYTES = A_STAGE_BYTES>
+template <int NSTAGES, int EPI_BYTES>
 __device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   uint32_t addr = smem_u32(raw);
   uint8_t* base = raw + ((1024u - (addr & 1023u)) & 1023u);
   GemmSmem s;
   s.a = base;
-  s.b = base + NSTAGES * A_BYTES;
+  s.b = base + NSTAGES * A_STAGE_BYTES;
   s.epi = s.b + NSTAGES * B_STAGE_BYTES;
   s.bias = reinterpret_cast<float*>(s.epi + EPI_BYTES);
   s.full = reinterpret_cast<uint64_t*>(s.bias + (EPI_BYTES ? BN : 0));
@@ -558,12 +556,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
-  // Tile = 256 out-features x 256 in-features per CTA: two M=128 UMMAs per K slice share the B tile, so a stage
-  // carries 64 KB for 1024 MMA cycles (64 B/clk, the per-SM operand ingest rate) instead of 48 KB per 512.
-  // The accumulator fills all 512 TMEM columns ([0,256) = out rows 0..127, [256,512) = rows 128..255); units are
-  // long (tens of K blocks), so the un-overlapped epilogue costs little.
   extern __shared__ uint8_t smem_raw[];
-  const GemmSmem s = carve_smem_t<WG_STAGES, 0, WG_A_STAGE_BYTES>(smem_raw);
+  const GemmSmem s = carve_smem_t<WG_STAGES, 0>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tmem_base = gemm_prologue_t<WG_STAGES>(s, warp);
@@ -581,11 +575,11 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&s.full[ps.stage], WG_A_STAGE_BYTES + B_STAGE_BYTES);
-          uint8_t* sa = s.a + ps.stage * WG_A_STAGE_BYTES;
+          mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          uint8_t* sa = s.a + ps.stage * A_STAGE_BYTES;
           uint8_t* sb = s.b + ps.stage * B_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < WG_BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], un.a_m0 + j * 64, kb * BK);
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], un.a_m0 + j * 64, kb * BK);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mb, &s.full[ps.stage], un.b_n0 + j * 64, kb * BK);
         }
@@ -598,68 +592,65 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
     const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(8192, 1024);
     const int kadv = p.k_adv ? p.k_adv : 2048;
     PipeStateT<WG_STAGES> ps;
+    int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
       const int kb0 = un.split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, kb_total);
-      mbar_wait(&s.tempty[0], acc_phase ^ 1);  // the epilogue has drained the previous unit's accumulator
+      mbar_wait(&s.tempty[acc], acc_phase ^ 1);
       tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.full[ps.stage], ps.phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(s.a + ps.stage * WG_A_STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
-          const uint32_t accum = (kb > kb0) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t bd = umma_desc(b_addr + k * kadv, dhi);
-            // out rows 0..127 (first two 64-wide M atoms) and 128..255 (next two)
-            umma_f16(tmem_base, umma_desc(a_addr + k * kadv, dhi), bd, idesc, accum | (k > 0 ? 1u : 0u));
-            umma_f16(tmem_base + BN, umma_desc(a_addr + 2 * 8192 + k * kadv, dhi), bd, idesc,
-                     accum | (k > 0 ? 1u : 0u));
+            umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&s.empty[ps.stage]);
         }
         __syncwarp();
         ps.advance();
       }
-      if (lane == 0) umma_commit(&s.tfull[0]);
+      if (lane == 0) umma_commit(&s.tfull[acc]);
       __syncwarp();
-      acc_phase ^= 1;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int lane_base = (warp & 3) * 32;
+    int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
       float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off + (size_t)(lane_base + lane) * un.ld;
-      mbar_wait(&s.tfull[0], acc_phase);
+      mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < WG_BM / BM; ++half) {
-        float* orow = out + (size_t)half * BM * un.ld;
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + half * BN + chunk * 32, raw);
-          tmem_ld_wait();
-          if (chunk * 32 < un.ncols_left) {
-            float4* o = reinterpret_cast<float4*>(orow + chunk * 32);
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + acc * BN + chunk * 32, raw);
+        tmem_ld_wait();
+        if (chunk * 32 < un.ncols_left) {
+          float4* o = reinterpret_cast<float4*>(out + chunk * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
-                                 __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
-          }
+          for (int i = 0; i < 8; ++i)
+            o[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                               __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[0]);
-      acc_phase ^= 1;
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   }
   gemm_teardown(tmem_base, warp);

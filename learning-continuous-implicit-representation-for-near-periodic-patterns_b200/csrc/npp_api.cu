@@ -364,11 +364,11 @@ static int alloc_plan_memory(NppPlan* p) {
 
   // split-K factor of the grouped weight-gradient kernel
   int tiles = 0;
-  for (auto& L : p->layers) tiles += (L.out / WG_BM) * ((L.kpad + BN - 1) / BN);
+  for (auto& L : p->layers) tiles += (L.out / BM) * ((L.kpad + BN - 1) / BN);
   int S = p->cfg.wgrad_splits;
   if (S <= 0) {
     double best = -1;
-    for (int s = 3; s <= NPP_MAX_SPLITS; ++s) {
+    for (int s = 3; s <= 10; ++s) {
       const int units = tiles * s;
       const double eff = (double)units / ((double)((units + p->num_sms - 1) / p->num_sms) * p->num_sms);
       if (eff > best + 0.02) {
@@ -471,7 +471,7 @@ static int alloc_plan_memory(NppPlan* p) {
   for (int li = 0; li < nl; ++li) {
     const Layer& L = p->layers[li];
     for (int s = 0; s < S; ++s)
-      for (int m0 = 0; m0 < L.out; m0 += WG_BM)
+      for (int m0 = 0; m0 < L.out; m0 += BM)
         for (int n0 = 0; n0 < L.kpad; n0 += BN) {
           const Seg* sg = nullptr;
           for (auto& g : L.segs)
@@ -1149,7 +1149,7 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
 }
 
 int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int n, int splits, void* stream) {
-  if (m % WG_BM != 0 || n % BN != 0 || splits < 1) return fail("npp_debug_wgrad: m % 256 == 0, n % 256 == 0 required");
+  if (m % BM != 0 || n % BN != 0 || splits < 1) return fail("npp_debug_wgrad: m % 128 == 0, n % 256 == 0 required");
   CKI(set_smem_attrs());
   WgradParams w;
   memset(&w, 0, sizeof(w));
@@ -1157,7 +1157,7 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
   CKI(make_map(&w.maps[1], b, rows, n, n, 64));
   std::vector<WgUnit> units;
   for (int s = 0; s < splits; ++s)
-    for (int m0 = 0; m0 < m; m0 += WG_BM)
+    for (int m0 = 0; m0 < m; m0 += BM)
       for (int n0 = 0; n0 < n; n0 += BN) {
         WgUnit u;
         u.a_map = 0;
