@@ -36,6 +36,8 @@ constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
 constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
+constexpr int PAIR_STAGES = 4;  // cta_group::2: a stage is A 16 KB + half of B 16 KB per CTA
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
 
 enum : int {
@@ -137,14 +139,14 @@ struct GemmSmem {
   uint32_t* tmem_ptr;
 };
 
-template <int NSTAGES, int EPI_BYTES>
+template <int NSTAGES, int EPI_BYTES, int A_BYTES = A_STAGE_BYTES, int B_BYTES = B_STAGE_BYTES>
 __device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   uint32_t addr = smem_u32(raw);
   uint8_t* base = raw + ((1024u - (addr & 1023u)) & 1023u);
   GemmSmem s;
   s.a = base;
-  s.b = base + NSTAGES * A_STAGE_BYTES;
-  s.epi = s.b + NSTAGES * B_STAGE_BYTES;
+  s.b = base + NSTAGES * A_BYTES;
+  s.epi = s.b + NSTAGES * B_BYTES;
   s.bias = reinterpret_cast<float*>(s.epi + EPI_BYTES);
   s.full = reinterpret_cast<uint64_t*>(s.bias + (EPI_BYTES ? BN : 0));
   s.empty = s.full + NSTAGES;
@@ -161,20 +163,23 @@ __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], CLUSTER);  // every CTA of the cluster releases the stage (multicast writes into all)
+      mbar_init(&s.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tfull[i], 1);
-      mbar_init(&s.tempty[i], NEPI);  // one arrive per epilogue warp
+      mbar_init(&s.tempty[i], NEPI * CLUSTER);  // one arrive per epilogue warp of every CTA feeding this accumulator
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
     for (int i = 0; i < 8; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
+  if (warp == 1) {
+    if (CLUSTER == 1) tmem_alloc(s.tmem_ptr, TMEM_COLS);
+    else tmem_alloc_pair(s.tmem_ptr, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();  // peers' barriers exist before anyone multicasts into them
+  if (CLUSTER > 1) cluster_sync_all();  // the peer's barriers exist before anything can signal them
   tc_fence_after();
   return *s.tmem_ptr;
 }
@@ -183,10 +188,11 @@ template <int CLUSTER = 1>
 __device__ __forceinline__ void gemm_teardown(uint32_t tmem_base, int warp) {
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers / write its smem
+  if (CLUSTER > 1) cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CLUSTER == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    else tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -399,21 +405,29 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
 }
 
 // ---------------------------------------------------------------------------------
+// CLUSTER == 1: every CTA is on its own (UMMA cta_group::1, M = 128).
+// CLUSTER == 2: CTA pairs (thread-block cluster of 2 = one TPC) run cta_group::2 UMMAs with M = 256: CTA r owns
+//   row stripe 2p + r, keeps its own A tile and HALF of every weight tile in its shared memory, and the leader
+//   (rank 0) issues the MMAs for both.  Per SM that halves the B bytes written by TMA and read by the tensor core,
+//   which is what lifts the shared-memory-port ceiling of the single-CTA SS-mode mainloop.
 template <int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ ChainParams cp) {
+  constexpr int NST = CLUSTER == 1 ? STAGES : PAIR_STAGES;
+  constexpr int B_BYTES = B_STAGE_BYTES / CLUSTER;       // this CTA's share of a weight tile
+  constexpr int B_ROWS = BN / CLUSTER;
   extern __shared__ uint8_t smem_raw[];
-  const GemmSmem s = carve_smem_t<STAGES, EPI_STAGE_BYTES>(smem_raw);
+  const GemmSmem s = carve_smem_t<NST, EPI_STAGE_BYTES, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue_t<STAGES, CLUSTER, EPI_WARPS>(s, warp);
-  // every CTA of a cluster runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
+  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
+  // every CTA of a pair runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
   const int stripe_iters = (cp.tiles_m + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t cmask = static_cast<uint16_t>((1u << CLUSTER) - 1u);
+  const bool leader = crank == 0;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    PipeState ps;
+    // ------------------------------------------------------------ TMA producer (every CTA)
+    PipeStateT<NST> ps;
     uint32_t stripe_iter = 0;
     uint32_t seen = 0;  // cumulative output sub-tiles known to be complete (minimum over the epilogue warps)
     for (int si = 0; si < stripe_iters; ++si, ++stripe_iter) {
@@ -438,12 +452,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             for (int kb = 0; kb < kbs; ++kb) {
               mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
               if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
-                mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                if (CLUSTER == 1)
-                  tma_load_2d(s.b + ps.stage * B_STAGE_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
-                else  // this CTA fetches 1/CLUSTER of the weight tile and multicasts it to the whole cluster
-                  tma_load_2d_mc(s.b + ps.stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / CLUSTER), &p.tmB[seg],
-                                 &s.full[ps.stage], bk0 + kb * BK, br0 + n0 + (int)crank * (BN / CLUSTER), cmask);
+                if (CLUSTER == 1) {
+                  mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_BYTES);
+                  tma_load_2d(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+                } else {
+                  // the leader's barrier collects the bytes of BOTH CTAs (A + half B each)
+                  if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
+                  tma_load_2d_pair(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK,
+                                   br0 + n0 + (int)crank * B_ROWS);
+                }
               }
               if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
                 // wait until all eight epilogue warps have published this sub-tile, remember how far they are
@@ -458,7 +475,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 __syncwarp();
               }
               if (lane == 0) {
-                tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
+                if (CLUSTER == 1)
+                  tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
+                else
+                  tma_load_2d_pair(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
               }
               __syncwarp();
               ps.advance();
@@ -468,48 +488,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ UMMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-    PipeState ps;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int si = 0; si < stripe_iters; ++si) {
-      for (int oi = 0; oi < cp.n_ops; ++oi) {
-        const KmajorParams& p = cp.ops[oi];
-        const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
-        const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
-        int total_kb = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
-        for (int nt = 0; nt < p.tiles_n; ++nt) {
-          mbar_wait(&s.tempty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int it = 0; it < total_kb; ++it) {
-            mbar_wait(&s.full[ps.stage], ps.phase);
+    // ------------------------------------------------------------ UMMA issuer (pair mode: leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * CLUSTER, BN, 0, 0);
+      constexpr uint16_t pair_mask = 0x3;
+      PipeStateT<NST> ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int si = 0; si < stripe_iters; ++si) {
+        for (int oi = 0; oi < cp.n_ops; ++oi) {
+          const KmajorParams& p = cp.ops[oi];
+          const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
+          const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
+          int total_kb = 0;
+          for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
+          for (int nt = 0; nt < p.tiles_n; ++nt) {
+            mbar_wait(&s.tempty[acc], acc_phase ^ 1);
             tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
-              const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int it = 0; it < total_kb; ++it) {
+              mbar_wait(&s.full[ps.stage], ps.phase);
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+                const uint32_t b_addr = smem_u32(s.b + ps.stage * B_BYTES);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
-                         (it | k) != 0);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  if (CLUSTER == 1)
+                    umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                             (it | k) != 0);
+                  else
+                    umma_f16_pair(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                                  (it | k) != 0);
+                }
+                if (CLUSTER == 1) umma_commit(&s.empty[ps.stage]);
+                else umma_commit_pair(&s.empty[ps.stage], pair_mask);   // frees the stage in both CTAs
               }
-              if (CLUSTER == 1) umma_commit(&s.empty[ps.stage]);
-              else umma_commit_mc(&s.empty[ps.stage], cmask);
+              __syncwarp();
+              ps.advance();
+            }
+            if (lane == 0) {
+              if (CLUSTER == 1) umma_commit(&s.tfull[acc]);
+              else umma_commit_pair(&s.tfull[acc], pair_mask);          // both CTAs' epilogues may read their half
             }
             __syncwarp();
-            ps.advance();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
           }
-          if (lane == 0) umma_commit(&s.tfull[acc]);
-          __syncwarp();
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
         }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------ epilogue warps (every CTA, own 128 rows)
     uint32_t ld_phase = 0;
     uint32_t seq = 0;
     int acc = 0;
@@ -543,11 +573,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s.tempty[acc]);
+          if (lane == 0) {
+            // the accumulator stage is released on the LEADER's barrier (it gates the leader's next UMMAs)
+            if (CLUSTER == 1 || leader) mbar_arrive(&s.tempty[acc]);
+            else mbar_arrive_remote(&s.tempty[acc], 0);
+          }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-
       }
     }
   }

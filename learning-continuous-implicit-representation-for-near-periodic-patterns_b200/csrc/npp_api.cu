@@ -141,7 +141,7 @@ struct NppPlan {
   int n_units = 0;
   int splits_max = 0;
   int num_sms = 148;
-  int cluster = 2;   // CTAs per cluster in the chain kernel (weight tiles are TMA-multicast across it); 1 = off
+  int cluster = 2;   // 2: the chain kernel runs on CTA pairs with cta_group::2 UMMAs; 1: single-CTA UMMAs
 
   bool keep_grads = false;  // fused train step also writes the gradient arena (tests)
   // bound arenas
@@ -612,14 +612,14 @@ static int g_smem_attr_done = 0;
 static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_kmajor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
   g_smem_attr_done = 1;
   return 0;
 }
 
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
-// cluster == 2: CTA pairs (thread-block clusters) share every weight tile through TMA multicast.
+// cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
 static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st, int subs_per_stripe,
                         int cluster = 1) {
   CKI(set_smem_attrs());
@@ -641,7 +641,7 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+  cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
