@@ -24,7 +24,12 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (reference arm, cpu_baseline) must use all host
+# cores, so the BLAS pools are sized before numpy is imported.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -42,6 +47,17 @@ def peaks():
         return p, "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def kernel_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), averaged
+    over its two launches per step (forward chain, dgrad chain).  None if no capture has been recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)["npp_gemm_kmajor"]
+        return 0.5 * (t["forward_chain_bytes"] + t["dgrad_chain_bytes"])
+    except Exception:
+        return None
 
 
 def synthetic_image(res=RES, seed=0):
@@ -332,7 +348,7 @@ def main():
         roofline = {"bound": "tensor", "kernel": "npp_gemm_kmajor (forward + dgrad GEMMs, tcgen05 kind::f16)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": f"{pk_kind} bf16 dense, {'sustained' if sustained else 'burst'} (fp16 and bf16 share the kind::f16 pipe)",
-                    "traffic": None,
+                    "traffic": kernel_traffic(),
                     "launches_per_step": gemm_launches / args.steps,
                     "avg_launch_us": gemm_ms * 1e3 / gemm_launches,
                     "flop_per_launch_avg": flops / gemm_launches,

@@ -588,82 +588,122 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 }
 
 // ---------------------------------------------------------------------------------
+// CLUSTER == 1: one CTA per 128(out) x 256(in) tile.
+// CLUSTER == 2: a CTA pair per 256(out) x 256(in) tile with cta_group::2 UMMAs: CTA r owns out rows
+//   [m0 + 128 r, +128) (its own delta columns as A) and loads only half of the activation tile (B columns
+//   [n0 + 128 r, +128)), so a pair moves 64 KB per K block for twice the MMA work (the single-CTA kernel is L2
+//   bandwidth bound: 1.5 GB of operand reads per step at 16 k rows).
+constexpr int WG_PAIR_STAGES = 5;
+constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 256 + 1024;
+
+template <int CLUSTER>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
+  constexpr int NST = CLUSTER == 1 ? WG_STAGES : WG_PAIR_STAGES;
+  constexpr int B_BYTES = B_STAGE_BYTES / CLUSTER;
+  constexpr int B_COLS = BN / CLUSTER;
   extern __shared__ uint8_t smem_raw[];
-  const GemmSmem s = carve_smem_t<WG_STAGES, 0>(smem_raw);
+  const GemmSmem s = carve_smem_t<NST, 0, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue_t<WG_STAGES>(s, warp);
+  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4>(s, warp);
   const int kb_total = (p.rows + BK - 1) / BK;
+  const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int unit0 = (int)blockIdx.x / CLUSTER;      // both CTAs of a pair walk the same unit list
+  const int ustride = (int)gridDim.x / CLUSTER;
 
   if (warp == 0) {
-    PipeStateT<WG_STAGES> ps;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    PipeStateT<NST> ps;
+    for (int u = unit0; u < p.n_units; u += ustride) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
       const int kb0 = un.split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, kb_total);
       const CUtensorMap* ma = &p.maps[un.a_map];
       const CUtensorMap* mb = &p.maps[un.b_map];
+      const int am0 = un.a_m0 + (int)crank * BM;
+      const int bn0 = un.b_n0 + (int)crank * B_COLS;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = s.a + ps.stage * A_STAGE_BYTES;
-          uint8_t* sb = s.b + ps.stage * B_STAGE_BYTES;
+          uint8_t* sb = s.b + ps.stage * B_BYTES;
+          if (CLUSTER == 1) {
+            mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_BYTES);
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], un.a_m0 + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], am0 + j * 64, kb * BK);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mb, &s.full[ps.stage], un.b_n0 + j * 64, kb * BK);
+            for (int j = 0; j < B_COLS / 64; ++j) tma_load_2d(sb + j * 8192, mb, &s.full[ps.stage], bn0 + j * 64, kb * BK);
+          } else {
+            if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_pair(sa + j * 8192, ma, &s.full[ps.stage], am0 + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < B_COLS / 64; ++j)
+              tma_load_2d_pair(sb + j * 8192, mb, &s.full[ps.stage], bn0 + j * 64, kb * BK);
+          }
         }
         __syncwarp();
         ps.advance();
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 1, 1);
-    const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(8192, 1024);
-    const int kadv = p.k_adv ? p.k_adv : 2048;
-    PipeStateT<WG_STAGES> ps;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const WgUnit un = p.units[u];
-      if (un.split >= p.n_splits) continue;
-      const int kb0 = un.split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, kb_total);
-      mbar_wait(&s.tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&s.full[ps.stage], ps.phase);
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * CLUSTER, BN, 1, 1);
+      constexpr uint16_t pair_mask = 0x3;
+      const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(8192, 1024);
+      const int kadv = p.k_adv ? p.k_adv : 2048;
+      PipeStateT<NST> ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = unit0; u < p.n_units; u += ustride) {
+        const WgUnit un = p.units[u];
+        if (un.split >= p.n_splits) continue;
+        const int kb0 = un.split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+        mbar_wait(&s.tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(s.b + ps.stage * B_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&s.full[ps.stage], ps.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(s.b + ps.stage * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (CLUSTER == 1)
+                umma_f16(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc, accum);
+              else
+                umma_f16_pair(d_tmem, umma_desc(a_addr + k * kadv, dhi), umma_desc(b_addr + k * kadv, dhi), idesc,
+                              accum);
+            }
+            if (CLUSTER == 1) umma_commit(&s.empty[ps.stage]);
+            else umma_commit_pair(&s.empty[ps.stage], pair_mask);
           }
-          umma_commit(&s.empty[ps.stage]);
+          __syncwarp();
+          ps.advance();
+        }
+        if (lane == 0) {
+          if (CLUSTER == 1) umma_commit(&s.tfull[acc]);
+          else umma_commit_pair(&s.tfull[acc], pair_mask);
         }
         __syncwarp();
-        ps.advance();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      if (lane == 0) umma_commit(&s.tfull[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int lane_base = (warp & 3) * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = unit0; u < p.n_units; u += ustride) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
-      float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off + (size_t)(lane_base + lane) * un.ld;
+      float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off +
+                   (size_t)((int)crank * BM + lane_base + lane) * un.ld;
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -681,12 +721,15 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      if (lane == 0) {
+        if (CLUSTER == 1 || leader) mbar_arrive(&s.tempty[acc]);
+        else mbar_arrive_remote(&s.tempty[acc], 0);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
-  gemm_teardown(tmem_base, warp);
+  gemm_teardown<CLUSTER>(tmem_base, warp);
 }
 
 }  // namespace npp

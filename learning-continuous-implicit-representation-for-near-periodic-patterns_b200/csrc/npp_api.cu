@@ -142,6 +142,7 @@ struct NppPlan {
   int splits_max = 0;
   int num_sms = 148;
   int cluster = 2;   // 2: the chain kernel runs on CTA pairs with cta_group::2 UMMAs; 1: single-CTA UMMAs
+  int wg_cluster = 2;  // same choice for the weight-gradient kernel (256 x 256 tile per CTA pair)
 
   bool keep_grads = false;  // fused train step also writes the gradient arena (tests)
   // bound arenas
@@ -364,13 +365,15 @@ static int alloc_plan_memory(NppPlan* p) {
 
   // split-K factor of the grouped weight-gradient kernel
   int tiles = 0;
-  for (auto& L : p->layers) tiles += (L.out / BM) * ((L.kpad + BN - 1) / BN);
+  const int wg_bm = BM * p->wg_cluster;   // out-features per work unit (a CTA pair covers 256)
+  for (auto& L : p->layers) tiles += (L.out / wg_bm) * ((L.kpad + BN - 1) / BN);
   int S = p->cfg.wgrad_splits;
   if (S <= 0) {
     double best = -1;
     for (int s = 3; s <= 10; ++s) {
       const int units = tiles * s;
-      const double eff = (double)units / ((double)((units + p->num_sms - 1) / p->num_sms) * p->num_sms);
+      const int slots = p->num_sms / p->wg_cluster;
+      const double eff = (double)units / ((double)((units + slots - 1) / slots) * slots);
       if (eff > best + 0.02) {
         best = eff;
         S = s;
@@ -471,7 +474,7 @@ static int alloc_plan_memory(NppPlan* p) {
   for (int li = 0; li < nl; ++li) {
     const Layer& L = p->layers[li];
     for (int s = 0; s < S; ++s)
-      for (int m0 = 0; m0 < L.out; m0 += BM)
+      for (int m0 = 0; m0 < L.out; m0 += wg_bm)
         for (int n0 = 0; n0 < L.kpad; n0 += BN) {
           const Seg* sg = nullptr;
           for (auto& g : L.segs)
@@ -613,7 +616,8 @@ static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_PAIR_SMEM_BYTES));
   g_smem_attr_done = 1;
   return 0;
 }
@@ -651,6 +655,32 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
+  return 0;
+}
+
+static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int cluster) {
+  CKI(set_smem_attrs());
+  if (cluster == 1) {
+    const int grid = w.n_units < num_sms ? w.n_units : num_sms;
+    npp_gemm_wgrad<1><<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, st>>>(w);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  int grid = 2 * w.n_units < num_sms ? 2 * w.n_units : num_sms / 2 * 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WGRAD_THREADS);
+  cfg.dynamicSmemBytes = WGRAD_PAIR_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, npp_gemm_wgrad<2>, w));
   return 0;
 }
 
@@ -713,9 +743,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
-    const int grid = p->n_units < p->num_sms ? p->n_units : p->num_sms;
-    npp_gemm_wgrad<<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, st>>>(p->wg_params);
-    CK(cudaGetLastError());
+    CKI(launch_wgrad(p->wg_params, p->num_sms, st, p->wg_cluster));
     ++p->launches;
   }
   if (finalize) {
@@ -797,6 +825,7 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   p->cfg = *cfg;
   p->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("NPP_CLUSTER")) p->cluster = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("NPP_WG_CLUSTER")) p->wg_cluster = atoi(e) == 1 ? 1 : 2;
   memset(&p->enc, 0, sizeof(p->enc));
   p->enc.topk = cfg->topk;
   p->enc.n_aug = cfg->n_aug;
@@ -1149,7 +1178,10 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
 }
 
 int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int n, int splits, void* stream) {
-  if (m % BM != 0 || n % BN != 0 || splits < 1) return fail("npp_debug_wgrad: m % 128 == 0, n % 256 == 0 required");
+  int wg_cluster = 2;
+  if (const char* e = getenv("NPP_WG_CLUSTER")) wg_cluster = atoi(e) == 1 ? 1 : 2;
+  if (m % (BM * wg_cluster) != 0 || n % BN != 0 || splits < 1)
+    return fail("npp_debug_wgrad: m % 256 == 0 (128 with NPP_WG_CLUSTER=1), n % 256 == 0 required");
   CKI(set_smem_attrs());
   WgradParams w;
   memset(&w, 0, sizeof(w));
@@ -1157,7 +1189,7 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
   CKI(make_map(&w.maps[1], b, rows, n, n, 64));
   std::vector<WgUnit> units;
   for (int s = 0; s < splits; ++s)
-    for (int m0 = 0; m0 < m; m0 += BM)
+    for (int m0 = 0; m0 < m; m0 += BM * wg_cluster)
       for (int n0 = 0; n0 < n; n0 += BN) {
         WgUnit u;
         u.a_map = 0;
@@ -1190,9 +1222,8 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = w.n_units < sms ? w.n_units : sms;
-  npp_gemm_wgrad<<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, (cudaStream_t)stream>>>(w);
-  cudaError_t e1 = cudaGetLastError();
+  int r = launch_wgrad(w, sms, (cudaStream_t)stream, wg_cluster);
+  cudaError_t e1 = r ? cudaErrorUnknown : cudaGetLastError();
   cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(d_units);
   CK(e1);

@@ -24,7 +24,7 @@ def one(kind):
             err = ((c - ref).abs().max() / ref.abs().max()).item()
             print(f"KM m={m} n={n} k={k} rel_err={err:.3e} nan={int(torch.isnan(c).sum())}", flush=True)
     else:
-        for (rows, m, n, s) in [(64, 128, 256, 1), (128, 128, 256, 1), (1000, 256, 512, 3)]:
+        for (rows, m, n, s) in [(64, 256, 256, 1), (128, 256, 256, 1), (1000, 256, 512, 3)]:
             a = torch.randn(rows, m, device="cuda").half()
             b = torch.randn(rows, n, device="cuda").half()
             c = torch.full((s, m, n), float("nan"), device="cuda")

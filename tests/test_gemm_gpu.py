@@ -24,7 +24,7 @@ def test_kmajor_gemm(native, m, n, k):
     assert _rel(c, ref) < 1e-4
 
 
-@pytest.mark.parametrize("rows,m,n,splits", [(64, 128, 256, 1), (512, 128, 256, 1), (1000, 256, 512, 3), (16384, 512, 1024, 6), (4100, 512, 512, 7)])
+@pytest.mark.parametrize("rows,m,n,splits", [(64, 256, 256, 1), (512, 256, 256, 1), (1000, 256, 512, 3), (16384, 512, 1024, 6), (4100, 512, 512, 7)])
 def test_wgrad_gemm(native, rows, m, n, splits):
     torch.manual_seed(0)
     a = torch.randn(rows, m, device="cuda").half()
