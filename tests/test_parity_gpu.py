@@ -334,3 +334,64 @@ def test_psnr_after_training_matches_oracle():
     _report("psnr", {"psnr_cuda_db": float(a), "psnr_oracle_db": float(b), "steps": 120, "rows_per_step": n})
     assert b > 15.0, b                     # the fit actually learned something
     assert abs(a - b) < 0.1, (a, b)
+
+
+@pytest.mark.parametrize("topk,n,binary_mask", [(3, 26624, True), (1, 16384, False)])
+def test_other_baseline_configs_follow_oracle(topk, n, binary_mask):
+    """Shapes of BASELINE.json configs 3 and 5: segmentation 1024^2 (K=3, 8192 + 2*96^2 = 26624 rows, 0/1 loss mask)
+    and one of the 192 independent K=1 fits (16384 rows).  Two train steps against the oracle."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(11)
+    res = (1024, 1024) if topk == 3 else (512, 512)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(res, ANGLES[:topk], [[p * 2 for p in q] for q in PERIODS[:topk]], freqs)
+    plan = Plan(enc, max_rows=n)
+    params = O.init_params(rng, topk=topk)
+    plan.load_state(params)
+    coords = np.stack([rng.integers(0, res[0], n), rng.integers(0, res[1], n)], 1).astype(np.float32)
+    target = rng.random((n, 3), dtype=np.float32)
+    mask = (rng.random((n, 1)) > 0.2).astype(np.float32) if binary_mask else np.ones((n, 1), np.float32)
+    tabs = [(enc.cos_t[j], enc.sin_t[j], enc.period[j]) for j in range(topk)]
+    e = O.encode(coords, tabs, freqs, res)
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    cd, td, md = (torch.from_numpy(a).cuda() for a in (coords, target, mask))
+    loss_d = torch.zeros((), device="cuda")
+    for step in (1, 2):
+        plan.train_step(cd, td, md, 5e-4, loss_d, step=step)
+        ref_loss, _ = O.train_step(p, m, v, step, e, target, mask, 5e-4, topk_model=topk > 1)
+        assert abs(loss_d.item() - ref_loss) < 1e-3 * ref_loss, (step, loss_d.item(), ref_loss)
+    got = plan.state()
+    for k in plan.grad_views():
+        assert np.abs(got[k].cpu().numpy() - p[k]).max() < 1.1e-3, k      # two Adam steps of 5e-4
+
+
+def test_full_size_batch_additivity():
+    """Size-independent property at BASELINE config 4's full size (2^18 rows, 2048^2 image): the gradient of a batch
+    equals the sum of the gradients of its two halves when both are normalised by the global row count -- exactly
+    what the data-parallel path relies on.  fp32 summation order differs, hence the 1e-4 relative bound."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(5)
+    n = 1 << 18
+    res = (2048, 2048)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(res, ANGLES, [[p * 4 for p in q] for q in PERIODS], freqs)
+    plan = Plan(enc, max_rows=n)
+    plan.load_state(O.init_params(rng, topk=3))
+    coords = torch.stack([torch.randint(0, res[0], (n,)), torch.randint(0, res[1], (n,))], 1).float().cuda()
+    target = torch.rand(n, 3, device="cuda")
+
+    def grads(lo, hi):
+        logits = plan.forward(coords[lo:hi])
+        assert torch.isfinite(logits).all()
+        _, g, _ = plan.mse(logits, target[lo:hi], None, n_norm=n)
+        plan.backward(hi - lo, g)
+        return plan.grads[: plan.trained_floats].clone()
+
+    full = grads(0, n)
+    halves = grads(0, n // 2) + grads(n // 2, n)
+    rel = ((full - halves).norm() / full.norm()).item()
+    assert full.abs().max() > 0 and rel < 1e-4, rel
