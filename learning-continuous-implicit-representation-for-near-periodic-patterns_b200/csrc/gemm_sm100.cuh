@@ -240,7 +240,8 @@ __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
-                                              uint64_t* tfull, uint32_t acc_phase, uint32_t& seq) {
+                                              uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
+                                              bool last_tile_of_op, uint32_t& deferred_seq) {
   constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
   // Two warps share each TMEM lane quadrant (warps 2..5 take sub-tiles 0 and 1, warps 6..9 take 2 and 3), so the
   // latency chain of one sub-tile (TMEM load -> math -> fence -> TMA store) overlaps the other warp's work.
@@ -264,9 +265,13 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   const float* bias = p.bias;
   float* colsum = p.colsum;
   float* out_f32 = p.out_f32;
+  // a previous tile may have deferred its drain: its TMA stores must at least have finished READING the staging
+  // buffers before this tile reuses them (cheap: they were issued a whole accumulator wait ago)
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
   if (EPI == EPI_DGRAD_MUL) {
-    // both warps of the quadrant drained their stores at the end of the previous tile; after this barrier the four
-    // buffers are free and the even warp refills them with this tile's multiplier
+    // after this barrier both warps of the quadrant are done with the previous tile's buffers and the even warp
+    // refills all four with this tile's multiplier
     asm volatile("bar.sync %0, 64;" ::"r"(3 + q) : "memory");
     if (e == 0 && lane == 0) {
       mbar_expect_tx(ebar, NSUB * EPI_BUF_BYTES);
@@ -388,20 +393,32 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && warp_ok) {
-      tma_store_2d(&p.tmOut0, obuf, col, row0);
-      if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
-      bulk_commit();
+    if (lane == 0) {
+      if (warp_ok) {
+        tma_store_2d(&p.tmOut0, obuf, col, row0);
+        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
+        bulk_commit();
+      }
+      if (deferred_seq != 0) {
+        // the previous tile of this op skipped its drain: by now its stores (every group but the one just
+        // committed) have long completed, so publishing them costs nothing
+        if (warp_ok) bulk_wait1();
+        publish_progress(&s.prog[warp - 2], deferred_seq);
+      }
     }
+    deferred_seq = 0;
   }
   seq += NSUB;  // progress is published per tile: all sub-tiles (of both warps of the quadrant) up to here
-  // tile end: drain this warp's stores and publish.  The warp would otherwise just wait for the next accumulator,
-  // so the store-completion latency (~1 us) is mostly hidden.
-  if (lane == 0) {
-    bulk_wait0();
-    publish_progress(&s.prog[warp - 2], seq);
+  if (last_tile_of_op) {
+    // the next op's K blocks 4.. wait for exactly this: drain the stores (~1 us) and publish right away
+    if (lane == 0) {
+      bulk_wait0();
+      publish_progress(&s.prog[warp - 2], seq);
+    }
+    __syncwarp();
+  } else {
+    deferred_seq = seq;  // published from inside the next tile of the same op (nobody is waiting for it yet)
   }
-  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------
@@ -542,6 +559,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     // ------------------------------------------------------------ epilogue warps (every CTA, own 128 rows)
     uint32_t ld_phase = 0;
     uint32_t seq = 0;
+    uint32_t deferred = 0;  // progress value of a tile whose drain + publish was deferred into the next tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int si = 0; si < stripe_iters; ++si) {
@@ -557,18 +575,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         for (int nt = 0; nt < p.tiles_n; ++nt) {
           const uint32_t tacc = tmem_base + acc * BN;
           const int n0 = nt * BN;
+          const bool last = nt == p.tiles_n - 1;
           switch (epi) {
             case EPI_LINEAR:
-              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
+              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
               break;
             case EPI_SNAKE:
-              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
+              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
               break;
             case EPI_DGRAD_MUL:
-              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
+              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
               break;
             default:
-              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq);
+              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
               break;
           }
           tc_fence_before();
