@@ -36,6 +36,7 @@ constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
 constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
+constexpr int STRIPE_GROUP = 2;  // stripes a CTA interleaves op by op when it owns more than one
 constexpr int PAIR_STAGES = 4;  // cta_group::2: a stage is A 16 KB + half of B 16 KB per CTA
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
@@ -445,11 +446,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
     PipeStateT<NST> ps;
-    uint32_t stripe_iter = 0;
-    uint32_t seen = 0;  // cumulative output sub-tiles known to be complete (minimum over the epilogue warps)
-    for (int si = 0; si < stripe_iters; ++si, ++stripe_iter) {
-      const int m0 = (si * (int)gridDim.x + (int)blockIdx.x) * BM;
-      const uint32_t stripe_base = stripe_iter * static_cast<uint32_t>(cp.subs_per_stripe);
+    uint32_t seen = 0;        // cumulative output sub-tiles known to be complete (minimum over the epilogue warps)
+    uint32_t group_base = 0;  // sub-tiles published by the stripe groups before the current one
+    for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
+      // A CTA that owns several stripes walks them two at a time, op by op (op -> stripe -> tile): while one
+      // stripe waits for its previous op's last tile to be stored and reloaded, the other one's MMAs run.
+      const int gi = min(STRIPE_GROUP, stripe_iters - si);
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
@@ -459,50 +461,60 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           }
         }
         const int nseg = p.nseg;
-        for (int nt = 0; nt < p.tiles_n; ++nt) {
-          const int n0 = nt * BN;
-          for (int seg = 0; seg < nseg; ++seg) {
-            const int kbs = p.kblocks[seg], ak0 = p.a_k0[seg], bk0 = p.b_k0[seg], br0 = p.b_row0[seg];
-            const int src = p.a_src[seg];
-            // K block kb of this segment is the 64-column sub-tile (ak0/64 + kb) written by op `src`
-            const uint32_t need0 = src >= 0 ? stripe_base + cp.ops[src].sub_base + ak0 / BK + 1 : 0u;
-            for (int kb = 0; kb < kbs; ++kb) {
-              mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
-              if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
-                if (CLUSTER == 1) {
-                  mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_BYTES);
-                  tma_load_2d(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
-                } else {
-                  // the leader's barrier collects the bytes of BOTH CTAs (A + half B each)
-                  if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
-                  tma_load_2d_pair(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK,
-                                   br0 + n0 + (int)crank * B_ROWS);
+        for (int sl = 0; sl < gi; ++sl) {
+          const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
+          for (int nt = 0; nt < p.tiles_n; ++nt) {
+            const int n0 = nt * BN;
+            for (int seg = 0; seg < nseg; ++seg) {
+              const int kbs = p.kblocks[seg], ak0 = p.a_k0[seg], bk0 = p.b_k0[seg], br0 = p.b_row0[seg];
+              const int src = p.a_src[seg];
+              // K block kb of this segment is the 64-column block (ak0/64 + kb) that op `src` wrote for the same
+              // stripe; in processing order that op's tiles come after gi * sub_base[src] sub-tiles of this group
+              // and after the sl earlier stripes of the op
+              uint32_t need0 = 0;
+              if (src >= 0)
+                need0 = group_base + (uint32_t)gi * cp.ops[src].sub_base +
+                        (uint32_t)sl * (uint32_t)(cp.ops[src].tiles_n * (BN / EPI_COLS)) + ak0 / BK + 1;
+              for (int kb = 0; kb < kbs; ++kb) {
+                mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+                if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
+                  if (CLUSTER == 1) {
+                    mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_BYTES);
+                    tma_load_2d(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+                  } else {
+                    // the leader's barrier collects the bytes of BOTH CTAs (A + half B each)
+                    if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
+                    tma_load_2d_pair(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK,
+                                     br0 + n0 + (int)crank * B_ROWS);
+                  }
                 }
-              }
-              if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
-                // wait until all eight epilogue warps have published this sub-tile, remember how far they are
-                // (later K blocks usually need no second look) and order the coming TMA loads after the acquire
-                const uint32_t need = need0 + kb;
-                uint32_t ahead = 0x7fffffffu;
-                if (lane < EPI_WARPS) ahead = wait_progress(&s.prog[lane], need) - need;
+                if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
+                  // wait until all eight epilogue warps have published this block, remember how far they are
+                  // (later K blocks usually need no second look) and order the coming TMA loads after the acquire
+                  const uint32_t need = need0 + kb;
+                  uint32_t ahead = 0x7fffffffu;
+                  if (lane < EPI_WARPS) ahead = wait_progress(&s.prog[lane], need) - need;
 #pragma unroll
-                for (int o = 4; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
-                seen = need + __shfl_sync(0xffffffffu, ahead, 0);
-                if (lane == 0) fence_proxy_async_all();
+                  for (int o = 4; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
+                  seen = need + __shfl_sync(0xffffffffu, ahead, 0);
+                  if (lane == 0) fence_proxy_async_all();
+                  __syncwarp();
+                }
+                if (lane == 0) {
+                  if (CLUSTER == 1)
+                    tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
+                  else
+                    tma_load_2d_pair(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK,
+                                     m0);
+                }
                 __syncwarp();
+                ps.advance();
               }
-              if (lane == 0) {
-                if (CLUSTER == 1)
-                  tma_load_2d(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
-                else
-                  tma_load_2d_pair(s.a + ps.stage * A_STAGE_BYTES, &p.tmA[seg], &s.full[ps.stage], ak0 + kb * BK, m0);
-              }
-              __syncwarp();
-              ps.advance();
             }
           }
         }
       }
+      group_base += (uint32_t)gi * (uint32_t)cp.subs_per_stripe;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer (pair mode: leader CTA only)
@@ -512,14 +524,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       PipeStateT<NST> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int si = 0; si < stripe_iters; ++si) {
+      for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
+        const int gi = min(STRIPE_GROUP, stripe_iters - si);
         for (int oi = 0; oi < cp.n_ops; ++oi) {
           const KmajorParams& p = cp.ops[oi];
           const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
           const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
           int total_kb = 0;
           for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
-          for (int nt = 0; nt < p.tiles_n; ++nt) {
+          for (int tile = 0; tile < gi * p.tiles_n; ++tile) {
             mbar_wait(&s.tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -562,8 +575,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     uint32_t deferred = 0;  // progress value of a tile whose drain + publish was deferred into the next tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int si = 0; si < stripe_iters; ++si) {
-      const int m0 = (si * (int)gridDim.x + (int)blockIdx.x) * BM;
+    for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
+      const int gi = min(STRIPE_GROUP, stripe_iters - si);
+      const bool final_group = si + gi >= stripe_iters;
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
@@ -572,33 +586,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           if (p.epi == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
         }
         const int epi = p.epi;
-        for (int nt = 0; nt < p.tiles_n; ++nt) {
-          const uint32_t tacc = tmem_base + acc * BN;
-          const int n0 = nt * BN;
-          const bool last = nt == p.tiles_n - 1;
-          switch (epi) {
-            case EPI_LINEAR:
-              epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
-              break;
-            case EPI_SNAKE:
-              epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
-              break;
-            case EPI_DGRAD_MUL:
-              epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
-              break;
-            default:
-              epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq, last, deferred);
-              break;
+        for (int sl = 0; sl < gi; ++sl) {
+          const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
+          for (int nt = 0; nt < p.tiles_n; ++nt) {
+            const uint32_t tacc = tmem_base + acc * BN;
+            const int n0 = nt * BN;
+            // Publish right away only when somebody is about to wait for it: a lone stripe's last tile of an op
+            // (its next op is next in line) and the very last tile of the kernel.  Everything else is published
+            // from inside the following tile (the consumer of an interleaved stripe comes a whole stripe later).
+            const bool last_of_stripe_op = nt == p.tiles_n - 1;
+            const bool last = (gi == 1 && last_of_stripe_op) ||
+                              (final_group && oi == cp.n_ops - 1 && sl == gi - 1 && last_of_stripe_op);
+            switch (epi) {
+              case EPI_LINEAR:
+                epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                                          last, deferred);
+                break;
+              case EPI_SNAKE:
+                epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                                         last, deferred);
+                break;
+              case EPI_DGRAD_MUL:
+                epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
+                                             seq, last, deferred);
+                break;
+              default:
+                epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                                         last, deferred);
+                break;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              // the accumulator stage is released on the LEADER's barrier (it gates the leader's next UMMAs)
+              if (CLUSTER == 1 || leader) mbar_arrive(&s.tempty[acc]);
+              else mbar_arrive_remote(&s.tempty[acc], 0);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            // the accumulator stage is released on the LEADER's barrier (it gates the leader's next UMMAs)
-            if (CLUSTER == 1 || leader) mbar_arrive(&s.tempty[acc]);
-            else mbar_arrive_remote(&s.tempty[acc], 0);
-          }
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
         }
       }
     }
