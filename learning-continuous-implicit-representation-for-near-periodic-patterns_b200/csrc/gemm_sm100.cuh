@@ -36,7 +36,8 @@ constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
 constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
 constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
-constexpr int STRIPE_GROUP = 2;  // stripes a CTA interleaves op by op when it owns more than one
+constexpr int STRIPE_GROUP = 1;  // stripes a CTA interleaves op by op (2 was measured neutral: large batches are
+                                 // bound by the snake epilogue's MUFU rate, not by dependency bubbles)
 constexpr int PAIR_STAGES = 4;  // cta_group::2: a stage is A 16 KB + half of B 16 KB per CTA
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
 constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;

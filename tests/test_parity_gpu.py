@@ -74,7 +74,7 @@ def _segments(plan, name, c):
     return c["a"][name]
 
 
-@pytest.mark.parametrize("topk,n", [(3, 1000), (1, 777), (3, 128), (3, 1), (1, 129)])
+@pytest.mark.parametrize("topk,n", [(3, 1000), (1, 777), (3, 128), (3, 1), (1, 129), (2, 300)])
 def test_forward_backward_parity(topk, n):
     """Two checks per layer, forward and backward:
       per-layer : the layer applied to exactly the inputs the kernel consumed (our fp16 buffers) with the
@@ -191,6 +191,33 @@ def test_forward_backward_parity(topk, n):
             assert v < TOL_CUM, (sect, k, v)
     # the network output itself (what the PSNR is computed from) stays within the north_star bound
     assert rep["fwd_cum"]["rgb_linear"] < TOL
+
+
+def test_shallow_network_depth4():
+    """netdepth is a plan parameter: D=4 with the skip after layer 1 (forward + backward against the oracle)."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(2)
+    n, topk, depth, skips = 500, 3, 4, (1,)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(RES, ANGLES, PERIODS, freqs)
+    plan = Plan(enc, depth=depth, skip_layer=skips[0], max_rows=n)
+    params = O.init_params(rng, topk=topk, depth=depth, skips=skips)
+    plan.load_state(params)
+    coords = np.stack([rng.integers(0, RES[0], n), rng.integers(0, RES[1], n)], 1).astype(np.float32)
+    tabs = [(enc.cos_t[j], enc.sin_t[j], enc.period[j]) for j in range(topk)]
+    e = O.encode(coords, tabs, freqs, RES)
+    logits_ref, c = O.forward(params, e, depth=depth, skips=skips)
+    logits = plan.forward(torch.from_numpy(coords).cuda())
+    assert rel(logits.cpu().numpy(), logits_ref) < TOL
+    target = rng.random((n, 3), dtype=np.float32)
+    g = O.mse_l2_grad_logits(logits_ref, target)
+    grads_ref, _ = O.backward(params, c, g, depth=depth, skips=skips)
+    plan.backward(n, torch.from_numpy(g).cuda())
+    gv = plan.grad_views()
+    assert sorted(gv) == sorted(grads_ref)
+    for k, ref in grads_ref.items():
+        assert rel(gv[k].cpu().numpy(), ref) < 2e-3, k
 
 
 def test_mse_kernel():
