@@ -88,6 +88,7 @@ struct ChainParams {
   int M;
   int tiles_m;
   int subs_per_stripe;  // output sub-tiles all ops write per stripe
+  long long* dbg;       // optional (tests): per-tile clock64 stamps of CTA 0 / warp 2: wait-begin, acc-ready, subs-done, tile-done
 };
 
 struct WgUnit {
@@ -243,8 +244,10 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
-                                              bool last_tile_of_op, uint32_t& deferred_seq) {
+                                              bool last_tile_of_op, uint32_t& deferred_seq, long long* dbg) {
   constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
+  const bool stamp = dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+  if (stamp) dbg[0] = clock64();
   // Two warps share each TMEM lane quadrant (warps 2..5 take sub-tiles 0 and 1, warps 6..9 take 2 and 3), so the
   // latency chain of one sub-tile (TMEM load -> math -> fence -> TMA store) overlaps the other warp's work.
   // Warp e ALWAYS owns staging buffers 2e and 2e+1 of its quadrant, whatever the epilogue type.
@@ -293,6 +296,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
+  if (stamp) dbg[1] = clock64();
   if (EPI == EPI_DGRAD_MUL) {
     mbar_wait(ebar, ld_phase);
     ld_phase ^= 1;
@@ -411,6 +415,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
     deferred_seq = 0;
   }
   seq += NSUB;  // progress is published per tile: all sub-tiles (of both warps of the quadrant) up to here
+  if (stamp) dbg[2] = clock64();
   if (last_tile_of_op) {
     // the next op's K blocks 4.. wait for exactly this: drain the stores (~1 us) and publish right away
     if (lane == 0) {
@@ -421,6 +426,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
   } else {
     deferred_seq = seq;  // published from inside the next tile of the same op (nobody is waiting for it yet)
   }
+  if (stamp) dbg[3] = clock64();
 }
 
 // ---------------------------------------------------------------------------------
@@ -574,6 +580,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     uint32_t ld_phase = 0;
     uint32_t seq = 0;
     uint32_t deferred = 0;  // progress value of a tile whose drain + publish was deferred into the next tile
+    int tile_counter = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
@@ -595,25 +602,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             // Publish right away only when somebody is about to wait for it: a lone stripe's last tile of an op
             // (its next op is next in line) and the very last tile of the kernel.  Everything else is published
             // from inside the following tile (the consumer of an interleaved stripe comes a whole stripe later).
+            long long* dbgp = cp.dbg ? cp.dbg + 4 * tile_counter : nullptr;
+            ++tile_counter;
             const bool last_of_stripe_op = nt == p.tiles_n - 1;
             const bool last = (gi == 1 && last_of_stripe_op) ||
                               (final_group && oi == cp.n_ops - 1 && sl == gi - 1 && last_of_stripe_op);
             switch (epi) {
               case EPI_LINEAR:
                 epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                          last, deferred);
+                                          last, deferred, dbgp);
                 break;
               case EPI_SNAKE:
                 epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred);
+                                         last, deferred, dbgp);
                 break;
               case EPI_DGRAD_MUL:
                 epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
-                                             seq, last, deferred);
+                                             seq, last, deferred, dbgp);
                 break;
               default:
                 epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred);
+                                         last, deferred, dbgp);
                 break;
             }
             tc_fence_before();

@@ -611,6 +611,7 @@ static int prepare(NppPlan* p, long long n) {
   return 0;
 }
 
+static long long* g_chain_dbg = nullptr;  // set by npp_debug_gemm_bench when NPP_DEBUG_STAMPS is given
 static int g_smem_attr_done = 0;
 static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
@@ -633,6 +634,7 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
   cp.subs_per_stripe = subs_per_stripe;
+  cp.dbg = g_chain_dbg;
   int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
   if (cluster == 1) {
     npp_gemm_kmajor<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
@@ -1164,6 +1166,12 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   KmajorParams* d_op = nullptr;
   CK(cudaMalloc(&d_op, ops.size() * sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, ops.data(), ops.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  long long* d_dbg = nullptr;
+  const int n_stamp_tiles = chain * (n / BN) * ((m + BM - 1) / BM / sms + 1);
+  if (getenv("NPP_DEBUG_STAMPS")) {
+    CK(cudaMalloc(&d_dbg, (size_t)n_stamp_tiles * 4 * sizeof(long long)));
+    CK(cudaMemset(d_dbg, 0, (size_t)n_stamp_tiles * 4 * sizeof(long long)));
+  }
   for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e0, 0));
   for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
@@ -1171,6 +1179,24 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(ms_out, e0, e1));
   *ms_out /= (float)chain;
+  if (d_dbg) {   // one extra stamped launch, printed as per-tile phase durations in clocks
+    g_chain_dbg = d_dbg;
+    int r2 = launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster);
+    g_chain_dbg = nullptr;
+    cudaDeviceSynchronize();
+    if (r2 == 0) {
+      std::vector<long long> h((size_t)n_stamp_tiles * 4);
+      cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      const int shown = chain * (n / BN) < n_stamp_tiles ? chain * (n / BN) : n_stamp_tiles;
+      for (int i = 0; i < shown; ++i) {
+        const long long* q = &h[(size_t)i * 4];
+        printf("  tile %2d: wait %6lld  subs %6lld  tail %6lld  | period %6lld clk\n", i, q[1] - q[0], q[2] - q[1],
+               q[3] - q[2], i ? q[0] - h[(size_t)(i - 1) * 4] : 0LL);
+      }
+      fflush(stdout);
+    }
+    cudaFree(d_dbg);
+  }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(d_op);
