@@ -240,8 +240,17 @@ __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t
 // Epilogue of one 128x256 accumulator tile.  Each warp owns 32 accumulator rows (its TMEM lane quadrant).
 // Results are staged in a per-warp 128B-swizzled 32x64 smem box and written with TMA stores (full 128-byte
 // lines); the dgrad multiplier (stored snake derivative) arrives the same way through a TMA load.
+// scalar fields of an op, copied to registers once per op (the descriptor itself lives in global memory)
+struct EpiArgs {
+  const float* bias;
+  float* colsum;
+  float* out_f32;
+  int ldf;
+};
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmSmem& s, uint32_t tmem_acc, int m0,
+__device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiArgs ea, const GemmSmem& s,
+                                              uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
                                               bool last_tile_of_op, uint32_t& deferred_seq, long long* dbg) {
@@ -329,7 +338,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const GemmS
         }
       }
       if (out_f32 != nullptr && row_ok) {
-        float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)row * p.ldf + hcol);
+        float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)row * ea.ldf + hcol);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
@@ -468,20 +477,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           }
         }
         const int nseg = p.nseg;
+        const int op_tiles_n = p.tiles_n;
+        int r_kbs[2], r_ak0[2], r_bk0[2], r_br0[2], r_src[2];
+        uint32_t r_srcbase[2], r_srctiles[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          r_kbs[q] = q < nseg ? p.kblocks[q] : 0;
+          r_ak0[q] = p.a_k0[q];
+          r_bk0[q] = p.b_k0[q];
+          r_br0[q] = p.b_row0[q];
+          r_src[q] = q < nseg ? p.a_src[q] : -1;
+          r_srcbase[q] = r_src[q] >= 0 ? (uint32_t)cp.ops[r_src[q]].sub_base : 0u;
+          r_srctiles[q] = r_src[q] >= 0 ? (uint32_t)cp.ops[r_src[q]].tiles_n : 0u;
+        }
         for (int sl = 0; sl < gi; ++sl) {
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
-          for (int nt = 0; nt < p.tiles_n; ++nt) {
+          for (int nt = 0; nt < op_tiles_n; ++nt) {
             const int n0 = nt * BN;
-            for (int seg = 0; seg < nseg; ++seg) {
-              const int kbs = p.kblocks[seg], ak0 = p.a_k0[seg], bk0 = p.b_k0[seg], br0 = p.b_row0[seg];
-              const int src = p.a_src[seg];
+#pragma unroll
+            for (int seg = 0; seg < 2; ++seg) {
+              if (seg >= nseg) break;
+              const int kbs = r_kbs[seg], ak0 = r_ak0[seg], bk0 = r_bk0[seg], br0 = r_br0[seg];
+              const int src = r_src[seg];
               // K block kb of this segment is the 64-column block (ak0/64 + kb) that op `src` wrote for the same
               // stripe; in processing order that op's tiles come after gi * sub_base[src] sub-tiles of this group
               // and after the sl earlier stripes of the op
               uint32_t need0 = 0;
               if (src >= 0)
-                need0 = group_base + (uint32_t)gi * cp.ops[src].sub_base +
-                        (uint32_t)sl * (uint32_t)(cp.ops[src].tiles_n * (BN / EPI_COLS)) + ak0 / BK + 1;
+                need0 = group_base + (uint32_t)gi * r_srcbase[seg] +
+                        (uint32_t)sl * (r_srctiles[seg] * (uint32_t)(BN / EPI_COLS)) + ak0 / BK + 1;
               for (int kb = 0; kb < kbs; ++kb) {
                 mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
                 if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
@@ -539,7 +563,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
           int total_kb = 0;
           for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
-          for (int tile = 0; tile < gi * p.tiles_n; ++tile) {
+          const int op_tiles = gi * p.tiles_n;
+          for (int tile = 0; tile < op_tiles; ++tile) {
             mbar_wait(&s.tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -594,9 +619,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           if (p.epi == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
         }
         const int epi = p.epi;
+        const int op_tiles_n = p.tiles_n;
+        EpiArgs ea;
+        ea.bias = p.bias;
+        ea.colsum = p.colsum;
+        ea.out_f32 = p.out_f32;
+        ea.ldf = p.ldf;
         for (int sl = 0; sl < gi; ++sl) {
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
-          for (int nt = 0; nt < p.tiles_n; ++nt) {
+          for (int nt = 0; nt < op_tiles_n; ++nt) {
             const uint32_t tacc = tmem_base + acc * BN;
             const int n0 = nt * BN;
             // Publish right away only when somebody is about to wait for it: a lone stripe's last tile of an op
@@ -604,24 +635,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             // from inside the following tile (the consumer of an interleaved stripe comes a whole stripe later).
             long long* dbgp = cp.dbg ? cp.dbg + 4 * tile_counter : nullptr;
             ++tile_counter;
-            const bool last_of_stripe_op = nt == p.tiles_n - 1;
+            const bool last_of_stripe_op = nt == op_tiles_n - 1;
             const bool last = (gi == 1 && last_of_stripe_op) ||
                               (final_group && oi == cp.n_ops - 1 && sl == gi - 1 && last_of_stripe_op);
             switch (epi) {
               case EPI_LINEAR:
-                epilogue_tile<EPI_LINEAR>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_LINEAR>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                           last, deferred, dbgp);
                 break;
               case EPI_SNAKE:
-                epilogue_tile<EPI_SNAKE>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_SNAKE>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                          last, deferred, dbgp);
                 break;
               case EPI_DGRAD_MUL:
-                epilogue_tile<EPI_DGRAD_MUL>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
+                epilogue_tile<EPI_DGRAD_MUL>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
                                              seq, last, deferred, dbgp);
                 break;
               default:
-                epilogue_tile<EPI_DGRAD>(p, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_DGRAD>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                          last, deferred, dbgp);
                 break;
             }
