@@ -131,10 +131,13 @@ struct NppPlan {
   float* acc = nullptr;  // [bias accumulators | head accumulators | amax | loss scratch]
   long long acc_floats = 0, headacc_off = 0, amax_off = 0;
   float* g_buf = nullptr;       // [max_rows,3] grad wrt logits (fused path)
+  unsigned int* d_barrier = nullptr;  // {arrivals, generation} of the fused head kernel's grid barrier
+  int head_fused_blocks = 0;          // co-resident blocks of npp_head_fused_kernel (0: not usable)
   float* logits_buf = nullptr;  // [max_rows,3] (fused path)
   FinalizeLayer* d_fin = nullptr;
   ShadowLayer* d_shadow = nullptr;
   UpdateLayer* d_update = nullptr;
+  UpdateTable update_table;      // the same table by value (kernel parameter of the fused update)
   KmajorParams* d_fwd_ops = nullptr;    // forward chain (one op per dense layer)
   KmajorParams* d_dgrad_ops = nullptr;  // dgrad chain
   WgUnit* d_units = nullptr;
@@ -391,6 +394,19 @@ static int alloc_plan_memory(NppPlan* p) {
   CK(cudaMalloc(&p->acc, p->acc_floats * sizeof(float)));
   CK(cudaMemset(p->acc, 0, p->acc_floats * sizeof(float)));
   CK(cudaMalloc(&p->g_buf, (size_t)R * 3 * sizeof(float)));
+  CK(cudaMalloc(&p->d_barrier, 2 * sizeof(unsigned int)));
+  CK(cudaMemset(p->d_barrier, 0, 2 * sizeof(unsigned int)));
+  {
+    int coop = 0, per_sm = 0, dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    int per_sm_reg = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, npp_head_fused_kernel, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_reg, npp_head_fused_reg_kernel, 256, 0));
+    if (per_sm_reg < per_sm) per_sm = per_sm_reg;
+    if (per_sm > 2) per_sm = 2;
+    p->head_fused_blocks = coop && p->head_width == 256 ? per_sm * p->num_sms : 0;
+  }
   CK(cudaMalloc(&p->logits_buf, (size_t)R * 3 * sizeof(float)));
 
   // device tables
@@ -450,6 +466,13 @@ static int alloc_plan_memory(NppPlan* p) {
       u.t_lo = sh[i].t_lo; u.t_hi = sh[i].t_hi; u.t_row0 = sh[i].t_row0;
       u.t_lo2 = sh[i].t_lo2; u.t_hi2 = sh[i].t_hi2; u.t_row02 = sh[i].t_row02;
       up.push_back(u);
+    }
+    if (up.size() > (size_t)NPP_MAX_UPDATE_LAYERS) return fail("too many layers for the fused update table");
+    memset(&p->update_table, 0, sizeof(p->update_table));
+    p->update_table.n_layers = (int)up.size();
+    for (size_t i = 0; i < up.size(); ++i) {
+      p->update_table.L[i] = up[i];
+      p->update_table.tile_begin[i + 1] = p->update_table.tile_begin[i] + (up[i].out / 32) * ((up[i].kpad + 127) / 128);
     }
     CK(cudaMalloc(&p->d_update, up.size() * sizeof(UpdateLayer)));
     CK(cudaMemcpy(p->d_update, up.data(), up.size() * sizeof(UpdateLayer), cudaMemcpyHostToDevice));
@@ -700,10 +723,13 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
   } else {
     ProfScope ps(p, st, PROF_ENCODE, 1);
     const int width = p->E;
-    dim3 grid((unsigned)((n + ENC_ROWS - 1) / ENC_ROWS), p->cfg.topk);
+    const int B = 2 * (p->cfg.include_input + 2 * p->cfg.n_aug);
+    const int rows = std::max(1, ENC_THREADS / (B / 2));   // one thread per (row, base-feature pair)
+    dim3 grid((unsigned)((n + rows - 1) / rows), p->cfg.topk);
+    const size_t smem = (size_t)enc_base_bytes(rows, B) + (size_t)rows * enc_row_stride(width) * sizeof(__half);
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
-    npp_encode_kernel<<<grid, 512, ENC_ROWS * width * sizeof(__half), st>>>(
-        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
+    npp_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(
+        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap, rows);
     CK(cudaGetLastError());
     ++p->launches;
   }
@@ -724,13 +750,14 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
 }
 
 // grad_logits must already be reflected in acc[amax] (loss kernel or amax kernel).
-static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st, bool finalize = true) {
+static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st, bool finalize = true,
+                        bool head_done = false) {
   if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
   CKI(prepare(p, n));
   CKI(set_smem_attrs());
   const Layer& last = p->layers.back();
   unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
-  {
+  if (!head_done) {
   ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
   npp_head_bwd_kernel<<<(unsigned)((n + HEAD_BWD_ROWS - 1) / HEAD_BWD_ROWS), 256, 0, st>>>(
       g, p->bufs[last.buf_h].ptr, p->bufs[last.buf_d].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off,
@@ -862,6 +889,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->partial);
   cudaFree(p->acc);
   cudaFree(p->g_buf);
+  cudaFree(p->d_barrier);
   cudaFree(p->logits_buf);
   cudaFree(p->d_fin);
   cudaFree(p->d_shadow);
@@ -964,7 +992,42 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
   CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
-  {
+  const bool fused_head = p->head_fused_blocks > 0 && !getenv("NPP_SPLIT_HEAD");
+  if (fused_head) {
+    // head forward + loss + head backward in one cooperative launch (grid barrier around the max|g| reduction)
+    CKI(prepare(p, n));
+    ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
+    const Layer& last = p->layers.back();
+    const __half* hp = p->bufs[last.buf_h].ptr;
+    const __half* dp = p->bufs[last.buf_d].ptr;
+    int ld = last.out, width = p->head_width, ni = (int)n, ldd = last.out;
+    const float* w = p->params + p->rgb_w_off;
+    const float* b = p->params + p->rgb_b_off;
+    float ic = inv_count;
+    float* logits = p->logits_buf;
+    float* g = p->g_buf;
+    unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
+    __half* delta = p->bufs[last.buf_delta].ptr;
+    float* head_acc = p->acc + p->headacc_off;
+    float* bias_acc = p->acc + last.bg_off;
+    unsigned int* bar = p->d_barrier;
+    void* args[] = {&hp, &dp, &ld, &width, &ni, &w, &b, &target, &mask, &ic, &logits, &g, &loss, &amax,
+                    &delta, &ldd, &head_acc, &bias_acc, &bar};
+    int blocks = p->head_fused_blocks;
+    const int want = (int)((n + 7) / 8);   // at least one row per warp
+    if (blocks > want) blocks = want;
+    int rows_per_block = (int)((n + blocks - 1) / blocks);
+    if (rows_per_block <= 8 * HEAD_MAXR && !getenv("NPP_HEAD_GENERIC")) {
+      void* rargs[] = {&hp, &dp, &ld, &ni, &w, &b, &target, &mask, &ic, &logits, &g, &loss, &amax,
+                       &delta, &ldd, &head_acc, &bias_acc, &bar, &rows_per_block};
+      CK(cudaLaunchCooperativeKernel((const void*)npp_head_fused_reg_kernel, dim3((unsigned)blocks), dim3(256), rargs, 0,
+                                     st));
+    } else {
+      CK(cudaLaunchCooperativeKernel((const void*)npp_head_fused_kernel, dim3((unsigned)blocks), dim3(256), args, 0,
+                                     st));
+    }
+    ++p->launches;
+  } else {
     ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
     const Layer& last = p->layers.back();
     int blocks = (int)((n + 31) / 32);   // 8 warps x 4 rows in flight each
@@ -976,7 +1039,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     CK(cudaGetLastError());
     ++p->launches;
   }
-  CKI(run_backward(p, n, p->g_buf, st, /*finalize=*/false));
+  CKI(run_backward(p, n, p->g_buf, st, /*finalize=*/false, /*head_done=*/fused_head));
   {
     if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
     if (step < 1) return fail("Adam step must be >= 1");
@@ -989,13 +1052,21 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     ad.step_size = (float)((double)lr / bc1);
     ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     ad.eps = eps;
-    const int nl = (int)p->layers.size();
-    dim3 grid(192, (unsigned)nl + 1);
-    npp_fused_update_kernel<<<grid, 256, 0, st>>>(p->d_update, nl, p->partial, p->wg_params.n_splits, p->slab_stride,
-                                                  p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,
-                                                  p->head_width,
-                                                  reinterpret_cast<unsigned int*>(p->acc + p->amax_off), p->params,
-                                                  p->keep_grads ? p->grads : nullptr, p->m, p->v, ad);
+    const unsigned blocks = (unsigned)p->update_table.tile_begin[p->update_table.n_layers] + 1;
+#define NPP_UPDATE_CASE(S_)                                                                                          \
+  case S_:                                                                                                           \
+    npp_fused_update_kernel<S_><<<blocks, 256, 0, st>>>(                                                             \
+        p->update_table, p->partial, p->slab_stride, p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,    \
+        p->head_width, reinterpret_cast<unsigned int*>(p->acc + p->amax_off), p->params,                             \
+        p->keep_grads ? p->grads : nullptr, p->m, p->v, ad);                                                         \
+    break;
+    switch (p->wg_params.n_splits) {
+      NPP_UPDATE_CASE(1) NPP_UPDATE_CASE(2) NPP_UPDATE_CASE(3) NPP_UPDATE_CASE(4) NPP_UPDATE_CASE(5) NPP_UPDATE_CASE(6)
+      NPP_UPDATE_CASE(7) NPP_UPDATE_CASE(8) NPP_UPDATE_CASE(9) NPP_UPDATE_CASE(10) NPP_UPDATE_CASE(11)
+      NPP_UPDATE_CASE(12)
+      default: return fail("unsupported split-K factor in the fused update");
+    }
+#undef NPP_UPDATE_CASE
     CK(cudaGetLastError());
     ++p->launches;
   }

@@ -28,10 +28,40 @@ struct EncTable {
 };
 
 // torch.remainder semantics (sign of the divisor), embedder.py:127 uses the % operator.
+// fmodf is exact (no rounding): for a moderate quotient it is one division, one truncation and one FMA.
+// q' = trunc(fl(a / b)) is the true quotient or one past it (rounding is monotonic), a - q' b is exactly
+// representable in both cases, so the FMA returns it exactly and a single correction step restores the sign rule.
+__device__ __forceinline__ float npp_fmodf(float a, float b) {
+  const float q = truncf(__fdiv_rn(a, b));
+  if (!(b > 0.0f) || !(fabsf(q) < 1048576.0f)) return fmodf(a, b);
+  float r = fmaf(-q, b, a);
+  if (a >= 0.0f) {
+    if (r < 0.0f) r += b;
+  } else {
+    if (r > 0.0f) r -= b;
+  }
+  return r == 0.0f ? copysignf(0.0f, a) : r;
+}
+
 __device__ __forceinline__ float torch_remainder(float a, float b) {
-  float r = fmodf(a, b);
+  float r = npp_fmodf(a, b);
   if (r != 0.0f && ((r < 0.0f) != (b < 0.0f))) r += b;
   return r;
+}
+
+// Phase phi of augmentation `aug` of direction `dir` (embedder.py:127-130):
+// (((y*cos + x*sin) % P) / P) * 2 * pi, every step rounded to fp32 like the eager torch ops.
+__device__ __forceinline__ float npp_phase(const EncTable& t, int j, int dir, int aug, float y, float x) {
+  const float ct = t.cos_t[j][dir][aug], st = t.sin_t[j][dir][aug], P = t.period[j][dir][aug];
+  const float proj = __fadd_rn(__fmul_rn(y, ct), __fmul_rn(x, st));
+  const float frac = __fdiv_rn(torch_remainder(proj, P), P);
+  return __fmul_rn(__fmul_rn(frac, 2.0f), 3.14159265358979323846f);
+}
+
+// (x / res[1] - 0.5) * 2  |  (y / res[0] - 0.5) * 2      embedder.py:107-108
+__device__ __forceinline__ float npp_norm_coord(const EncTable& t, int dir, float y, float x) {
+  const float v = dir == 0 ? __fdiv_rn(x, t.res_w) : __fdiv_rn(y, t.res_h);
+  return __fmul_rn(__fsub_rn(v, 0.5f), 2.0f);
 }
 
 // Base periodic feature c (0 .. 2*(1+2*n_aug)-1) of one proposal for pixel (row y, col x).
@@ -42,60 +72,101 @@ __device__ __forceinline__ float npp_base_feature(const EncTable& t, int j, int 
   const int dir = c / per_dir;
   int r = c - dir * per_dir;
   if (t.include_input) {
-    if (r == 0) {
-      // (x / res[1] - 0.5) * 2  |  (y / res[0] - 0.5) * 2      embedder.py:107-108
-      const float v = dir == 0 ? __fdiv_rn(x, t.res_w) : __fdiv_rn(y, t.res_h);
-      return __fmul_rn(__fsub_rn(v, 0.5f), 2.0f);
-    }
+    if (r == 0) return npp_norm_coord(t, dir, y, x);
     r -= 1;
   }
-  const int aug = r >> 1;
-  const float ct = t.cos_t[j][dir][aug], st = t.sin_t[j][dir][aug], P = t.period[j][dir][aug];
-  // (((y*cos + x*sin) % P) / P) * 2 * pi, every step rounded to fp32 like the eager torch ops
-  const float proj = __fadd_rn(__fmul_rn(y, ct), __fmul_rn(x, st));
-  const float frac = __fdiv_rn(torch_remainder(proj, P), P);
-  const float phi = __fmul_rn(__fmul_rn(frac, 2.0f), 3.14159265358979323846f);
+  const float phi = npp_phase(t, j, dir, r >> 1, y, x);
   return (r & 1) ? cosf(phi) : sinf(phi);
 }
 
-// Expanded encoding of ENC_ROWS rows of one proposal -> fp16, reference column order
+// Expanded encoding of `rows` rows of one proposal -> fp16, reference column order
 // out[:, b*B + c]: b = 0 identity, b = 1+2k sin(f_k u_c), b = 2+2k cos(f_k u_c)   (embedder.py:41-44,56)
-constexpr int ENC_ROWS = 16;
-__global__ void __launch_bounds__(512) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
-                                                         __half* __restrict__ enc1, int ld1,
-                                                         __half* __restrict__ enca, int lda) {
-  extern __shared__ __half enc_tile[];  // [ENC_ROWS][width]
-  const int B = 2 * (t.include_input + 2 * t.n_aug);
+// Three phases per block: (0) the B base features of every row in fp32 (one phase evaluation per sin/cos pair),
+// (1) the Fourier expansion, one thread per (row, pair of adjacent base features) so that every shared-memory store
+// is a half2, (2) copy-out with 16-byte stores: the tile row is kept at the same offset modulo 16 bytes as its
+// destination row, so whole aligned chunks move as uint4 and only the two ragged ends fall back to half2.
+constexpr int ENC_THREADS = 256;
+__host__ __device__ inline int enc_row_stride(int width) { return (width + 8 + 7) & ~7; }  // halfs, room for the shift
+__host__ __device__ inline int enc_base_bytes(int rows, int B) { return (rows * B * 4 + 15) & ~15; }
+__global__ void __launch_bounds__(ENC_THREADS) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
+                                                                 __half* __restrict__ enc1, int ld1,
+                                                                 __half* __restrict__ enca, int lda, int rows) {
+  extern __shared__ __align__(16) uint8_t enc_smem[];
+  const int per_dir = t.include_input + 2 * t.n_aug;
+  const int B = 2 * per_dir;
   const int F = 1 + 2 * t.n_freq;
   const int width = B * F;
+  const int RS = enc_row_stride(width);
+  float* ubase = reinterpret_cast<float*>(enc_smem);                              // [rows][B] fp32 base features
+  __half* tile = reinterpret_cast<__half*>(enc_smem + enc_base_bytes(rows, B));   // [rows][RS] fp16
   const int j = blockIdx.y;
-  const int row0 = blockIdx.x * ENC_ROWS;
-  for (int idx = threadIdx.x; idx < ENC_ROWS * B; idx += blockDim.x) {
-    const int r = idx / B, c = idx - r * B;
+  const int row0 = blockIdx.x * rows;
+  __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
+  const int ld = j == 0 ? ld1 : lda;
+
+  // index decomposition by a small runtime divisor d: (idx + 0.5) / d is at least 0.5 / d away from an integer,
+  // far more than the fp32 error of the product for idx < 2^16, d <= 64
+  const int per_dir_items = t.include_input + t.n_aug;
+  const int items_row = 2 * per_dir_items;
+  const float inv_items_row = 1.0f / (float)items_row, inv_per_dir_items = 1.0f / (float)per_dir_items;
+  for (int idx = threadIdx.x; idx < rows * items_row; idx += blockDim.x) {
+    const int r = __float2int_rz(((float)idx + 0.5f) * inv_items_row), q = idx - r * items_row;
+    const int dir = __float2int_rz(((float)q + 0.5f) * inv_per_dir_items), a = q - dir * per_dir_items;
     const int row = row0 + r;
-    if (row < n) {
-      const float y = coords[2 * row], x = coords[2 * row + 1];
-      const float u = npp_base_feature(t, j, c, y, x);
-      __half* o = enc_tile + r * width + c;
-      o[0] = __float2half_rn(u);
-      for (int k = 0; k < t.n_freq; ++k) {
-        const float a = __fmul_rn(u, t.freq[k]);  // p_fn(x * freq), embedder.py:43
-        o[(1 + 2 * k) * B] = __float2half_rn(__sinf(a));
-        o[(2 + 2 * k) * B] = __float2half_rn(__cosf(a));
-      }
+    if (row >= n) continue;
+    const float y = coords[2 * row], x = coords[2 * row + 1];
+    float* u = ubase + r * B + dir * per_dir;
+    if (t.include_input && a == 0) {
+      u[0] = npp_norm_coord(t, dir, y, x);
+    } else {
+      const int aug = a - t.include_input;
+      float sn, cs;
+      sincosf(npp_phase(t, j, dir, aug, y, x), &sn, &cs);
+      u[t.include_input + 2 * aug] = sn;
+      u[t.include_input + 2 * aug + 1] = cs;
     }
   }
   __syncthreads();
-  __half* dst = j == 0 ? enc1 : enca + (size_t)(j - 1) * width;
-  const int ld = j == 0 ? ld1 : lda;
-  const int w2 = width >> 1;  // width is even (B is even)
+
+  const int half_b = B >> 1;
+  const float inv_half_b = 1.0f / (float)half_b;
+  for (int idx = threadIdx.x; idx < rows * half_b; idx += blockDim.x) {
+    const int r = __float2int_rz(((float)idx + 0.5f) * inv_half_b), cp = idx - r * half_b;
+    const int row = row0 + r;
+    if (row >= n) continue;
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(dst + (size_t)row * ld) >> 1) & 7);
+    const float2 u = *reinterpret_cast<const float2*>(ubase + r * B + 2 * cp);
+    __half2* o = reinterpret_cast<__half2*>(tile + r * RS + shift + 2 * cp);
+    o[0] = __floats2half2_rn(u.x, u.y);
+    o += half_b;
+    for (int k = 0; k < t.n_freq; ++k) {
+      const float f = t.freq[k];
+      const float a0 = __fmul_rn(u.x, f), a1 = __fmul_rn(u.y, f);  // p_fn(x * freq), embedder.py:43
+      o[0] = __floats2half2_rn(__sinf(a0), __sinf(a1));
+      o[half_b] = __floats2half2_rn(__cosf(a0), __cosf(a1));
+      o += B;
+    }
+  }
+  __syncthreads();
+
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int r = wib; r < ENC_ROWS; r += nw) {  // one warp per row: coalesced 128-byte stores, no division
+  for (int r = wib; r < rows; r += nw) {
     const int row = row0 + r;
     if (row >= n) break;
-    const __half2* src = reinterpret_cast<const __half2*>(enc_tile + r * width);
-    __half2* d2 = reinterpret_cast<__half2*>(dst + (size_t)row * ld);
-    for (int c2 = lane; c2 < w2; c2 += 32) d2[c2] = src[c2];
+    __half* grow = dst + (size_t)row * ld;
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(grow) >> 1) & 7);
+    const __half* srow = tile + r * RS;
+    __half* gal = grow - shift;  // 16-byte aligned
+    const int end = shift + width;
+    const int first_full = (shift + 7) >> 3, last_full = end >> 3;  // 8-half chunks [first_full, last_full) are whole
+    for (int ch = first_full + lane; ch < last_full; ch += 32)
+      reinterpret_cast<uint4*>(gal)[ch] = reinterpret_cast<const uint4*>(srow)[ch];
+    if (lane < 8) {  // ragged ends: at most three half2 in front and three behind
+      const int head_end = min(first_full << 3, end);
+      const int pos = lane < 4 ? shift + 2 * lane : (last_full << 3) + 2 * (lane - 4);
+      const bool ok = lane < 4 ? pos < head_end : (last_full >= first_full && pos < end);
+      if (ok) *reinterpret_cast<__half2*>(gal + pos) = *reinterpret_cast<const __half2*>(srow + pos);
+    }
   }
 }
 
@@ -230,12 +301,11 @@ __global__ void __launch_bounds__(256) npp_mse_kernel(const float* __restrict__ 
 
 // Fused RGB head + sigmoid + masked MSE for the train-step path: one warp per row computes the three
 // logits (networks.py:94), lanes 0..2 then apply helpers.py:55-56 and mse_calculator.py:13-27 ('l2').
-__global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __restrict__ hp, int ld, int width, int n,
-                                                            const float* __restrict__ w, const float* __restrict__ b,
-                                                            const float* __restrict__ target,
-                                                            const float* __restrict__ mask, float inv_count,
-                                                            float* __restrict__ logits, float* __restrict__ g,
-                                                            float* __restrict__ loss, unsigned int* __restrict__ amax_bits) {
+__device__ __forceinline__ void npp_head_loss_part(const __half* __restrict__ hp, int ld, int width, int n,
+                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                   const float* __restrict__ target, const float* __restrict__ mask,
+                                                   float inv_count, float* logits, float* g, float* loss,
+                                                   unsigned int* amax_bits) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   float lsum = 0.f, lmax = 0.f;
@@ -342,6 +412,15 @@ __global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __rest
   }
 }
 
+__global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __restrict__ hp, int ld, int width, int n,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            const float* __restrict__ target,
+                                                            const float* __restrict__ mask, float inv_count,
+                                                            float* __restrict__ logits, float* __restrict__ g,
+                                                            float* __restrict__ loss, unsigned int* __restrict__ amax_bits) {
+  npp_head_loss_part(hp, ld, width, n, w, b, target, mask, inv_count, logits, g, loss, amax_bits);
+}
+
 // max |g| of an externally supplied gradient (autograd path).
 __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__ g, int total,
                                                        unsigned int* __restrict__ amax_bits) {
@@ -357,19 +436,19 @@ __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__
 // dW_rgb, db_rgb (unscaled fp32) and the bias gradient of the P layer (scaled column sums).
 // One warp per row, lane owns 8 consecutive columns (16-byte loads/stores); per-lane partial sums are reduced
 // across the block's warps in shared memory, then one atomic per column per block.
-constexpr int HEAD_BWD_ROWS = 32;   // rows per block: ~3.5 blocks per SM at 16 k rows
-__global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
-                                                           const __half* __restrict__ dp, int ld, int width, int n,
-                                                           const float* __restrict__ w,
-                                                           const unsigned int* __restrict__ amax_bits,
-                                                           __half* __restrict__ delta, int ldd,
-                                                           float* __restrict__ head_acc /*[3*width+3]*/,
-                                                           float* __restrict__ bias_acc /*[width]*/) {
+constexpr int HEAD_BWD_ROWS = 32;   // rows per block of the stand-alone kernel: ~3.5 blocks per SM at 16 k rows
+// g and amax_bits may have been written earlier in the SAME kernel (fused variant): they are read through L2
+// (ld.global.cg), never through the non-coherent path.
+__device__ __forceinline__ void npp_head_bwd_part(const float* g, const __half* __restrict__ hp,
+                                                  const __half* __restrict__ dp, int ld, int width, int n,
+                                                  const float* __restrict__ w, const unsigned int* amax_bits,
+                                                  __half* __restrict__ delta, int ldd, float* head_acc /*[3*width+3]*/,
+                                                  float* bias_acc /*[width]*/, int rows_per_block) {
   __shared__ float red[8][4 * 256 + 4];
-  const float scale = npp_grad_scale(__uint_as_float(*amax_bits));
+  const float scale = npp_grad_scale(__uint_as_float(__ldcg(amax_bits)));
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int row_begin = blockIdx.x * HEAD_BWD_ROWS;
-  const int row_end = min(row_begin + HEAD_BWD_ROWS, n);
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(row_begin + rows_per_block, n);
   float gsum[3] = {0.f, 0.f, 0.f};
   for (int k0 = lane * 8; k0 < width; k0 += 256) {   // one pass for width == 256
     float wr[3][8], aw[3][8], ab[8];
@@ -384,7 +463,8 @@ __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restri
     for (int i = 0; i < 8; ++i) ab[i] = 0.f;
 #pragma unroll 4
     for (int row = row_begin + wib; row < row_end; row += 8) {
-      const float g0 = g[3 * (size_t)row], g1 = g[3 * (size_t)row + 1], g2 = g[3 * (size_t)row + 2];
+      const float g0 = __ldcg(g + 3 * (size_t)row), g1 = __ldcg(g + 3 * (size_t)row + 1),
+                  g2 = __ldcg(g + 3 * (size_t)row + 2);
       const uint4 hraw = *reinterpret_cast<const uint4*>(hp + (size_t)row * ld + k0);
       const uint4 draw = *reinterpret_cast<const uint4*>(dp + (size_t)row * ld + k0);
       const __half2* h2 = reinterpret_cast<const __half2*>(&hraw);
@@ -445,6 +525,235 @@ __global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restri
       __syncthreads();
     }
   }
+}
+
+__global__ void __launch_bounds__(256) npp_head_bwd_kernel(const float* __restrict__ g, const __half* __restrict__ hp,
+                                                           const __half* __restrict__ dp, int ld, int width, int n,
+                                                           const float* __restrict__ w,
+                                                           const unsigned int* __restrict__ amax_bits,
+                                                           __half* __restrict__ delta, int ldd,
+                                                           float* __restrict__ head_acc, float* __restrict__ bias_acc) {
+  npp_head_bwd_part(g, hp, dp, ld, width, n, w, amax_bits, delta, ldd, head_acc, bias_acc, HEAD_BWD_ROWS);
+}
+
+// Self-resetting grid barrier (sense reversal on a generation word): state[0] = arrivals, state[1] = generation.
+// Needs every block of the grid to be resident (cooperative launch).
+__device__ __forceinline__ void npp_grid_barrier(unsigned int* state) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(state + 1) : "memory");
+    __threadfence();
+    const unsigned int prev = atomicAdd(state, 1u);
+    if (prev == gridDim.x - 1) {
+      state[0] = 0u;  // nobody touches the counter again before the generation moves
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(state + 1), "r"(gen + 1u) : "memory");
+    } else {
+      unsigned int now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(state + 1) : "memory");
+      } while (now == gen);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Train-step head in ONE cooperative launch: RGB head + sigmoid + masked MSE (writes g, loss, max|g|), a grid
+// barrier so that every block sees the final max|g| (the fp16 delta scale), then the head backward.  The second
+// read of h_P comes from L2 (8 MB at 16 k rows).
+__global__ void __launch_bounds__(256, 2) npp_head_fused_kernel(const __half* __restrict__ hp, const __half* __restrict__ dp,
+                                                                int ld, int width, int n, const float* __restrict__ w,
+                                                                const float* __restrict__ b,
+                                                                const float* __restrict__ target,
+                                                                const float* __restrict__ mask, float inv_count,
+                                                                float* logits, float* g, float* loss,
+                                                                unsigned int* amax_bits, __half* __restrict__ delta,
+                                                                int ldd, float* head_acc, float* bias_acc,
+                                                                unsigned int* barrier_state) {
+  npp_head_loss_part(hp, ld, width, n, w, b, target, mask, inv_count, logits, g, loss, amax_bits);
+  npp_grid_barrier(barrier_state);
+  const int rows_per_block = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  npp_head_bwd_part(g, hp, dp, ld, width, n, w, amax_bits, delta, ldd, head_acc, bias_acc, rows_per_block);
+}
+
+// Register-resident variant for width == 256 and at most 8 * HEAD_MAXR rows per block (16 k rows on 2 x 148 blocks):
+// every global load of a phase is issued up front, h_P is read once (logits AND dW_rgb come from the same
+// registers), and the snake-derivative rows are fetched before the grid barrier so that their latency hides behind it.
+constexpr int HEAD_MAXR = 8;
+__global__ void __launch_bounds__(256, 2) npp_head_fused_reg_kernel(
+    const __half* __restrict__ hp, const __half* __restrict__ dp, int ld, int n, const float* __restrict__ w,
+    const float* __restrict__ b, const float* __restrict__ target, const float* __restrict__ mask, float inv_count,
+    float* logits, float* g, float* loss, unsigned int* amax_bits, __half* __restrict__ delta, int ldd,
+    float* head_acc /*[3*256+3]*/, float* bias_acc /*[256]*/, unsigned int* barrier_state, int rows_per_block) {
+  constexpr int W = 256;
+  __shared__ float red[8][4 * W + 4];
+  __shared__ float ssum[8], smax[8], gs[3];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(row_begin + rows_per_block, n);
+  if (threadIdx.x < 3) gs[threadIdx.x] = 0.f;
+
+  // ---- phase A: logits, loss, g, dW_rgb
+  uint4 hraw[HEAD_MAXR];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXR; ++i) {
+    const int row = row_begin + wib + 8 * i;
+    hraw[i] = make_uint4(0, 0, 0, 0);
+    if (row < row_end) hraw[i] = *reinterpret_cast<const uint4*>(hp + (size_t)row * ld + lane * 8);
+  }
+  float wr[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c * W + lane * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c * W + lane * 8 + 4));
+    wr[c][0] = w0.x; wr[c][1] = w0.y; wr[c][2] = w0.z; wr[c][3] = w0.w;
+    wr[c][4] = w1.x; wr[c][5] = w1.y; wr[c][6] = w1.z; wr[c][7] = w1.w;
+  }
+  // lane L < 24 finishes (row slot i = L / 3, channel c = L % 3): its target / mask loads go out now as well
+  const int my_i = lane / 3, my_c = lane - 3 * my_i;
+  const int my_row = row_begin + wib + 8 * my_i;
+  const bool mine = lane < 3 * HEAD_MAXR && my_row < row_end;
+  float my_t = 0.f, my_m = 1.0f, my_b = 0.f;
+  if (mine) {
+    my_t = target[3 * (size_t)my_row + my_c];
+    if (mask) my_m = mask[my_row];
+    my_b = b[my_c];
+  }
+  float a[HEAD_MAXR][3];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXR; ++i) {
+    a[i][0] = a[i][1] = a[i][2] = 0.f;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&hraw[i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h2[k]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[i][c] = fmaf(f.x, wr[c][2 * k], fmaf(f.y, wr[c][2 * k + 1], a[i][c]));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1)
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXR; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[i][c] += __shfl_xor_sync(0xffffffffu, a[i][c], s);
+  float gi = 0.f, lsum = 0.f;
+  {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXR; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (3 * i + c == lane) acc = a[i][c];
+    if (mine) {
+      const float z = acc + my_b;
+      const float yh = 1.0f / (1.0f + expf(-z));
+      const float wgt = my_m + (1.0f - my_m) * 0.3f;
+      const float d = (yh - my_t) * wgt;
+      lsum = d * d;
+      gi = 2.0f * d * wgt * inv_count * yh * (1.0f - yh);
+      const size_t idx = 3 * (size_t)my_row + my_c;
+      if (logits) logits[idx] = z;
+      g[idx] = gi;
+      atomicAdd(&gs[my_c], gi);  // db_rgb
+    }
+  }
+  float lmax = fabsf(gi);
+  // dW_rgb partial sums of this warp's rows (lane owns 8 columns)
+  float aw[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[c][k] = 0.f;
+  float gr[HEAD_MAXR][3];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXR; ++i) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gr[i][c] = __shfl_sync(0xffffffffu, gi, 3 * i + c);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&hraw[i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h2[k]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        aw[c][2 * k] = fmaf(gr[i][c], f.x, aw[c][2 * k]);
+        aw[c][2 * k + 1] = fmaf(gr[i][c], f.y, aw[c][2 * k + 1]);
+      }
+    }
+  }
+  // snake-derivative rows for phase B: in flight across the barrier
+  uint4 draw[HEAD_MAXR];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXR; ++i) {
+    const int row = row_begin + wib + 8 * i;
+    draw[i] = make_uint4(0, 0, 0, 0);
+    if (row < row_end) draw[i] = *reinterpret_cast<const uint4*>(dp + (size_t)row * ld + lane * 8);
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, s);
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, s));
+  }
+  if (lane == 0) {
+    ssum[wib] = lsum;
+    smax[wib] = lmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.f, y = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      x += ssum[i];
+      y = fmaxf(y, smax[i]);
+    }
+    atomicAdd(loss, x * inv_count);
+    if (y > 0.f) atomicMax(amax_bits, __float_as_uint(y));
+  }
+  npp_grid_barrier(barrier_state);
+
+  // ---- phase B: delta_P = (g . W_rgb) * snake'(z_P) * scale, bias gradient of the P layer
+  const float scale = npp_grad_scale(__uint_as_float(__ldcg(amax_bits)));
+  float ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ab[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXR; ++i) {
+    const int row = row_begin + wib + 8 * i;
+    if (row >= row_end) continue;
+    const __half2* d2 = reinterpret_cast<const __half2*>(&draw[i]);
+    uint4 outv;
+    __half2* o2 = reinterpret_cast<__half2*>(&outv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __half22float2(d2[k]);
+      const float dax = fmaf(gr[i][0], wr[0][2 * k], fmaf(gr[i][1], wr[1][2 * k], gr[i][2] * wr[2][2 * k]));
+      const float day = fmaf(gr[i][0], wr[0][2 * k + 1], fmaf(gr[i][1], wr[1][2 * k + 1], gr[i][2] * wr[2][2 * k + 1]));
+      const __half2 dh = __floats2half2_rn(dax * d.x * scale, day * d.y * scale);
+      o2[k] = dh;
+      const float2 df = __half22float2(dh);
+      ab[2 * k] += df.x;
+      ab[2 * k + 1] += df.y;
+    }
+    *reinterpret_cast<uint4*>(delta + (size_t)row * ldd + lane * 8) = outv;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[wib][0 * W + lane * 8 + k] = aw[0][k];
+    red[wib][1 * W + lane * 8 + k] = aw[1][k];
+    red[wib][2 * W + lane * 8 + k] = aw[2][k];
+    red[wib][3 * W + lane * 8 + k] = ab[k];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 4 * W; idx += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][idx];
+    const int acc_i = idx >> 8, col = idx & (W - 1);
+    if (acc_i < 3) atomicAdd(head_acc + acc_i * W + col, t);
+    else atomicAdd(bias_acc + col, t);
+  }
+  if (threadIdx.x < 3) atomicAdd(head_acc + 3 * W + threadIdx.x, gs[threadIdx.x]);
 }
 
 // ------------------------------------------------------------- gradients / Adam
@@ -509,23 +818,35 @@ __device__ __forceinline__ float npp_adam1(float p, float g, float& m, float& v,
   v = v * a.beta2 + (1.0f - a.beta2) * g * g;
   return p - a.step_size * (m / (sqrtf(v) * a.inv_sqrt_bc2 + a.eps));
 }
-__global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer* __restrict__ layers, int n_layers,
-                                                               const float* __restrict__ partial, int n_splits,
-                                                               long long slab_stride, const float* __restrict__ bias_acc,
+// All layers of one plan, passed by value (constant bank: no dependent global load before the first slab read).
+constexpr int NPP_MAX_UPDATE_LAYERS = 24;
+struct UpdateTable {
+  UpdateLayer L[NPP_MAX_UPDATE_LAYERS];
+  int tile_begin[NPP_MAX_UPDATE_LAYERS + 1];  // prefix sums of 32 x 128 tiles; block b works on exactly one tile
+  int n_layers;
+};
+
+// One block = one tile of 32 weight rows x 128 PADDED columns (blockIdx.x == total tiles: the rgb_linear head).
+// A thread owns 4 consecutive padded columns of one row per pass, so the split-K slabs are read with aligned
+// float4 loads; padded columns map back to reference columns per segment (segment boundaries are multiples of 64,
+// so the four columns never straddle one).  The four passes run as two groups of two: every load of a group
+// (S slab float4 + master/m/v) is issued before the first result is consumed, which is what keeps enough bytes in
+// flight to approach HBM bandwidth.
+template <int S>
+__global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_constant__ UpdateTable tab,
+                                                               const float* __restrict__ partial, long long slab_stride,
+                                                               const float* __restrict__ bias_acc,
                                                                const float* __restrict__ head_acc, long long rgb_w_off,
                                                                long long rgb_b_off, int head_width,
                                                                const unsigned int* __restrict__ amax_bits,
                                                                float* __restrict__ params, float* __restrict__ grads,
                                                                float* __restrict__ m, float* __restrict__ v,
                                                                AdamScalars ad) {
-  // Tile = 32 weight rows x 128 PADDED columns; a thread owns 4 consecutive padded columns of one row per pass, so
-  // the split-K slabs are read with aligned float4 loads.  Padded columns map back to reference columns per segment
-  // (segment boundaries are multiples of 64, so the four columns never straddle one).
   __shared__ float tile[32][129];
-  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
-  if ((int)blockIdx.y == n_layers) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
+  const int total_tiles = tab.tile_begin[tab.n_layers];
+  if ((int)blockIdx.x >= total_tiles) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
     const int total = 3 * head_width + 3;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const long long idx = i < 3 * head_width ? rgb_w_off + i : rgb_b_off + (i - 3 * head_width);
       const float g = head_acc[i];
       if (grads) grads[idx] = g;
@@ -533,54 +854,110 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer
     }
     return;
   }
-  const UpdateLayer L = layers[blockIdx.y];
+  int li = 0;
+  while ((int)blockIdx.x >= tab.tile_begin[li + 1]) ++li;
+  const UpdateLayer& L = tab.L[li];
+  const int t = (int)blockIdx.x - tab.tile_begin[li];
+  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
   const int tiles_c = (L.kpad + 127) >> 7;
-  const int tiles_r = L.out >> 5;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 column groups x 8 rows per pass
   const bool two_seg = L.in_ref > L.split_col;
-  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
-    const int r0 = (t / tiles_c) << 5, pc0 = (t % tiles_c) << 7;
-    __syncthreads();
+  const int r0 = (t / tiles_c) << 5, pc0 = (t % tiles_c) << 7;
+  const int pc = pc0 + 4 * tx;
+  // this thread's four padded columns -> reference columns [c, c+4) clipped to lim (-1: padding only)
+  int c = -1, lim = 0;
+  if (pc < L.kpad) {
+    if (two_seg && pc >= L.off1) {
+      c = pc - L.off1 + L.split_col;
+      lim = L.in_ref;
+    } else {
+      c = pc - L.off0;
+      lim = L.split_col;
+    }
+    if (c >= lim) c = -1;
+  }
+  // float2 access to the fp32 arenas needs even offsets (true for every reference shape: widths are even)
+  const bool vec2 = ((L.in_ref | L.split_col | (int)(L.w_off & 1)) & 1) == 0;
+  const long long s4 = slab_stride >> 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty + 8 * i;
-      const int pc = pc0 + 4 * tx;
-      float pn[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pc < L.kpad) {
-        int c, lim;
-        if (two_seg && pc >= L.off1) {
-          c = pc - L.off1 + L.split_col;
-          lim = L.in_ref;
-        } else {
-          c = pc - L.off0;
-          lim = L.split_col;
-        }
-        if (c < lim) {
-          const float4* pp = reinterpret_cast<const float4*>(partial + L.pg_off + (long long)r * L.kpad + pc);
-          const long long s4 = slab_stride >> 2;
-          float4 acc[NPP_MAX_SPLITS];
+  for (int grp = 0; grp < 2; ++grp) {
+    float4 acc[2][S];
+    float pv[2][4], mv[2][4], vv[2][4];
 #pragma unroll
-          for (int k = 0; k < NPP_MAX_SPLITS; ++k)
-            acc[k] = k < n_splits ? __ldg(pp + k * s4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + ty + 8 * (2 * grp + u);
 #pragma unroll
-          for (int k = 0; k < NPP_MAX_SPLITS; ++k) {
-            g4[0] += acc[k].x;
-            g4[1] += acc[k].y;
-            g4[2] += acc[k].z;
-            g4[3] += acc[k].w;
-          }
-          const long long base = L.w_off + (long long)r * L.in_ref + c;
+      for (int j = 0; j < 4; ++j) pv[u][j] = mv[u][j] = vv[u][j] = 0.f;
+      if (c >= 0) {
+        const float4* pp = reinterpret_cast<const float4*>(partial + L.pg_off + (long long)r * L.kpad + pc);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+        for (int k = 0; k < S; ++k) acc[u][k] = __ldg(pp + k * s4);
+        const long long base = L.w_off + (long long)r * L.in_ref + c;
+        if (vec2) {
+#pragma unroll
+          for (int j = 0; j < 4; j += 2)
             if (c + j < lim) {
-              const float g = g4[j] * inv;
-              if (grads) grads[base + j] = g;
-              pn[j] = npp_adam1(params[base + j], g, m[base + j], v[base + j], ad);
-              params[base + j] = pn[j];
+              const float2 a = *reinterpret_cast<const float2*>(params + base + j);
+              const float2 b = *reinterpret_cast<const float2*>(m + base + j);
+              const float2 d = *reinterpret_cast<const float2*>(v + base + j);
+              pv[u][j] = a.x; pv[u][j + 1] = a.y;
+              mv[u][j] = b.x; mv[u][j + 1] = b.y;
+              vv[u][j] = d.x; vv[u][j + 1] = d.y;
             }
-          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < lim) {
+              pv[u][j] = params[base + j];
+              mv[u][j] = m[base + j];
+              vv[u][j] = v[base + j];
+            }
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < S; ++k) acc[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + ty + 8 * (2 * grp + u);
+      float pn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c >= 0) {
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < S; ++k) {  // fixed order: deterministic
+          g4[0] += acc[u][k].x;
+          g4[1] += acc[u][k].y;
+          g4[2] += acc[u][k].z;
+          g4[3] += acc[u][k].w;
+        }
+        const long long base = L.w_off + (long long)r * L.in_ref + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          g4[j] *= inv;
+          if (c + j < lim) pn[j] = npp_adam1(pv[u][j], g4[j], mv[u][j], vv[u][j], ad);
+        }
+        if (vec2) {
+#pragma unroll
+          for (int j = 0; j < 4; j += 2)
+            if (c + j < lim) {
+              if (grads) *reinterpret_cast<float2*>(grads + base + j) = make_float2(g4[j], g4[j + 1]);
+              *reinterpret_cast<float2*>(params + base + j) = make_float2(pn[j], pn[j + 1]);
+              *reinterpret_cast<float2*>(m + base + j) = make_float2(mv[u][j], mv[u][j + 1]);
+              *reinterpret_cast<float2*>(v + base + j) = make_float2(vv[u][j], vv[u][j + 1]);
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < lim) {
+              if (grads) grads[base + j] = g4[j];
+              params[base + j] = pn[j];
+              m[base + j] = mv[u][j];
+              v[base + j] = vv[u][j];
+            }
+        }
+      }
+      if (pc < L.kpad) {
         // forward shadow: four halves (padding columns are written as the zeros they must stay)
         const __half2 lo = __floats2half2_rn(pn[0], pn[1]), hi = __floats2half2_rn(pn[2], pn[3]);
         uint2 pk;
@@ -589,33 +966,37 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const UpdateLayer
         *reinterpret_cast<uint2*>(L.wf + (long long)r * L.kpad + pc) = pk;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tile[ty + 8 * i][4 * tx + j] = pn[j];
-    }
-    __syncthreads();
-    if (L.wt != nullptr) {
-      // transposed shadow for dgrad: row = reference input column (within the ranges that need a gradient)
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int pcl = ty + 8 * i;
-        const int pc = pc0 + pcl;
-        if (pc >= L.kpad) break;
-        int c, lim;
-        if (two_seg && pc >= L.off1) {
-          c = pc - L.off1 + L.split_col;
-          lim = L.in_ref;
-        } else {
-          c = pc - L.off0;
-          lim = L.split_col;
-        }
-        if (c >= lim) continue;
-        int trow = -1;
-        if (c >= L.t_lo && c < L.t_hi) trow = L.t_row0 + (c - L.t_lo);
-        else if (c >= L.t_lo2 && c < L.t_hi2) trow = L.t_row02 + (c - L.t_lo2);
-        if (trow >= 0) L.wt[(long long)trow * L.out + r0 + tx] = __float2half_rn(tile[tx][pcl]);
-      }
+      for (int j = 0; j < 4; ++j) tile[ty + 8 * (2 * grp + u)][4 * tx + j] = pn[j];
     }
   }
-  if (blockIdx.x == 0) {
+  __syncthreads();
+  if (L.wt != nullptr) {
+    // transposed shadow for dgrad: row = reference input column (within the ranges that need a gradient); a
+    // half-warp writes one column as 16 half2 (two weight rows each), so a warp covers two columns per pass
+    const int rp = 2 * (tx & 15);
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+      const int pcl = 2 * ty + (tx >> 4) + 16 * i;
+      const int pcc = pc0 + pcl;
+      if (pcc >= L.kpad) continue;
+      int cc, ll;
+      if (two_seg && pcc >= L.off1) {
+        cc = pcc - L.off1 + L.split_col;
+        ll = L.in_ref;
+      } else {
+        cc = pcc - L.off0;
+        ll = L.split_col;
+      }
+      if (cc >= ll) continue;
+      int trow = -1;
+      if (cc >= L.t_lo && cc < L.t_hi) trow = L.t_row0 + (cc - L.t_lo);
+      else if (cc >= L.t_lo2 && cc < L.t_hi2) trow = L.t_row02 + (cc - L.t_lo2);
+      if (trow >= 0)
+        *reinterpret_cast<__half2*>(L.wt + (long long)trow * L.out + r0 + rp) =
+            __floats2half2_rn(tile[rp][pcl], tile[rp + 1][pcl]);
+    }
+  }
+  if (t == 0) {
     for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
       const long long idx = L.b_off + o;
       const float g = bias_acc[L.bg_off + o] * inv;
