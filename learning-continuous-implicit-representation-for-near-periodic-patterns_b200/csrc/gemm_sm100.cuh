@@ -23,7 +23,7 @@ constexpr int BM = 128;      // UMMA M  (rows of the coordinate batch / out-feat
 constexpr int BN = 256;      // UMMA N
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle atom of halves
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;     // chain kernel: 3 x 48 KB ring + 64 KB epilogue staging
+constexpr int STAGES = 2;     // single-CTA fallback of the chain kernel: 2 x 48 KB ring + 96 KB epilogue staging
 constexpr int WG_STAGES = 4;  // wgrad kernel: no staging, deeper ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
@@ -33,14 +33,16 @@ constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_COLS = 64;                         // epilogue sub-tile: 32 rows x 64 halves = one 4 KB SW128 box per warp
 constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;     // 4 KB
-constexpr int EPI_BUFS = 4;                          // per warp: 2 outputs x double buffer, or one whole-tile multiplier
-constexpr int EPI_STAGE_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 4 epilogue warps x 4 buffers = 64 KB
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
+constexpr int EPI_OUT_BYTES = 4 * 4 * EPI_BUF_BYTES;          // output staging: 4 sub-tiles x 4 quadrants = one 128 x 256 tile, 64 KB
+constexpr int EPI_AUX_BYTES = EPI_WARPS * EPI_BUF_BYTES;      // one box per epilogue warp (snake derivative out / dgrad multiplier in), 32 KB
+constexpr int EPI_STAGE_BYTES = EPI_OUT_BYTES + EPI_AUX_BYTES;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + BN * 4 + 512 + 1024;
 constexpr int STRIPE_GROUP = 1;  // stripes a CTA interleaves op by op (2 was measured neutral: large batches are
                                  // bound by the snake epilogue's MUFU rate, not by dependency bubbles)
 constexpr int PAIR_STAGES = 4;  // cta_group::2: a stage is A 16 KB + half of B 16 KB per CTA
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + EPI_STAGE_BYTES + BN * 4 + 256 + 1024;
-constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + EPI_STAGE_BYTES + BN * 4 + 512 + 1024;
+static_assert(PAIR_SMEM_BYTES <= 232448, "chain kernel exceeds 227 KB of shared memory");
+constexpr int WGRAD_SMEM_BYTES = WG_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 512 + 1024;
 
 enum : int {
   EPI_LINEAR = 0,     // out0 = acc + bias                              (feature_linear1/2)
@@ -78,7 +80,18 @@ struct alignas(64) KmajorParams {
   int ldf;
   unsigned long long desc_hi;  // UMMA smem descriptor bits [16,64) (0 = default K-major SW128)
   int k_adv;                   // byte advance per UMMA_K slice (0 = default 32)
+  // On-chip forwarding between consecutive ops of a chain: the epilogue of op i writes each 128 x 64 output block
+  // straight into the pipeline stage where tile 0 / segment 0 of op i+1 expects that K block of its A operand
+  // (same 128-byte-swizzled K-major layout), so the first tile of the next op starts without waiting for
+  // TMA store -> L2 -> TMA load.  The copy in global memory is still written (tile 1 of op i+1, the backward pass).
+  int fwd_out;      // this op's epilogue forwards into the stages of the next op (needs tiles_n <= 2)
+  int fwd_in;       // tile 0 / segment 0 of this op receives its A blocks from the previous op's epilogue
+  int kb_per_tile;  // sum of kblocks[] (pipeline stages one tile of this op consumes)
 };
+
+// ring position p of a forwarded K block holds block fwd_perm(p): the epilogue finishes sub-tiles in the order
+// 0, 2, 1, 3 (two warps per TMEM lane quadrant, two sub-tiles each), so the UMMAs consume them in that order
+__host__ __device__ constexpr int fwd_perm(int p) { return (p & ~3) | ((p & 1) << 1) | ((p >> 1) & 1); }
 
 // A chain = ops executed in order for every 128-row stripe; op i may read what ops < i wrote for the
 // same rows (rows are independent in forward and dgrad), so a CTA that owns a stripe needs no grid sync.
@@ -88,7 +101,8 @@ struct ChainParams {
   int M;
   int tiles_m;
   int subs_per_stripe;  // output sub-tiles all ops write per stripe
-  long long* dbg;       // optional (tests): per-tile clock64 stamps of CTA 0 / warp 2: wait-begin, acc-ready, subs-done, tile-done
+  long long* dbg;       // optional (tests): per-tile clock64 stamps of one CTA (epilogue warp dbg_warp and the UMMA warp of its pair)
+  int dbg_block, dbg_warp;
 };
 
 struct WgUnit {
@@ -137,7 +151,9 @@ struct GemmSmem {
   uint64_t* empty;
   uint64_t* tfull;
   uint64_t* tempty;
-  uint64_t* epi_bar;  // one per epilogue warp (TMA loads of the dgrad multiplier)
+  uint64_t* epi_bar;  // [8] one per epilogue warp (TMA loads of the dgrad multiplier)
+  uint64_t* fempty;   // [4] forwarding: staging block b has been consumed by the next op's UMMAs
+  uint64_t* afull;    // [8] forwarding: A block k of the next op (sub-tile k & 3 of tile k >> 2) is in the staging
   uint32_t* prog;     // [8] per epilogue warp: output sub-tiles (cumulative) whose TMA stores have completed
   uint32_t* tmem_ptr;
 };
@@ -156,23 +172,27 @@ __device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   s.tfull = s.empty + NSTAGES;
   s.tempty = s.tfull + 2;
   s.epi_bar = s.tempty + 2;
-  s.prog = reinterpret_cast<uint32_t*>(s.epi_bar + 4);
+  s.fempty = s.epi_bar + 8;
+  s.afull = s.fempty + 4;
+  s.prog = reinterpret_cast<uint32_t*>(s.afull + 8);
   s.tmem_ptr = s.prog + 8;
   return s;
 }
 
-template <int NSTAGES, int CLUSTER = 1, int NEPI = 4>
+template <int NSTAGES, int CLUSTER = 1, int NEPI = 4, int FULL_COUNT = 1>
 __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
-      mbar_init(&s.full[i], 1);
+      mbar_init(&s.full[i], FULL_COUNT);
       mbar_init(&s.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tfull[i], 1);
       mbar_init(&s.tempty[i], NEPI * CLUSTER);  // one arrive per epilogue warp of every CTA feeding this accumulator
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&s.epi_bar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.epi_bar[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&s.fempty[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&s.afull[i], (NEPI / 2) * CLUSTER);  // 4 quadrant warps of every CTA
     for (int i = 0; i < 8; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
@@ -242,10 +262,13 @@ __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t
 // lines); the dgrad multiplier (stored snake derivative) arrives the same way through a TMA load.
 // scalar fields of an op, copied to registers once per op (the descriptor itself lives in global memory)
 struct EpiArgs {
-  const float* bias;
+  float bias_val;   // bias of output column (tile n0 + this thread's index among the 256 epilogue threads), prefetched
   float* colsum;
   float* out_f32;
   int ldf;
+  int fwd_out;      // the next op's first tile reads this op's output staging as its A blocks
+  int nt;           // N-tile index inside the op
+  bool leader;      // this CTA owns the UMMA-side barriers (always true without clusters)
 };
 
 template <int EPI>
@@ -253,73 +276,61 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
                                               uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
-                                              bool last_tile_of_op, uint32_t& deferred_seq, long long* dbg) {
+                                              bool last_tile_of_op, uint32_t& deferred_seq, long long* dbg,
+                                              uint32_t& fwd_phase) {
   constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
-  const bool stamp = dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+  const bool stamp = dbg != nullptr && lane == 0;
   if (stamp) dbg[0] = clock64();
   // Two warps share each TMEM lane quadrant (warps 2..5 take sub-tiles 0 and 1, warps 6..9 take 2 and 3), so the
   // latency chain of one sub-tile (TMEM load -> math -> fence -> TMA store) overlaps the other warp's work.
-  // Warp e ALWAYS owns staging buffers 2e and 2e+1 of its quadrant, whatever the epilogue type.
   const int q = warp & 3;
   const int e = (warp - 2) >> 2;
   const int lane_base = q * 32;
-  // per-quadrant staging (4 x 4 KB, 128B-swizzled 32x64 boxes):
-  //   snake        : warp e stages out0 in [2e] and out1 (snake derivative) in [2e+1], single-buffered
-  //   linear/dgrad : warp e stages its two sub-tiles in [2e] and [2e+1]
-  //   dgrad * d    : [sub] holds the multiplier of sub-tile `sub` (whole tile fetched during the accumulator wait);
-  //                  the result overwrites it in place and is stored from there
-  uint8_t* qbuf = s.epi + q * EPI_BUFS * EPI_BUF_BYTES;
-  uint64_t* ebar = &s.epi_bar[q];
+  // Output staging: block `sub` (16 KB) holds the 128 x 64 output sub-tile `sub` of the CTA in the 128-byte-swizzled
+  // K-major layout of a UMMA A operand (quadrant q = rows [32 q, 32 q + 32) at + 4 KB q).  The TMA store reads it
+  // from there, and when the op forwards (fwd_out) the next op's first tile reads it as its A block, no copy.
+  // Aux: one 4 KB box per warp: the snake derivative on its way out, or the dgrad multiplier on its way in.
+  uint8_t* aux = s.epi + EPI_OUT_BYTES + (warp - 2) * EPI_BUF_BYTES;
+  uint64_t* ebar = &s.epi_bar[warp - 2];
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const int row0 = m0 + lane_base;
   const int row = row0 + lane;
   const bool row_ok = row < M;
   const bool warp_ok = row0 < M;
-  const float* bias = p.bias;
-  float* colsum = p.colsum;
-  float* out_f32 = p.out_f32;
-  // a previous tile may have deferred its drain: its TMA stores must at least have finished READING the staging
-  // buffers before this tile reuses them (cheap: they were issued a whole accumulator wait ago)
-  if (lane == 0) bulk_wait_read0();
-  __syncwarp();
+  float* colsum = ea.colsum;
+  float* out_f32 = ea.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
-    // after this barrier both warps of the quadrant are done with the previous tile's buffers and the even warp
-    // refills all four with this tile's multiplier
-    asm volatile("bar.sync %0, 64;" ::"r"(3 + q) : "memory");
-    if (e == 0 && lane == 0) {
-      mbar_expect_tx(ebar, NSUB * EPI_BUF_BYTES);
-#pragma unroll
-      for (int t = 0; t < NSUB; ++t) tma_load_2d(qbuf + t * EPI_BUF_BYTES, &p.tmMul, ebar, n0 + t * EPI_COLS, row0);
+    // multiplier of this warp's first sub-tile: its latency hides behind the accumulator wait
+    if (lane == 0) {
+      mbar_expect_tx(ebar, EPI_BUF_BYTES);
+      tma_load_2d(aux, &p.tmMul, ebar, n0 + 2 * e * EPI_COLS, row0);
     }
   }
   if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
     // bias slice of this tile -> smem once (its load latency hides behind the accumulator wait); the two named
     // barriers order the refill against the other epilogue warps' reads of the previous tile's slice
     const int et = (warp - 2) * 32 + lane;  // 0..255
-    float bv = 0.f;
-    if (bias != nullptr) bv = __ldg(bias + n0 + et);
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    s.bias[et] = bv;
+    s.bias[et] = ea.bias_val;  // loaded from global memory a whole tile ago
     asm volatile("bar.sync 2, 256;" ::: "memory");
   }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
   if (stamp) dbg[1] = clock64();
-  if (EPI == EPI_DGRAD_MUL) {
-    mbar_wait(ebar, ld_phase);
-    ld_phase ^= 1;
-  }
 #pragma unroll 1
   for (int sub = 2 * e; sub < 2 * e + 2; ++sub) {
     const int col = n0 + sub * EPI_COLS;
-    uint8_t* obuf = qbuf + ((EPI == EPI_SNAKE) ? 2 * e : sub) * EPI_BUF_BYTES;
-    uint8_t* dbuf = qbuf + (2 * e + 1) * EPI_BUF_BYTES;
+    uint8_t* obuf = s.epi + sub * (4 * EPI_BUF_BYTES) + q * EPI_BUF_BYTES;
     // both 32-column halves of the sub-tile are fetched from TMEM before either is consumed
     uint32_t raw0[32], raw1[32];
     tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS, raw0);
     tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + sub * EPI_COLS + 32, raw1);
     tmem_ld_wait();
+    if (EPI == EPI_DGRAD_MUL) {
+      mbar_wait(ebar, ld_phase);
+      ld_phase ^= 1;
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float v[32];
@@ -364,7 +375,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t c = static_cast<uint32_t>(half * 4 + j);
-            const uint4 m4 = *reinterpret_cast<const uint4*>(obuf + row_off + ((c ^ sw) << 4));
+            const uint4 m4 = *reinterpret_cast<const uint4*>(aux + row_off + ((c ^ sw) << 4));
             const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -373,24 +384,44 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
               v[8 * j + 2 * t + 1] *= m2.y;
             }
           }
+          if (half == 1 && sub == 2 * e) {
+            // the whole box has been read: fetch the second sub-tile's multiplier into it while this one is packed
+            __syncwarp();
+            if (lane == 0) {
+              mbar_expect_tx(ebar, EPI_BUF_BYTES);
+              tma_load_2d(aux, &p.tmMul, ebar, col + EPI_COLS, row0);
+            }
+          }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
       }
-      if (EPI == EPI_SNAKE && half == 0 && sub == 2 * e + 1) {
-        // snake stages two tensors per sub-tile, so its second sub-tile reuses the buffers of the first: that
-        // store must have finished reading them (all other cases use each buffer once per tile; tiles end drained)
-        if (lane == 0) bulk_wait_read0();
+      if (half == 0) {
+        // Every sub-tile is one bulk group (out0 from staging block `sub`, snake: plus the derivative from the aux
+        // box).  Before overwriting a buffer the group that read it must have finished reading: block `sub` was read
+        // two groups ago (same sub-tile of the previous tile), the aux box by the previous group.  Asked here, a whole
+        // sub-tile of math after those stores were issued.
+        if (lane == 0) {
+          if (EPI == EPI_SNAKE) bulk_wait_read0();
+          else bulk_wait_read1();
+        }
         __syncwarp();
+        if (ea.fwd_out && ea.nt > 0) {
+          // Staging block `sub` still holds the previous tile's sub-tile, which the NEXT op's first tile reads as an
+          // A block: wait until its UMMAs have consumed it (one commit per block on the class barrier, so this warp
+          // sees every phase of the two blocks it owns).  Tile 0 needs no such wait: the previous occupant fed the
+          // tile whose accumulator this warp is draining.
+          mbar_wait(&s.fempty[sub], (fwd_phase >> (sub & 1)) & 1u);
+          fwd_phase ^= 1u << (sub & 1);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t c = static_cast<uint32_t>(half * 4 + j);
-        // dgrad: in place over this thread's own multiplier chunks (already consumed above)
         *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
             make_uint4(hd[4 * j], hd[4 * j + 1], hd[4 * j + 2], hd[4 * j + 3]);
         if (EPI == EPI_SNAKE)
-          *reinterpret_cast<uint4*>(dbuf + row_off + ((c ^ sw) << 4)) =
+          *reinterpret_cast<uint4*>(aux + row_off + ((c ^ sw) << 4)) =
               make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
       }
       if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
@@ -409,9 +440,14 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
+      if (ea.fwd_out) {  // this warp's 32 x 64 part of A block (4 nt + sub) of the next op is in place
+        uint64_t* afull = &s.afull[4 * ea.nt + sub];
+        if (ea.leader) mbar_arrive(afull);
+        else mbar_arrive_remote_relaxed(afull, 0);
+      }
       if (warp_ok) {
         tma_store_2d(&p.tmOut0, obuf, col, row0);
-        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, dbuf, col, row0);
+        if (EPI == EPI_SNAKE) tma_store_2d(&p.tmOut1, aux, col, row0);
         bulk_commit();
       }
       if (deferred_seq != 0) {
@@ -426,7 +462,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
   seq += NSUB;  // progress is published per tile: all sub-tiles (of both warps of the quadrant) up to here
   if (stamp) dbg[2] = clock64();
   if (last_tile_of_op) {
-    // the next op's K blocks 4.. wait for exactly this: drain the stores (~1 us) and publish right away
+    // the next op's second tile reloads this op's output from global memory: drain the stores (~1 us) and publish
     if (lane == 0) {
       bulk_wait0();
       publish_progress(&s.prog[warp - 2], seq);
@@ -478,6 +514,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         }
         const int nseg = p.nseg;
         const int op_tiles_n = p.tiles_n;
+        const bool fwd_in = p.fwd_in != 0;
         int r_kbs[2], r_ak0[2], r_bk0[2], r_br0[2], r_src[2];
         uint32_t r_srcbase[2], r_srctiles[2];
 #pragma unroll
@@ -506,18 +543,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
               if (src >= 0)
                 need0 = group_base + (uint32_t)gi * r_srcbase[seg] +
                         (uint32_t)sl * (r_srctiles[seg] * (uint32_t)(BN / EPI_COLS)) + ak0 / BK + 1;
+              // tile 0 / segment 0 of a forwarded op: the UMMAs read the A blocks from the previous op's output
+              // staging (ring position kb pairs with K block fwd_perm(kb)); only the weight half is loaded here
+              const bool fwd_blk = fwd_in && nt == 0 && seg == 0;
               for (int kb = 0; kb < kbs; ++kb) {
                 mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+                const int kbb = fwd_blk ? fwd_perm(kb) : kb;
+                const uint32_t a_bytes = fwd_blk ? 0u : (uint32_t)A_STAGE_BYTES;
                 if (lane == 0) {  // the weight tile never depends on this chain: fetch it while waiting for A
                   if (CLUSTER == 1) {
-                    mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + B_BYTES);
-                    tma_load_2d(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK, br0 + n0);
+                    mbar_expect_tx(&s.full[ps.stage], a_bytes + B_BYTES);
+                    tma_load_2d(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kbb * BK, br0 + n0);
                   } else {
                     // the leader's barrier collects the bytes of BOTH CTAs (A + half B each)
-                    if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
-                    tma_load_2d_pair(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kb * BK,
+                    if (leader) {
+                      mbar_expect_tx(&s.full[ps.stage], CLUSTER * (a_bytes + B_BYTES));
+                      }
+                    tma_load_2d_pair(s.b + ps.stage * B_BYTES, &p.tmB[seg], &s.full[ps.stage], bk0 + kbb * BK,
                                      br0 + n0 + (int)crank * B_ROWS);
                   }
+                }
+                if (fwd_blk) {
+                  __syncwarp();
+                  ps.advance();
+                  continue;
                 }
                 if (src >= 0 && static_cast<int32_t>(seen - (need0 + kb)) < 0) {
                   // wait until all eight epilogue warps have published this block, remember how far they are
@@ -528,7 +577,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 #pragma unroll
                   for (int o = 4; o >= 1; o >>= 1) ahead = min(ahead, __shfl_xor_sync(0xffffffffu, ahead, o));
                   seen = need + __shfl_sync(0xffffffffu, ahead, 0);
-                  if (lane == 0) fence_proxy_async_all();
+                  // No proxy fence: the data was written by the async proxy (TMA stores, complete and visible once
+                  // their wait_group returned, before the release above) and is read by the async proxy (TMA load).
                   __syncwarp();
                 }
                 if (lane == 0) {
@@ -555,6 +605,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       PipeStateT<NST> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int mma_tile_counter = 0;
+      uint32_t afull_phase = 0;  // one phase bit per forwarded A block barrier
       for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
         const int gi = min(STRIPE_GROUP, stripe_iters - si);
         for (int oi = 0; oi < cp.n_ops; ++oi) {
@@ -564,15 +616,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           int total_kb = 0;
           for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
           const int op_tiles = gi * p.tiles_n;
+          const bool fwd_in = p.fwd_in != 0;
+          const int kb_seg0 = p.kblocks[0];
           for (int tile = 0; tile < op_tiles; ++tile) {
+            long long* mdbg = (cp.dbg && (int)blockIdx.x == (cp.dbg_block & ~(CLUSTER - 1)) && lane == 0) ? cp.dbg + 8 * mma_tile_counter : nullptr;
+            ++mma_tile_counter;
             mbar_wait(&s.tempty[acc], acc_phase ^ 1);
             tc_fence_after();
+            if (mdbg) mdbg[5] = clock64();
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int it = 0; it < total_kb; ++it) {
               mbar_wait(&s.full[ps.stage], ps.phase);
               tc_fence_after();
+              if (mdbg && it == 0) mdbg[6] = clock64();
+              if (mdbg && it == total_kb - 1) mdbg[7] = clock64();
+              // forwarded K block: A comes straight from the previous op's output staging (no copy, no TMA)
+              const bool fwd_blk = fwd_in && tile == 0 && it < kb_seg0;
+              const int fblk = fwd_perm(it);
+              if (fwd_blk) {
+                if (CLUSTER == 1) mbar_wait(&s.afull[fblk], (afull_phase >> fblk) & 1u);
+                else mbar_wait_cluster(&s.afull[fblk], (afull_phase >> fblk) & 1u);  // the peer's warps arrive too
+                afull_phase ^= 1u << fblk;
+                tc_fence_after();
+              }
               if (lane == 0) {
-                const uint32_t a_addr = smem_u32(s.a + ps.stage * A_STAGE_BYTES);
+                const uint32_t a_addr = fwd_blk ? smem_u32(s.epi + (fblk & 3) * (4 * EPI_BUF_BYTES))
+                                                : smem_u32(s.a + ps.stage * A_STAGE_BYTES);
                 const uint32_t b_addr = smem_u32(s.b + ps.stage * B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -585,6 +654,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 }
                 if (CLUSTER == 1) umma_commit(&s.empty[ps.stage]);
                 else umma_commit_pair(&s.empty[ps.stage], pair_mask);   // frees the stage in both CTAs
+                // staging block fblk held sub-tile fblk of the previous op's FIRST tile; once these UMMAs are done its
+                // second tile may overwrite it (only if there is a second tile: one wait per commit)
+                if (fwd_blk && it < 4 && kb_seg0 > 4) {
+                  if (CLUSTER == 1) umma_commit(&s.fempty[fblk]);
+                  else umma_commit_pair(&s.fempty[fblk], pair_mask);
+                }
               }
               __syncwarp();
               ps.advance();
@@ -608,6 +683,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     int tile_counter = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t fwd_phase = 0;  // phase bits of the two forwarding class barriers this warp waits on
+    const int et_idx = (warp - 2) * 32 + lane;  // this thread's column inside a 256-wide tile (bias staging)
+    float bias_pref = 0.f;
+    bool first_tile = true;
+    static_assert(STRIPE_GROUP == 1, "on-chip forwarding assumes one stripe at a time");
     for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
       const int gi = min(STRIPE_GROUP, stripe_iters - si);
       const bool final_group = si + gi >= stripe_iters;
@@ -621,19 +701,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         const int epi = p.epi;
         const int op_tiles_n = p.tiles_n;
         EpiArgs ea;
-        ea.bias = p.bias;
+        const float* op_bias = p.bias;
+        // the bias row of the op that follows in processing order (its first tile is prefetched during this op's last)
+        const float* next_op_bias = nullptr;
+        if (oi + 1 < cp.n_ops) next_op_bias = cp.ops[oi + 1].bias;
+        else if (si + gi < stripe_iters) next_op_bias = cp.ops[0].bias;
+        if (first_tile) {
+          bias_pref = op_bias != nullptr ? __ldg(op_bias + et_idx) : 0.f;
+          first_tile = false;
+        }
         ea.colsum = p.colsum;
         ea.out_f32 = p.out_f32;
         ea.ldf = p.ldf;
+        ea.fwd_out = p.fwd_out;
+        ea.leader = CLUSTER == 1 || leader;
         for (int sl = 0; sl < gi; ++sl) {
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
           for (int nt = 0; nt < op_tiles_n; ++nt) {
+            ea.nt = nt;
+            ea.bias_val = bias_pref;
+            {  // bias of the NEXT tile: in flight while this tile is drained
+              const float* nb = nt + 1 < op_tiles_n ? op_bias : next_op_bias;
+              const int ncol = nt + 1 < op_tiles_n ? (nt + 1) * BN : 0;
+              bias_pref = nb != nullptr ? __ldg(nb + ncol + et_idx) : 0.f;
+            }
             const uint32_t tacc = tmem_base + acc * BN;
             const int n0 = nt * BN;
             // Publish right away only when somebody is about to wait for it: a lone stripe's last tile of an op
             // (its next op is next in line) and the very last tile of the kernel.  Everything else is published
             // from inside the following tile (the consumer of an interleaved stripe comes a whole stripe later).
-            long long* dbgp = cp.dbg ? cp.dbg + 4 * tile_counter : nullptr;
+            long long* dbgp = (cp.dbg && (int)blockIdx.x == cp.dbg_block && warp == cp.dbg_warp) ? cp.dbg + 8 * tile_counter : nullptr;
             ++tile_counter;
             const bool last_of_stripe_op = nt == op_tiles_n - 1;
             const bool last = (gi == 1 && last_of_stripe_op) ||
@@ -641,19 +738,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             switch (epi) {
               case EPI_LINEAR:
                 epilogue_tile<EPI_LINEAR>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                          last, deferred, dbgp);
+                                          last, deferred, dbgp, fwd_phase);
                 break;
               case EPI_SNAKE:
                 epilogue_tile<EPI_SNAKE>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred, dbgp);
+                                         last, deferred, dbgp, fwd_phase);
                 break;
               case EPI_DGRAD_MUL:
                 epilogue_tile<EPI_DGRAD_MUL>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
-                                             seq, last, deferred, dbgp);
+                                             seq, last, deferred, dbgp, fwd_phase);
                 break;
               default:
                 epilogue_tile<EPI_DGRAD>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred, dbgp);
+                                         last, deferred, dbgp, fwd_phase);
                 break;
             }
             tc_fence_before();
@@ -661,7 +758,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             if (lane == 0) {
               // the accumulator stage is released on the LEADER's barrier (it gates the leader's next UMMAs)
               if (CLUSTER == 1 || leader) mbar_arrive(&s.tempty[acc]);
-              else mbar_arrive_remote(&s.tempty[acc], 0);
+              else mbar_arrive_remote_relaxed(&s.tempty[acc], 0);
+              if (dbgp != nullptr) dbgp[4] = clock64();
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -680,7 +778,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 //   [n0 + 128 r, +128)), so a pair moves 64 KB per K block for twice the MMA work (the single-CTA kernel is L2
 //   bandwidth bound: 1.5 GB of operand reads per step at 16 k rows).
 constexpr int WG_PAIR_STAGES = 5;
-constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 256 + 1024;
+constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 512 + 1024;
 
 template <int CLUSTER>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {

@@ -525,6 +525,42 @@ static int alloc_plan_memory(NppPlan* p) {
   return 0;
 }
 
+// Completes a chain's op list: stages per tile, and on-chip forwarding between consecutive ops where the next op
+// reads this op's whole output (<= 512 columns) as one K segment.  That segment becomes segment 0 of the next op
+// (the order of K segments only changes the fp32 summation order).
+static void finish_chain_ops(std::vector<KmajorParams>& ops, int cluster) {
+  for (auto& k : ops) {
+    k.kb_per_tile = 0;
+    for (int s = 0; s < k.nseg; ++s) k.kb_per_tile += k.kblocks[s];
+    k.fwd_in = k.fwd_out = 0;
+  }
+  // Needs the 4-stage ring of the pair kernel: the four blocks of a tile must land in four different stages whose
+  // previous occupants belong to UMMAs that do not wait for this very epilogue (with 3 stages block 3 would wait
+  // for the next op's first UMMA, which waits for this tile's accumulator: a cycle).
+  if (cluster != 2 || getenv("NPP_NO_FWD")) return;
+  static_assert(PAIR_STAGES == 4, "on-chip forwarding is laid out for a 4-stage ring");
+  for (size_t i = 0; i + 1 < ops.size(); ++i) {
+    KmajorParams& cur = ops[i];
+    KmajorParams& nxt = ops[i + 1];
+    if (cur.tiles_n < 1 || cur.tiles_n > 2) continue;
+    int sseg = -1;
+    for (int s = 0; s < nxt.nseg; ++s)
+      if (nxt.a_src[s] == (int)i && nxt.a_k0[s] == 0 && nxt.kblocks[s] == cur.tiles_n * (BN / BK)) sseg = s;
+    if (sseg < 0) continue;
+    if (sseg == 1) {
+      std::swap(nxt.tmA[0], nxt.tmA[1]);
+      std::swap(nxt.tmB[0], nxt.tmB[1]);
+      std::swap(nxt.kblocks[0], nxt.kblocks[1]);
+      std::swap(nxt.a_k0[0], nxt.a_k0[1]);
+      std::swap(nxt.b_k0[0], nxt.b_k0[1]);
+      std::swap(nxt.b_row0[0], nxt.b_row0[1]);
+      std::swap(nxt.a_src[0], nxt.a_src[1]);
+    }
+    cur.fwd_out = 1;
+    nxt.fwd_in = 1;
+  }
+}
+
 // ------------------------------------------------------------------- per-row-count setup
 static int prepare(NppPlan* p, long long n) {
   if (n <= 0 || n > p->cfg.max_rows)
@@ -615,6 +651,8 @@ static int prepare(NppPlan* p, long long n) {
   }
   p->fwd_subs = fwd_subs;
   p->dgrad_subs = dg_subs;
+  finish_chain_ops(p->fwd_params, p->cluster);
+  finish_chain_ops(p->dgrad_params, p->cluster);
   CK(cudaMemcpy(p->d_fwd_ops, p->fwd_params.data(), p->fwd_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_dgrad_ops, p->dgrad_params.data(), p->dgrad_params.size() * sizeof(KmajorParams),
                 cudaMemcpyHostToDevice));
@@ -658,6 +696,8 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   cp.tiles_m = (M + BM - 1) / BM;
   cp.subs_per_stripe = subs_per_stripe;
   cp.dbg = g_chain_dbg;
+  cp.dbg_block = getenv("NPP_DEBUG_STAMP_BLOCK") ? atoi(getenv("NPP_DEBUG_STAMP_BLOCK")) : 0;
+  cp.dbg_warp = getenv("NPP_DEBUG_STAMP_WARP") ? atoi(getenv("NPP_DEBUG_STAMP_WARP")) : 2;
   int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
   if (cluster == 1) {
     npp_gemm_kmajor<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
@@ -1183,6 +1223,11 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
   CK(cudaMalloc(&d_op, sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
   kp.a_src[0] = kp.a_src[1] = -1;
+  {
+    std::vector<KmajorParams> one(1, kp);
+    finish_chain_ops(one, 1);
+    kp = one[0];
+  }
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
   int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / EPI_COLS));
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
@@ -1234,14 +1279,15 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
     }
   else
     for (int i = 0; i < chain; ++i) ops[i].sub_base = i * subs_op;
+  finish_chain_ops(ops, cluster);
   KmajorParams* d_op = nullptr;
   CK(cudaMalloc(&d_op, ops.size() * sizeof(KmajorParams)));
   CK(cudaMemcpy(d_op, ops.data(), ops.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
   long long* d_dbg = nullptr;
   const int n_stamp_tiles = chain * (n / BN) * ((m + BM - 1) / BM / sms + 1);
   if (getenv("NPP_DEBUG_STAMPS")) {
-    CK(cudaMalloc(&d_dbg, (size_t)n_stamp_tiles * 4 * sizeof(long long)));
-    CK(cudaMemset(d_dbg, 0, (size_t)n_stamp_tiles * 4 * sizeof(long long)));
+    CK(cudaMalloc(&d_dbg, (size_t)n_stamp_tiles * 8 * sizeof(long long)));
+    CK(cudaMemset(d_dbg, 0, (size_t)n_stamp_tiles * 8 * sizeof(long long)));
   }
   for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e0, 0));
@@ -1256,13 +1302,16 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
     g_chain_dbg = nullptr;
     cudaDeviceSynchronize();
     if (r2 == 0) {
-      std::vector<long long> h((size_t)n_stamp_tiles * 4);
+      std::vector<long long> h((size_t)n_stamp_tiles * 8);
       cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       const int shown = chain * (n / BN) < n_stamp_tiles ? chain * (n / BN) : n_stamp_tiles;
+      const long long t0 = h[0];
+      // epilogue warp 2 of CTA 0: enter, accumulator ready, sub-tiles done, tile done, accumulator released;
+      // UMMA warp of CTA 0: accumulator free, first K block landed, last K block landed (all clocks since the first stamp)
       for (int i = 0; i < shown; ++i) {
-        const long long* q = &h[(size_t)i * 4];
-        printf("  tile %2d: wait %6lld  subs %6lld  tail %6lld  | period %6lld clk\n", i, q[1] - q[0], q[2] - q[1],
-               q[3] - q[2], i ? q[0] - h[(size_t)(i - 1) * 4] : 0LL);
+        const long long* q = &h[(size_t)i * 8];
+        printf("  tile %2d: epi enter %7lld ready %7lld subs %7lld done %7lld released %7lld | mma free %7lld kb0 %7lld kbN %7lld\n",
+               i, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - t0);
       }
       fflush(stdout);
     }

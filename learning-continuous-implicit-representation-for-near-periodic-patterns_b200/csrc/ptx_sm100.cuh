@@ -39,6 +39,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// wait that synchronises with release.cluster arrives of the peer CTA (generic-proxy data forwarded through smem)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -98,6 +114,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t targe
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      :
+      : "r"(smem_u32(bar)), "r"(target_rank)
+      : "memory");
+}
+// Same without the release fence (which compiles to MEMBAR.ALL.GPU and costs ~2000 clocks per arrive).  For
+// signals that do not publish generic-proxy global memory: "my tcgen05.ld of the accumulator are done" (ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync) and "my part of an smem operand is written" (ordered by the
+// fence.proxy.async each lane executed before the __syncwarp that precedes this arrive).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t target_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
       :
       : "r"(smem_u32(bar)), "r"(target_rank)
       : "memory");
