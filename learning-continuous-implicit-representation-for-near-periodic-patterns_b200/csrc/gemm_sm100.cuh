@@ -93,10 +93,25 @@ struct alignas(64) KmajorParams {
 // 0, 2, 1, 3 (two warps per TMEM lane quadrant, two sub-tiles each), so the UMMAs consume them in that order
 __host__ __device__ constexpr int fwd_perm(int p) { return (p & ~3) | ((p & 1) << 1) | ((p >> 1) & 1); }
 
+// The scalar part of an op, copied into the kernel parameters (constant bank): the roles read it at every op
+// boundary, and a dependent chain of global loads there (~1500 clocks) is exactly where the pipeline has no slack.
+constexpr int MAX_CHAIN_OPS = 16;
+struct OpScalars {
+  int nseg, tiles_n, epi, fwd_in, fwd_out, kb_per_tile;
+  int kblocks[2], a_k0[2], b_k0[2], b_row0[2], a_src[2];
+  int src_sub_base[2], src_tiles_n[2];  // sub_base / tiles_n of op a_src[s]
+  int ldf, k_adv;
+  const float* bias;
+  float* colsum;
+  float* out_f32;
+  unsigned long long desc_hi;
+};
+
 // A chain = ops executed in order for every 128-row stripe; op i may read what ops < i wrote for the
 // same rows (rows are independent in forward and dgrad), so a CTA that owns a stripe needs no grid sync.
 struct ChainParams {
-  const KmajorParams* ops;  // device array
+  OpScalars sc[MAX_CHAIN_OPS];
+  const KmajorParams* ops;  // device array (tensor maps)
   int n_ops;
   int M;
   int tiles_m;
@@ -507,25 +522,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
-          for (int i = 0; i < p.nseg; ++i) {
+          for (int i = 0; i < cp.sc[oi].nseg; ++i) {
             tma_prefetch_desc(&p.tmA[i]);
             tma_prefetch_desc(&p.tmB[i]);
           }
         }
-        const int nseg = p.nseg;
-        const int op_tiles_n = p.tiles_n;
-        const bool fwd_in = p.fwd_in != 0;
+        const OpScalars& sc = cp.sc[oi];
+        const int nseg = sc.nseg;
+        const int op_tiles_n = sc.tiles_n;
+        const bool fwd_in = sc.fwd_in != 0;
         int r_kbs[2], r_ak0[2], r_bk0[2], r_br0[2], r_src[2];
         uint32_t r_srcbase[2], r_srctiles[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          r_kbs[q] = q < nseg ? p.kblocks[q] : 0;
-          r_ak0[q] = p.a_k0[q];
-          r_bk0[q] = p.b_k0[q];
-          r_br0[q] = p.b_row0[q];
-          r_src[q] = q < nseg ? p.a_src[q] : -1;
-          r_srcbase[q] = r_src[q] >= 0 ? (uint32_t)cp.ops[r_src[q]].sub_base : 0u;
-          r_srctiles[q] = r_src[q] >= 0 ? (uint32_t)cp.ops[r_src[q]].tiles_n : 0u;
+          r_kbs[q] = q < nseg ? sc.kblocks[q] : 0;
+          r_ak0[q] = sc.a_k0[q];
+          r_bk0[q] = sc.b_k0[q];
+          r_br0[q] = sc.b_row0[q];
+          r_src[q] = q < nseg ? sc.a_src[q] : -1;
+          r_srcbase[q] = r_src[q] >= 0 ? (uint32_t)sc.src_sub_base[q] : 0u;
+          r_srctiles[q] = r_src[q] >= 0 ? (uint32_t)sc.src_tiles_n[q] : 0u;
         }
         for (int sl = 0; sl < gi; ++sl) {
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
@@ -611,13 +627,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         const int gi = min(STRIPE_GROUP, stripe_iters - si);
         for (int oi = 0; oi < cp.n_ops; ++oi) {
           const KmajorParams& p = cp.ops[oi];
-          const uint64_t dhi = p.desc_hi ? p.desc_hi : umma_desc_hi(16, 1024);
-          const int kadv = p.k_adv ? p.k_adv : UMMA_K * 2;
-          int total_kb = 0;
-          for (int seg = 0; seg < p.nseg; ++seg) total_kb += p.kblocks[seg];
-          const int op_tiles = gi * p.tiles_n;
-          const bool fwd_in = p.fwd_in != 0;
-          const int kb_seg0 = p.kblocks[0];
+          const OpScalars& sc = cp.sc[oi];
+          const uint64_t dhi = sc.desc_hi ? sc.desc_hi : umma_desc_hi(16, 1024);
+          const int kadv = sc.k_adv ? sc.k_adv : UMMA_K * 2;
+          const int total_kb = sc.kb_per_tile;
+          const int op_tiles = gi * sc.tiles_n;
+          const bool fwd_in = sc.fwd_in != 0;
+          const int kb_seg0 = sc.kblocks[0];
           for (int tile = 0; tile < op_tiles; ++tile) {
             long long* mdbg = (cp.dbg && (int)blockIdx.x == (cp.dbg_block & ~(CLUSTER - 1)) && lane == 0) ? cp.dbg + 8 * mma_tile_counter : nullptr;
             ++mma_tile_counter;
@@ -695,25 +711,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         const KmajorParams& p = cp.ops[oi];
         if (lane == 0) {
           tma_prefetch_desc(&p.tmOut0);
-          if (p.epi == EPI_SNAKE) tma_prefetch_desc(&p.tmOut1);
-          if (p.epi == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
+          if (cp.sc[oi].epi == EPI_SNAKE) tma_prefetch_desc(&p.tmOut1);
+          if (cp.sc[oi].epi == EPI_DGRAD_MUL) tma_prefetch_desc(&p.tmMul);
         }
-        const int epi = p.epi;
-        const int op_tiles_n = p.tiles_n;
+        const OpScalars& sc = cp.sc[oi];
+        const int epi = sc.epi;
+        const int op_tiles_n = sc.tiles_n;
         EpiArgs ea;
-        const float* op_bias = p.bias;
+        const float* op_bias = sc.bias;
         // the bias row of the op that follows in processing order (its first tile is prefetched during this op's last)
         const float* next_op_bias = nullptr;
-        if (oi + 1 < cp.n_ops) next_op_bias = cp.ops[oi + 1].bias;
-        else if (si + gi < stripe_iters) next_op_bias = cp.ops[0].bias;
+        if (oi + 1 < cp.n_ops) next_op_bias = cp.sc[oi + 1].bias;
+        else if (si + gi < stripe_iters) next_op_bias = cp.sc[0].bias;
         if (first_tile) {
           bias_pref = op_bias != nullptr ? __ldg(op_bias + et_idx) : 0.f;
           first_tile = false;
         }
-        ea.colsum = p.colsum;
-        ea.out_f32 = p.out_f32;
-        ea.ldf = p.ldf;
-        ea.fwd_out = p.fwd_out;
+        ea.colsum = sc.colsum;
+        ea.out_f32 = sc.out_f32;
+        ea.ldf = sc.ldf;
+        ea.fwd_out = sc.fwd_out;
         ea.leader = CLUSTER == 1 || leader;
         for (int sl = 0; sl < gi; ++sl) {
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;

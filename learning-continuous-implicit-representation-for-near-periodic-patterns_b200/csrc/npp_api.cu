@@ -110,6 +110,8 @@ struct DgradOp {
 
 enum { PROF_ENCODE = 0, PROF_GEMM_FWD, PROF_HEAD_LOSS, PROF_GEMM_DGRAD, PROF_GEMM_WGRAD, PROF_FINALIZE, PROF_ADAM, NPP_PROF_CLASSES };
 
+constexpr long long WG_ROWS_PER_SPLIT = 32768;  // rows one split-K accumulator of the wgrad kernel may see
+
 struct NppPlan {
   NppConfig cfg;
   EncTable enc;
@@ -142,7 +144,9 @@ struct NppPlan {
   KmajorParams* d_dgrad_ops = nullptr;  // dgrad chain
   WgUnit* d_units = nullptr;
   int n_units = 0;
-  int splits_max = 0;
+  int splits_max = 0;       // slabs allocated
+  int splits_fill = 1;      // splits that give every CTA pair a unit (or the caller's explicit choice)
+  bool splits_auto = false;
   int num_sms = 148;
   int cluster = 2;   // 2: the chain kernel runs on CTA pairs with cta_group::2 UMMAs; 1: single-CTA UMMAs
   int wg_cluster = 2;  // same choice for the weight-gradient kernel (256 x 256 tile per CTA pair)
@@ -380,7 +384,12 @@ static int alloc_plan_memory(NppPlan* p) {
     const int slots = p->num_sms / p->wg_cluster;
     S = tiles > 0 ? (slots + tiles / 2) / tiles : 1;
     if (S < 1) S = 1;
+    p->splits_auto = true;
   }
+  p->splits_fill = S;
+  // one fp32 accumulator should not see more than WG_ROWS_PER_SPLIT rows: beyond that the rounding of the running
+  // sum shows (2^18 rows in one split: 1.1e-4 relative difference between a batch and its two halves)
+  if (p->splits_auto) S = std::max(S, (int)((p->cfg.max_rows + WG_ROWS_PER_SPLIT - 1) / WG_ROWS_PER_SPLIT));
   if (S > NPP_MAX_SPLITS) S = NPP_MAX_SPLITS;
   p->splits_max = S;
   CK(cudaMalloc(&p->partial, (size_t)S * p->slab_stride * sizeof(float)));
@@ -643,7 +652,7 @@ static int prepare(NppPlan* p, long long n) {
       k.ldm = P.out;
       k.tmMul = p->map_ep[P.buf_d];
     }
-    k.colsum = p->acc + P.bg_off;
+    k.colsum = getenv("NPP_DEBUG_NO_COLSUM") ? nullptr : p->acc + P.bg_off;   // (timing experiments)
     k.epi = P.act ? EPI_DGRAD_MUL : EPI_DGRAD;
     p->dgrad_params.push_back(k);
   }
@@ -662,7 +671,10 @@ static int prepare(NppPlan* p, long long n) {
   w.n_units = p->n_units;
   w.rows = (int)n;
   const int kb_total = (int)((n + BK - 1) / BK);
-  w.kb_per_split = (kb_total + p->splits_max - 1) / p->splits_max;
+  int want_splits = p->splits_fill;
+  if (p->splits_auto) want_splits = std::max(want_splits, (int)((n + WG_ROWS_PER_SPLIT - 1) / WG_ROWS_PER_SPLIT));
+  if (want_splits > p->splits_max) want_splits = p->splits_max;
+  w.kb_per_split = (kb_total + want_splits - 1) / want_splits;
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
   w.partial = p->partial;
   w.slab_stride = p->slab_stride;
@@ -684,10 +696,27 @@ static int set_smem_attrs() {
 
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
 // cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
-static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms, cudaStream_t st, int subs_per_stripe,
-                        int cluster = 1) {
+static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, int n_ops, int M, int num_sms,
+                        cudaStream_t st, int subs_per_stripe, int cluster = 1) {
   CKI(set_smem_attrs());
+  if (n_ops > MAX_CHAIN_OPS) return fail("chain longer than MAX_CHAIN_OPS");
   ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  for (int i = 0; i < n_ops; ++i) {
+    const KmajorParams& k = h_ops[i];
+    OpScalars& sc = cp.sc[i];
+    sc.nseg = k.nseg; sc.tiles_n = k.tiles_n; sc.epi = k.epi;
+    sc.fwd_in = k.fwd_in; sc.fwd_out = k.fwd_out; sc.kb_per_tile = k.kb_per_tile;
+    for (int s = 0; s < 2; ++s) {
+      sc.kblocks[s] = k.kblocks[s]; sc.a_k0[s] = k.a_k0[s]; sc.b_k0[s] = k.b_k0[s];
+      sc.b_row0[s] = k.b_row0[s]; sc.a_src[s] = s < k.nseg ? k.a_src[s] : -1;
+      const int src = sc.a_src[s];
+      sc.src_sub_base[s] = src >= 0 ? h_ops[src].sub_base : 0;
+      sc.src_tiles_n[s] = src >= 0 ? h_ops[src].tiles_n : 0;
+    }
+    sc.ldf = k.ldf; sc.k_adv = k.k_adv; sc.bias = k.bias; sc.colsum = k.colsum; sc.out_f32 = k.out_f32;
+    sc.desc_hi = k.desc_hi;
+  }
   cp.ops = d_ops;
   cp.n_ops = n_ops;
   cp.M = M;
@@ -717,6 +746,37 @@ static int launch_chain(const KmajorParams* d_ops, int n_ops, int M, int num_sms
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // NPP_DEBUG_MODEL_STAMPS=<k>: the k-th chain launch of the process prints the per-tile clock stamps of one CTA
+  static int model_stamp_calls = 0;
+  const char* ms_env = getenv("NPP_DEBUG_MODEL_STAMPS");
+  if (ms_env != nullptr && cp.dbg == nullptr && ++model_stamp_calls == atoi(ms_env)) {
+    const int max_tiles = 256;
+    long long* d_dbg = nullptr;
+    CK(cudaMalloc(&d_dbg, (size_t)max_tiles * 8 * sizeof(long long)));
+    CK(cudaMemset(d_dbg, 0, (size_t)max_tiles * 8 * sizeof(long long)));
+    cp.dbg = d_dbg;
+    CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)max_tiles * 8);
+    CK(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    std::vector<KmajorParams> ops((size_t)n_ops);
+    CK(cudaMemcpy(ops.data(), d_ops, ops.size() * sizeof(KmajorParams), cudaMemcpyDeviceToHost));
+    int tile = 0;
+    const long long t0 = h[0];
+    long long prev_enter = t0;
+    for (int oi = 0; oi < n_ops && tile < max_tiles; ++oi)
+      for (int nt = 0; nt < ops[oi].tiles_n && tile < max_tiles; ++nt, ++tile) {
+        const long long* q = &h[(size_t)tile * 8];
+        printf("  op %2d tile %d (epi %d kb %2d fwd_in %d): enter %7lld (+%6lld) ready %7lld subs %7lld done %7lld released %7lld | "
+               "mma free %7lld kb0 %7lld kbN %7lld\n",
+               oi, nt, ops[oi].epi, ops[oi].kb_per_tile, ops[oi].fwd_in, q[0] - t0, q[0] - prev_enter, q[1] - t0, q[2] - t0,
+               q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - t0);
+        prev_enter = q[0];
+      }
+    fflush(stdout);
+    cudaFree(d_dbg);
+    return 0;
+  }
   CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
   return 0;
 }
@@ -773,7 +833,8 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
   }
   {
     ProfScope ps(p, st, PROF_GEMM_FWD, 1);
-    CKI(launch_chain(p->d_fwd_ops, (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs, p->cluster));
+    CKI(launch_chain(p->d_fwd_ops, p->fwd_params.data(), (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs,
+                     p->cluster));
     ++p->launches;
   }
   if (!with_head) return 0;
@@ -805,7 +866,8 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_GEMM_DGRAD, 1);
-    CKI(launch_chain(p->d_dgrad_ops, (int)p->dgrads.size(), (int)n, p->num_sms, st, p->dgrad_subs, p->cluster));
+    CKI(launch_chain(p->d_dgrad_ops, p->dgrad_params.data(), (int)p->dgrads.size(), (int)n, p->num_sms, st,
+                     p->dgrad_subs, p->cluster));
     ++p->launches;
   }
   {
@@ -1227,7 +1289,7 @@ int npp_debug_gemm(const void* a, const void* b, float* c, int m, int n, int k, 
     kp = one[0];
   }
   CK(cudaMemcpy(d_op, &kp, sizeof(KmajorParams), cudaMemcpyHostToDevice));
-  int r = launch_chain(d_op, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / EPI_COLS));
+  int r = launch_chain(d_op, &kp, 1, m, sms, (cudaStream_t)stream, (n / BN) * (BN / EPI_COLS));
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(scratch);
   cudaFree(d_op);
@@ -1287,16 +1349,16 @@ int npp_debug_gemm_bench(const void* a, const void* b, void* out0, void* out1, i
     CK(cudaMalloc(&d_dbg, (size_t)n_stamp_tiles * 8 * sizeof(long long)));
     CK(cudaMemset(d_dbg, 0, (size_t)n_stamp_tiles * 8 * sizeof(long long)));
   }
-  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
+  for (int i = 0; i < 3; ++i) CKI(launch_chain(d_op, ops.data(), chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e0, 0));
-  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster));
+  for (int i = 0; i < iters; ++i) CKI(launch_chain(d_op, ops.data(), chain, m, sms, 0, chain * subs_op, cluster));
   CK(cudaEventRecord(e1, 0));
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(ms_out, e0, e1));
   *ms_out /= (float)chain;
   if (d_dbg) {   // one extra stamped launch, printed as per-tile phase durations in clocks
     g_chain_dbg = d_dbg;
-    int r2 = launch_chain(d_op, chain, m, sms, 0, chain * subs_op, cluster);
+    int r2 = launch_chain(d_op, ops.data(), chain, m, sms, 0, chain * subs_op, cluster);
     g_chain_dbg = nullptr;
     cudaDeviceSynchronize();
     if (r2 == 0) {
