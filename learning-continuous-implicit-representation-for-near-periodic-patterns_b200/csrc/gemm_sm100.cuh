@@ -281,6 +281,8 @@ struct EpiArgs {
   float* colsum;
   float* out_f32;
   int ldf;
+  const CUtensorMap* next_mul;  // dgrad * d: multiplier map of the tile that follows in this stripe (nullptr: none)
+  int next_mul_col;             // its first column
   int fwd_out;      // the next op's first tile reads this op's output staging as its A blocks
   int nt;           // N-tile index inside the op
   bool leader;      // this CTA owns the UMMA-side barriers (always true without clusters)
@@ -292,7 +294,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
                                               uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
                                               bool last_tile_of_op, uint32_t& deferred_seq, long long* dbg,
-                                              uint32_t& fwd_phase) {
+                                              uint32_t& fwd_phase, bool& mul_ready) {
   constexpr int NSUB = BN / EPI_COLS;  // 4 sub-tiles of 64 columns
   const bool stamp = dbg != nullptr && lane == 0;
   if (stamp) dbg[0] = clock64();
@@ -316,12 +318,14 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
   float* colsum = ea.colsum;
   float* out_f32 = ea.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
-    // multiplier of this warp's first sub-tile: its latency hides behind the accumulator wait
-    if (lane == 0) {
+    // Multiplier of this warp's first sub-tile.  Normally the previous tile already asked for it (right after it had
+    // read its own last multiplier out of the aux box), so that the load has a whole sub-tile of work to land.
+    if (!mul_ready && lane == 0) {
       mbar_expect_tx(ebar, EPI_BUF_BYTES);
       tma_load_2d(aux, &p.tmMul, ebar, n0 + 2 * e * EPI_COLS, row0);
     }
   }
+  mul_ready = false;
   if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
     // bias slice of this tile -> smem once (its load latency hides behind the accumulator wait); the two named
     // barriers order the refill against the other epilogue warps' reads of the previous tile's slice
@@ -399,12 +403,21 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
               v[8 * j + 2 * t + 1] *= m2.y;
             }
           }
-          if (half == 1 && sub == 2 * e) {
-            // the whole box has been read: fetch the second sub-tile's multiplier into it while this one is packed
+          if (half == 1) {
+            // the whole box has been read: fetch the next multiplier into it while this sub-tile is packed and stored
+            // (the second sub-tile of this tile, or the first one of the tile that follows)
             __syncwarp();
-            if (lane == 0) {
-              mbar_expect_tx(ebar, EPI_BUF_BYTES);
-              tma_load_2d(aux, &p.tmMul, ebar, col + EPI_COLS, row0);
+            if (sub == 2 * e) {
+              if (lane == 0) {
+                mbar_expect_tx(ebar, EPI_BUF_BYTES);
+                tma_load_2d(aux, &p.tmMul, ebar, col + EPI_COLS, row0);
+              }
+            } else if (ea.next_mul != nullptr) {
+              if (lane == 0) {
+                mbar_expect_tx(ebar, EPI_BUF_BYTES);
+                tma_load_2d(aux, ea.next_mul, ebar, ea.next_mul_col + 2 * e * EPI_COLS, row0);
+              }
+              mul_ready = true;
             }
           }
         }
@@ -700,6 +713,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t fwd_phase = 0;  // phase bits of the two forwarding class barriers this warp waits on
+    bool mul_ready = false;  // the dgrad multiplier of the coming tile's first sub-tile is already on its way
     const int et_idx = (warp - 2) * 32 + lane;  // this thread's column inside a 256-wide tile (bias staging)
     float bias_pref = 0.f;
     bool first_tile = true;
@@ -736,6 +750,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
           const int m0 = ((si + sl) * (int)gridDim.x + (int)blockIdx.x) * BM;
           for (int nt = 0; nt < op_tiles_n; ++nt) {
             ea.nt = nt;
+            ea.next_mul = nullptr;
+            ea.next_mul_col = 0;
+            if (epi == EPI_DGRAD_MUL && gi == 1) {  // the tile that follows in this stripe, if it multiplies too
+              if (nt + 1 < op_tiles_n) {
+                ea.next_mul = &p.tmMul;
+                ea.next_mul_col = (nt + 1) * BN;
+              } else if (oi + 1 < cp.n_ops && cp.sc[oi + 1].epi == EPI_DGRAD_MUL) {
+                ea.next_mul = &cp.ops[oi + 1].tmMul;
+              }
+            }
             ea.bias_val = bias_pref;
             {  // bias of the NEXT tile: in flight while this tile is drained
               const float* nb = nt + 1 < op_tiles_n ? op_bias : next_op_bias;
@@ -755,19 +779,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
             switch (epi) {
               case EPI_LINEAR:
                 epilogue_tile<EPI_LINEAR>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                          last, deferred, dbgp, fwd_phase);
+                                          last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               case EPI_SNAKE:
                 epilogue_tile<EPI_SNAKE>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred, dbgp, fwd_phase);
+                                         last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               case EPI_DGRAD_MUL:
                 epilogue_tile<EPI_DGRAD_MUL>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
-                                             seq, last, deferred, dbgp, fwd_phase);
+                                             seq, last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               default:
                 epilogue_tile<EPI_DGRAD>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
-                                         last, deferred, dbgp, fwd_phase);
+                                         last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
             }
             tc_fence_before();

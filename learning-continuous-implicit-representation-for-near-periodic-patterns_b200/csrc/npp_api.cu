@@ -808,7 +808,7 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
 }
 
 static int run_forward(NppPlan* p, const float* coords, long long n, float* logits, cudaStream_t st, bool with_head = true,
-                       const float* enc_f32 = nullptr) {
+                       const float* enc_f32 = nullptr, float* zero_loss = nullptr) {
   if (!p->params) return fail("npp_plan_bind has not been called");
   CKI(prepare(p, n));
   if (enc_f32 != nullptr) {
@@ -827,7 +827,8 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     const size_t smem = (size_t)enc_base_bytes(rows, B) + (size_t)rows * enc_row_stride(width) * sizeof(__half);
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
     npp_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(
-        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap, rows);
+        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap, rows,
+        zero_loss ? p->acc : nullptr, zero_loss ? (int)p->acc_floats : 0, zero_loss);
     CK(cudaGetLastError());
     ++p->launches;
   }
@@ -1088,9 +1089,8 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   if (n_norm <= 0) return fail("n_norm must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
-  CKI(zero_acc(p, st));
-  CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false));
+  // the encode kernel clears the accumulators and the loss scalar of this step
+  CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false, nullptr, loss));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
   const bool fused_head = p->head_fused_blocks > 0 && !getenv("NPP_SPLIT_HEAD");
   if (fused_head) {

@@ -90,8 +90,16 @@ __host__ __device__ inline int enc_row_stride(int width) { return (width + 8 + 7
 __host__ __device__ inline int enc_base_bytes(int rows, int B) { return (rows * B * 4 + 15) & ~15; }
 __global__ void __launch_bounds__(ENC_THREADS) npp_encode_kernel(const float* __restrict__ coords, int n, EncTable t,
                                                                  __half* __restrict__ enc1, int ld1,
-                                                                 __half* __restrict__ enca, int lda, int rows) {
+                                                                 __half* __restrict__ enca, int lda, int rows,
+                                                                 float* __restrict__ zero_a, int zero_a_n,
+                                                                 float* __restrict__ zero_b) {
   extern __shared__ __align__(16) uint8_t enc_smem[];
+  // first kernel of a fused train step: also clears the step's accumulators (bias-gradient sums, head gradients,
+  // max|g|) and the loss scalar, which saves two memset nodes per step
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < zero_a_n; i += blockDim.x) zero_a[i] = 0.f;
+    if (zero_b != nullptr && threadIdx.x == 0) *zero_b = 0.f;
+  }
   const int per_dir = t.include_input + 2 * t.n_aug;
   const int B = 2 * per_dir;
   const int F = 1 + 2 * t.n_freq;
