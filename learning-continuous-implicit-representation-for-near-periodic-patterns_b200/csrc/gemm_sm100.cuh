@@ -277,7 +277,7 @@ __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t
 // lines); the dgrad multiplier (stored snake derivative) arrives the same way through a TMA load.
 // scalar fields of an op, copied to registers once per op (the descriptor itself lives in global memory)
 struct EpiArgs {
-  float bias_val;   // bias of output column (tile n0 + this thread's index among the 256 epilogue threads), prefetched
+  float4 bias4;     // bias of the warp's 128 output columns, 4 per lane (columns 128 e + 4 lane ..), prefetched a tile ahead
   float* colsum;
   float* out_f32;
   int ldf;
@@ -326,14 +326,6 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
     }
   }
   mul_ready = false;
-  if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
-    // bias slice of this tile -> smem once (its load latency hides behind the accumulator wait); the two named
-    // barriers order the refill against the other epilogue warps' reads of the previous tile's slice
-    const int et = (warp - 2) * 32 + lane;  // 0..255
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    s.bias[et] = ea.bias_val;  // loaded from global memory a whole tile ago
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-  }
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
   if (stamp) dbg[1] = clock64();
@@ -358,13 +350,16 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
       const int hcol = col + half * 32;
 
       if (EPI == EPI_LINEAR || EPI == EPI_SNAKE) {
+        // The warp's 128 bias values live in registers, four per lane; a column's value comes by shuffle.  (Staging
+        // the slice in shared memory needed two 256-thread barriers per tile, which made every epilogue warp wait
+        // for the slowest one: 1300-1900 clocks per tile in the snake layers.)
+        const int src0 = (sub - 2 * e) * 16 + half * 8;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s.bias + sub * EPI_COLS + half * 32 + i);
-          v[i] += b4.x;
-          v[i + 1] += b4.y;
-          v[i + 2] += b4.z;
-          v[i + 3] += b4.w;
+          v[i] += __shfl_sync(0xffffffffu, ea.bias4.x, src0 + (i >> 2));
+          v[i + 1] += __shfl_sync(0xffffffffu, ea.bias4.y, src0 + (i >> 2));
+          v[i + 2] += __shfl_sync(0xffffffffu, ea.bias4.z, src0 + (i >> 2));
+          v[i + 3] += __shfl_sync(0xffffffffu, ea.bias4.w, src0 + (i >> 2));
         }
       }
       if (out_f32 != nullptr && row_ok) {
@@ -714,8 +709,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
     uint32_t acc_phase = 0;
     uint32_t fwd_phase = 0;  // phase bits of the two forwarding class barriers this warp waits on
     bool mul_ready = false;  // the dgrad multiplier of the coming tile's first sub-tile is already on its way
-    const int et_idx = (warp - 2) * 32 + lane;  // this thread's column inside a 256-wide tile (bias staging)
-    float bias_pref = 0.f;
+    const int et_idx = ((warp - 2) >> 2) * 128 + 4 * lane;  // first of this lane's four bias columns inside a tile
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bias_pref = zero4;
     bool first_tile = true;
     static_assert(STRIPE_GROUP == 1, "on-chip forwarding assumes one stripe at a time");
     for (int si = 0; si < stripe_iters; si += STRIPE_GROUP) {
@@ -738,7 +734,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
         if (oi + 1 < cp.n_ops) next_op_bias = cp.sc[oi + 1].bias;
         else if (si + gi < stripe_iters) next_op_bias = cp.sc[0].bias;
         if (first_tile) {
-          bias_pref = op_bias != nullptr ? __ldg(op_bias + et_idx) : 0.f;
+          bias_pref = op_bias != nullptr ? __ldg(reinterpret_cast<const float4*>(op_bias + et_idx)) : zero4;
           first_tile = false;
         }
         ea.colsum = sc.colsum;
@@ -760,11 +756,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 ea.next_mul = &cp.ops[oi + 1].tmMul;
               }
             }
-            ea.bias_val = bias_pref;
+            ea.bias4 = bias_pref;
             {  // bias of the NEXT tile: in flight while this tile is drained
               const float* nb = nt + 1 < op_tiles_n ? op_bias : next_op_bias;
               const int ncol = nt + 1 < op_tiles_n ? (nt + 1) * BN : 0;
-              bias_pref = nb != nullptr ? __ldg(nb + ncol + et_idx) : 0.f;
+              bias_pref = nb != nullptr ? __ldg(reinterpret_cast<const float4*>(nb + ncol + et_idx)) : zero4;
             }
             const uint32_t tacc = tmem_base + acc * BN;
             const int n0 = nt * BN;
