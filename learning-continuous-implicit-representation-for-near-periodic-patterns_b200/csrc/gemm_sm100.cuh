@@ -161,7 +161,7 @@ struct GemmSmem {
   uint8_t* a;
   uint8_t* b;
   uint8_t* epi;  // 4 warps x 4 x 4 KB staging, 1024-B aligned
-  float* bias;   // BN floats: bias slice of the current tile, shared by the 4 epilogue warps
+  float* bias;   // BN floats, spare (the bias now lives in registers; kept so the barrier block stays 1 KB aligned)
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tfull;

@@ -138,11 +138,12 @@ __global__ void __launch_bounds__(ENC_THREADS) npp_encode_kernel(const float* __
 
   const int half_b = B >> 1;
   const float inv_half_b = 1.0f / (float)half_b;
+  const int shift0 = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 1) & 7);  // every row's, if ld % 8 == 0
   for (int idx = threadIdx.x; idx < rows * half_b; idx += blockDim.x) {
     const int r = __float2int_rz(((float)idx + 0.5f) * inv_half_b), cp = idx - r * half_b;
     const int row = row0 + r;
     if (row >= n) continue;
-    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(dst + (size_t)row * ld) >> 1) & 7);
+    const int shift = (ld & 7) == 0 ? shift0 : static_cast<int>((reinterpret_cast<uintptr_t>(dst + (size_t)row * ld) >> 1) & 7);
     const float2 u = *reinterpret_cast<const float2*>(ubase + r * B + 2 * cp);
     __half2* o = reinterpret_cast<__half2*>(tile + r * RS + shift + 2 * cp);
     o[0] = __floats2half2_rn(u.x, u.y);
@@ -157,6 +158,34 @@ __global__ void __launch_bounds__(ENC_THREADS) npp_encode_kernel(const float* __
   }
   __syncthreads();
 
+  if ((ld & 7) == 0) {
+    // Row pitch is a multiple of 16 bytes (every plan buffer): all rows of the block share one alignment shift, so
+    // thread t owns 16-byte chunk column t % 64 and walks rows t / 64, +4, ... with plain pointer increments.
+    const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 1) & 7);
+    const int end = shift + width;
+    const int first_full = (shift + 7) >> 3, last_full = end >> 3;
+    const int nch = (end + 7) >> 3;
+    const int rows_here = min(rows, n - row0);
+    for (int ch = threadIdx.x & 63; ch < nch; ch += 64) {
+      const bool whole = ch >= first_full && ch < last_full;
+      const uint8_t* sp = reinterpret_cast<const uint8_t*>(tile) + (size_t)(threadIdx.x >> 6) * RS * 2 + ch * 16;
+      uint8_t* gp = reinterpret_cast<uint8_t*>(dst + (size_t)(row0 + (threadIdx.x >> 6)) * ld - shift) + ch * 16;
+      const size_t sstep = (size_t)RS * 2 * (ENC_THREADS / 64), gstep = (size_t)ld * 2 * (ENC_THREADS / 64);
+      for (int r = threadIdx.x >> 6; r < rows_here; r += ENC_THREADS / 64, sp += sstep, gp += gstep) {
+        if (whole) {
+          *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+        } else {  // ragged first / last chunk: the half2 pieces that belong to this proposal
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pos = ch * 8 + 2 * i;
+            if (pos >= shift && pos < end)
+              *reinterpret_cast<__half2*>(gp + 4 * i) = *reinterpret_cast<const __half2*>(sp + 4 * i);
+          }
+        }
+      }
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int r = wib; r < rows; r += nw) {
     const int row = row0 + r;
