@@ -114,6 +114,14 @@ int npp_train_step(NppPlan* plan, const float* coords, const float* target, cons
                    int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
                    void* stream);
 
+/* Optional input pipelining for npp_train_step (the data-loader analogue of NPP_completion/train.py:164-181, where
+ * the reference gathers the next batch's rows of the encoding table): encodes `coords` of a FUTURE step into the
+ * plan's second encoding buffer on an internal stream.  It waits for everything already enqueued on `stream`
+ * (including whatever produces `coords`) and for nothing enqueued afterwards, so call it BEFORE enqueueing the step
+ * it should overlap with.  The step whose coords pointer and row count match picks the encoding up instead of
+ * encoding again; `coords` must stay unchanged until then.  At most one prefetch per future step is kept. */
+int npp_encode_prefetch(NppPlan* plan, const float* coords, int64_t n, void* stream);
+
 /* By default npp_train_step goes straight from the split-K slabs to the Adam update and never writes the
  * gradient arena; turn this on to have it written as well (tests, gradient inspection). */
 int npp_set_keep_grads(NppPlan* plan, int on);

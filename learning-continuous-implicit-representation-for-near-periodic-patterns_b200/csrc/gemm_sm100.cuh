@@ -118,6 +118,9 @@ struct ChainParams {
   int subs_per_stripe;  // output sub-tiles all ops write per stripe
   long long* dbg;       // optional (tests): per-tile clock64 stamps of one CTA (epilogue warp dbg_warp and the UMMA warp of its pair)
   int dbg_block, dbg_warp;
+  float* zero_a;        // optional: accumulators (and *zero_b) that CTA 0 clears before the chain starts (fused train step
+  int zero_n;           //   whose encoding was prefetched: the encode kernel, which normally does this, did not run)
+  float* zero_b;
 };
 
 struct WgUnit {
@@ -512,6 +515,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   const GemmSmem s = carve_smem_t<NST, EPI_STAGE_BYTES, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && cp.zero_n > 0) {
+    for (int i = threadIdx.x; i < cp.zero_n; i += blockDim.x) cp.zero_a[i] = 0.f;
+    if (threadIdx.x == 0 && cp.zero_b != nullptr) *cp.zero_b = 0.f;
+  }
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
   // every CTA of a pair runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
   const int stripe_iters = (cp.tiles_m + (int)gridDim.x - 1) / (int)gridDim.x;

@@ -123,6 +123,16 @@ struct NppPlan {
   long long arena_total = 0, arena_trained = 0;
   long long rgb_w_off = 0, rgb_b_off = 0;
   int buf_enc1 = -1, buf_enca = -1;
+  int buf_enc1_alt = -1, buf_enca_alt = -1;   // second encoding set: filled by npp_encode_prefetch while a step runs
+  int enc_set = 0;                            // encoding set the last forward used (its backward reads it again)
+  struct PrefRec {                            // an encoding written ahead of its step by npp_encode_prefetch
+    const float* coords = nullptr;            //   identified by the coords pointer + row count of the step that uses it
+    long long n = 0;
+    bool valid = false;
+    cudaEvent_t done = nullptr;
+  } pref[2];                                  // one per encoding set
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t pref_fork = nullptr;
   int head_width = 0;  // W/2
 
   // device memory owned by the plan
@@ -141,6 +151,7 @@ struct NppPlan {
   UpdateLayer* d_update = nullptr;
   UpdateTable update_table;      // the same table by value (kernel parameter of the fused update)
   KmajorParams* d_fwd_ops = nullptr;    // forward chain (one op per dense layer)
+  KmajorParams* d_fwd_ops_alt = nullptr;  // same, reading the second encoding set
   KmajorParams* d_dgrad_ops = nullptr;  // dgrad chain
   WgUnit* d_units = nullptr;
   int n_units = 0;
@@ -160,8 +171,8 @@ struct NppPlan {
   std::vector<CUtensorMap> map_a;   // per buffer, box {64,128}: K-major A operand
   std::vector<CUtensorMap> map_mn;  // per buffer, box {64,64}: MN-major wgrad operand
   std::vector<CUtensorMap> map_ep;  // per buffer, box {64,32}: per-warp epilogue store / load
-  std::vector<KmajorParams> fwd_params, dgrad_params;
-  WgradParams wg_params;
+  std::vector<KmajorParams> fwd_params, fwd_params_alt, dgrad_params;
+  WgradParams wg_params, wg_params_alt;
   std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
   int launches = 0;
   int fwd_subs = 0, dgrad_subs = 0;  // output sub-tiles per stripe of each chain
@@ -267,6 +278,8 @@ static int build_graph(NppPlan* p) {
   p->head_width = W / 2;
   p->buf_enc1 = add_buf(p, "enc1", p->Ep);
   if (c.model == NPP_MODEL_TOPK) p->buf_enca = add_buf(p, "enc_aux", p->Ap);
+  p->buf_enc1_alt = add_buf(p, "enc1_alt", p->Ep);
+  if (c.model == NPP_MODEL_TOPK) p->buf_enca_alt = add_buf(p, "enc_aux_alt", p->Ap);
 
   typedef std::pair<int, std::pair<int, int>> S;
   auto src = [](int buf, int w, int prod) { return S(buf, std::make_pair(w, prod)); };
@@ -485,6 +498,10 @@ static int alloc_plan_memory(NppPlan* p) {
     CK(cudaMemcpy(p->d_update, up.data(), up.size() * sizeof(UpdateLayer), cudaMemcpyHostToDevice));
   }
   CK(cudaMalloc(&p->d_fwd_ops, p->layers.size() * sizeof(KmajorParams)));
+  CK(cudaMalloc(&p->d_fwd_ops_alt, p->layers.size() * sizeof(KmajorParams)));
+  CK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&p->pref_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&p->pref[i].done, cudaEventDisableTiming));
   CK(cudaMalloc(&p->d_dgrad_ops, (p->dgrads.size() + 1) * sizeof(KmajorParams)));
   CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
   CK(cudaMemcpy(p->d_shadow, sh.data(), sh.size() * sizeof(ShadowLayer), cudaMemcpyHostToDevice));
@@ -618,6 +635,12 @@ static int prepare(NppPlan* p, long long n) {
     }
     p->fwd_params.push_back(k);
   }
+  // the same chain reading the second encoding set
+  auto alt_buf = [&](int b) { return b == p->buf_enc1 ? p->buf_enc1_alt : (b == p->buf_enca ? p->buf_enca_alt : b); };
+  p->fwd_params_alt = p->fwd_params;
+  for (size_t li = 0; li < p->layers.size(); ++li)
+    for (size_t s = 0; s < p->layers[li].segs.size(); ++s)
+      p->fwd_params_alt[li].tmA[s] = p->map_a[alt_buf(p->layers[li].segs[s].buf)];
   p->dgrad_params.clear();
   int dg_subs = 0;
   for (auto& op : p->dgrads) {
@@ -659,8 +682,11 @@ static int prepare(NppPlan* p, long long n) {
   p->fwd_subs = fwd_subs;
   p->dgrad_subs = dg_subs;
   finish_chain_ops(p->fwd_params, p->cluster);
+  finish_chain_ops(p->fwd_params_alt, p->cluster);
   finish_chain_ops(p->dgrad_params, p->cluster);
   CK(cudaMemcpy(p->d_fwd_ops, p->fwd_params.data(), p->fwd_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_fwd_ops_alt, p->fwd_params_alt.data(), p->fwd_params_alt.size() * sizeof(KmajorParams),
+                cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_dgrad_ops, p->dgrad_params.data(), p->dgrad_params.size() * sizeof(KmajorParams),
                 cudaMemcpyHostToDevice));
   WgradParams& w = p->wg_params;
@@ -678,7 +704,10 @@ static int prepare(NppPlan* p, long long n) {
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
   w.partial = p->partial;
   w.slab_stride = p->slab_stride;
+  p->wg_params_alt = w;
+  for (size_t i = 0; i < p->wg_src_bufs.size(); ++i) p->wg_params_alt.maps[nl + i] = p->map_mn[alt_buf(p->wg_src_bufs[i])];
   p->prepared_n = n;
+  p->pref[0].valid = p->pref[1].valid = false;   // prefetched encodings belong to the previous row count
   return 0;
 }
 
@@ -697,7 +726,8 @@ static int set_smem_attrs() {
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
 // cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
 static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, int n_ops, int M, int num_sms,
-                        cudaStream_t st, int subs_per_stripe, int cluster = 1) {
+                        cudaStream_t st, int subs_per_stripe, int cluster = 1, float* zero_a = nullptr, int zero_n = 0,
+                        float* zero_b = nullptr) {
   CKI(set_smem_attrs());
   if (n_ops > MAX_CHAIN_OPS) return fail("chain longer than MAX_CHAIN_OPS");
   ChainParams cp;
@@ -718,6 +748,9 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
     sc.desc_hi = k.desc_hi;
   }
   cp.ops = d_ops;
+  cp.zero_a = zero_a;
+  cp.zero_n = zero_n;
+  cp.zero_b = zero_b;
   cp.n_ops = n_ops;
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
@@ -807,35 +840,74 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   return 0;
 }
 
+// Encodes `coords` into encoding set `set` (0: enc1 / enc_aux, 1: their alternates).  zero_loss != nullptr: the kernel
+// also clears the step accumulators and *zero_loss (first kernel of a fused train step).
+static int launch_encode(NppPlan* p, const float* coords, long long n, int set, cudaStream_t st, float* zero_loss) {
+  const int width = p->E;
+  const int B = 2 * (p->cfg.include_input + 2 * p->cfg.n_aug);
+  const int rows = std::max(1, ENC_THREADS / (B / 2));   // one thread per (row, base-feature pair)
+  dim3 grid((unsigned)((n + rows - 1) / rows), p->cfg.topk);
+  const size_t smem = (size_t)enc_base_bytes(rows, B) + (size_t)rows * enc_row_stride(width) * sizeof(__half);
+  const int b1 = set ? p->buf_enc1_alt : p->buf_enc1;
+  const int ba = set ? p->buf_enca_alt : p->buf_enca;
+  __half* enca = ba >= 0 ? p->bufs[ba].ptr : nullptr;
+  npp_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, enca, p->Ap, rows,
+                                                     zero_loss ? p->acc : nullptr, zero_loss ? (int)p->acc_floats : 0,
+                                                     zero_loss);
+  CK(cudaGetLastError());
+  ++p->launches;
+  return 0;
+}
+
 static int run_forward(NppPlan* p, const float* coords, long long n, float* logits, cudaStream_t st, bool with_head = true,
                        const float* enc_f32 = nullptr, float* zero_loss = nullptr) {
   if (!p->params) return fail("npp_plan_bind has not been called");
   CKI(prepare(p, n));
+  bool prefetched = false;
   if (enc_f32 != nullptr) {
     ProfScope ps(p, st, PROF_ENCODE, 1);
+    if (p->pref[0].valid) {   // a pending prefetch into set 0 is overwritten: order after it, then forget it
+      CK(cudaStreamWaitEvent(st, p->pref[0].done, 0));
+      p->pref[0].valid = false;
+    }
+    p->enc_set = 0;
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
     npp_load_encoding_kernel<<<p->num_sms * 8, 256, 0, st>>>(enc_f32, (int)n, p->cfg.topk, p->E,
                                                              p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
     CK(cudaGetLastError());
     ++p->launches;
   } else {
-    ProfScope ps(p, st, PROF_ENCODE, 1);
-    const int width = p->E;
-    const int B = 2 * (p->cfg.include_input + 2 * p->cfg.n_aug);
-    const int rows = std::max(1, ENC_THREADS / (B / 2));   // one thread per (row, base-feature pair)
-    dim3 grid((unsigned)((n + rows - 1) / rows), p->cfg.topk);
-    const size_t smem = (size_t)enc_base_bytes(rows, B) + (size_t)rows * enc_row_stride(width) * sizeof(__half);
-    __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
-    npp_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(
-        coords, (int)n, p->enc, p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap, rows,
-        zero_loss ? p->acc : nullptr, zero_loss ? (int)p->acc_floats : 0, zero_loss);
-    CK(cudaGetLastError());
-    ++p->launches;
+    int hit = -1;
+    for (int i = 0; i < 2; ++i)
+      if (p->pref[i].valid && p->pref[i].coords == coords && p->pref[i].n == n) hit = i;
+    if (hit >= 0) {
+      // npp_encode_prefetch already wrote this batch's encoding into set `hit` (on the side stream, while earlier
+      // work was running): wait for it, switch sets, and let the chain kernel clear the step accumulators
+      CK(cudaStreamWaitEvent(st, p->pref[hit].done, 0));
+      p->pref[hit].valid = false;
+      p->enc_set = hit;
+      prefetched = true;
+      ++p->launches;   // the encode launch belongs to this step
+    } else {
+      // encode in line, into a set nobody has prefetched into (or, failing that, over a prefetch that is now stale)
+      int set = p->enc_set;
+      if (p->pref[set].valid && !p->pref[1 - set].valid) set = 1 - set;
+      if (p->pref[set].valid) {
+        CK(cudaStreamWaitEvent(st, p->pref[set].done, 0));
+        p->pref[set].valid = false;
+      }
+      p->enc_set = set;
+      ProfScope ps(p, st, PROF_ENCODE, 1);
+      CKI(launch_encode(p, coords, n, set, st, zero_loss));
+    }
   }
   {
     ProfScope ps(p, st, PROF_GEMM_FWD, 1);
-    CKI(launch_chain(p->d_fwd_ops, p->fwd_params.data(), (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs,
-                     p->cluster));
+    const bool alt = p->enc_set != 0;
+    CKI(launch_chain(alt ? p->d_fwd_ops_alt : p->d_fwd_ops, alt ? p->fwd_params_alt.data() : p->fwd_params.data(),
+                     (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs, p->cluster,
+                     prefetched && zero_loss ? p->acc : nullptr, prefetched && zero_loss ? (int)p->acc_floats : 0,
+                     prefetched ? zero_loss : nullptr));
     ++p->launches;
   }
   if (!with_head) return 0;
@@ -873,7 +945,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   }
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
-    CKI(launch_wgrad(p->wg_params, p->num_sms, st, p->wg_cluster));
+    CKI(launch_wgrad(p->enc_set ? p->wg_params_alt : p->wg_params, p->num_sms, st, p->wg_cluster));
     ++p->launches;
   }
   if (finalize) {
@@ -996,6 +1068,10 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_shadow);
   cudaFree(p->d_update);
   cudaFree(p->d_fwd_ops);
+  cudaFree(p->d_fwd_ops_alt);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  if (p->pref_fork) cudaEventDestroy(p->pref_fork);
+  for (int i = 0; i < 2; ++i) if (p->pref[i].done) cudaEventDestroy(p->pref[i].done);
   cudaFree(p->d_dgrad_ops);
   cudaFree(p->d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
@@ -1038,6 +1114,33 @@ int npp_encode(NppPlan* p, const float* coords, int64_t n, float* out, void* str
   if (n <= 0) return 0;
   npp_encode_f32_kernel<<<p->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(coords, (int)n, p->enc, out);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int npp_encode_prefetch(NppPlan* p, const float* coords, int64_t n, void* stream) {
+  if (!p || !coords) return fail("npp_encode_prefetch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CKI(prepare(p, n));
+  // The target set was last read by the step BEFORE the one that is running / about to be enqueued; everything
+  // already enqueued on `stream` (that step, and whatever produces `coords`) is waited for, nothing enqueued later.
+  // Target: the set the NEXT step will not use.  That step takes a pending prefetch if there is one, else the set of
+  // the last step.  The target was last read by a step that is already enqueued on `stream`: everything enqueued
+  // there so far (that step, and whatever produces `coords`) is waited for, nothing enqueued later -- call this
+  // BEFORE enqueueing the step that should overlap with the encoding.
+  int next_set = p->enc_set;
+  for (int i = 0; i < 2; ++i)
+    if (p->pref[i].valid) next_set = i;
+  const int set = 1 - next_set;
+  CK(cudaEventRecord(p->pref_fork, st));
+  CK(cudaStreamWaitEvent(p->side_stream, p->pref_fork, 0));
+  if (p->pref[set].valid) CK(cudaStreamWaitEvent(p->side_stream, p->pref[set].done, 0));
+  const int launches = p->launches;
+  CKI(launch_encode(p, coords, n, set, p->side_stream, nullptr));
+  p->launches = launches;   // counted by the step that consumes it
+  CK(cudaEventRecord(p->pref[set].done, p->side_stream));
+  p->pref[set].coords = coords;
+  p->pref[set].n = n;
+  p->pref[set].valid = true;
   return 0;
 }
 

@@ -266,6 +266,12 @@ class Plan:
                                           n if n_norm is None else int(n_norm), lr, betas[0], betas[1], eps, step,
                                           loss_out.data_ptr(), nat.current_stream()))
 
+    def prefetch_encode(self, coords: torch.Tensor):
+        """Encode the coordinates of a FUTURE `train_step` on the plan's side stream, so that it overlaps with the
+        step that is enqueued next (call this first, then that step).  `coords` must be the very tensor (same storage,
+        unchanged) the future step is called with; it must be a contiguous fp32 CUDA tensor."""
+        nat.check(self.lib.npp_encode_prefetch(self.handle, coords.data_ptr(), coords.shape[0], nat.current_stream()))
+
     def keep_grads(self, on: bool = True):
         nat.check(self.lib.npp_set_keep_grads(self.handle, int(on)))
 

@@ -283,6 +283,45 @@ def test_train_steps_follow_oracle(topk):
         assert np.abs(got[k].cpu().numpy() - p[k]).max() < 1e-3, k
 
 
+def test_prefetched_encoding_gives_the_same_steps():
+    """npp_encode_prefetch (next batch encoded on the side stream while a step runs) must not change anything:
+    same losses and same weights as encoding in line, over batches that rotate through both encoding sets and
+    with a mismatching (unused) prefetch thrown in."""
+    n = 3000
+    rng = np.random.default_rng(11)
+    batches = [torch.from_numpy(np.stack([rng.integers(0, RES[0], n), rng.integers(0, RES[1], n)], 1).astype(np.float32)).cuda()
+               for _ in range(4)]
+    targets = [torch.rand(n, 3, device="cuda") for _ in range(4)]
+    mask = torch.ones(n, 1, device="cuda")
+
+    def run(prefetch):
+        plan, *_ = make(3, n)
+        loss_d = torch.zeros((), device="cuda")
+        losses = []
+        for step in range(1, 8):
+            b = (step - 1) % 4
+            if prefetch:
+                plan.prefetch_encode(batches[step % 4])            # the NEXT step's coordinates
+                if step == 4:
+                    plan.prefetch_encode(batches[(step + 2) % 4])  # a prefetch nobody picks up next (stale later)
+            plan.train_step(batches[b], targets[b], mask, 5e-4, loss_d, step=step)
+            losses.append(loss_d.item())
+        assert plan.launch_count() == 6
+        return losses, {k: v.clone() for k, v in plan.state().items()}
+
+    l0, s0 = run(False)
+    l1, s1 = run(True)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-3 * abs(a), (l0, l1)   # run-to-run noise (float atomics) is ~1e-5; a wrong or stale encoding is O(1)
+    for k in s0:
+        # float atomics (bias-gradient sums, head) make two runs differ in the last bits, and Adam's normalised update
+        # can turn that into whole 5e-4 steps on weights whose gradient is ~0: bound the worst weight by the 7 steps
+        # taken and the average tightly
+        d = (s0[k] - s1[k]).abs()
+        mean_tol = 1e-5 if d.numel() >= 1024 else 7 * 5e-4   # a 3-element bias can take opposite steps on noise alone
+        assert d.max().item() < 7 * 5e-4 + 1e-6 and d.mean().item() < mean_tol, (k, d.max().item(), d.mean().item())
+
+
 def test_linearity_of_backward_in_grad():
     """Size-independent property: the weight gradient is linear in dL/dlogits, including the fp16 delta
     scaling (a power of two, so scaling g by 2^k must scale every gradient exactly by 2^k)."""
