@@ -341,9 +341,9 @@ def main():
             ev_free[k].record(main_stream)
             issue_copies(i + 1)
             return l.item()
-        issue_copies(i + 1)                             # next step's inputs: copies + encoding overlap this step
         plan.train_step(c, t, mk, lr, loss_d)
         ev_free[k].record(main_stream)
+        issue_copies(i + 1)                             # next step's inputs: copies + encoding overlap this step
         return loss_d.item()
 
     issue_copies(0)
