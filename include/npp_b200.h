@@ -104,6 +104,19 @@ int npp_backward(NppPlan* plan, int64_t n, const float* grad_logits, void* strea
 int npp_mse_fwd_bwd(NppPlan* plan, const float* logits, const float* target, const float* mask, int64_t n,
                     int64_t n_norm, float* pred, float* grad_logits, float* loss, void* stream);
 
+/* Barron's adaptive robust pixel loss, the reference's default --loss_type (models/mse_calculator.py:24-25 ->
+ * externel_lib/robust_loss_pytorch/adaptive.py:178-198, distribution.py:173-210, general.py:84-118), forward and
+ * backward in one pass over x = network output [n,3] (after the sigmoid), y = target [n,3], mask [n,1] or NULL:
+ *   d = (x - y) (m + 0.3 (1 - m));  loss = mean_{n,3} [ rho(d, alpha_c, s_c) + log s_c + log Z(alpha_c) ]
+ * latent_alpha / latent_scale: the 3 + 3 parameters of AdaptiveLossFunction (device).  cfg4 (host) = {alpha_lo,
+ * alpha_hi, scale_lo, scale_init}.  logz_values / logz_derivs (device, n_knots floats each): log Z and its derivative
+ * at uniformly spaced alpha in [0, alpha_max].  scratch9: 9 device floats.  out7 (device) = {loss, dL/dlatent_alpha[3],
+ * dL/dlatent_scale[3]};  grad_x [n,3] = dL/dx.  No plan needed. */
+int npp_robust_adaptive_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, const float* latent_alpha,
+                                const float* latent_scale, const float* cfg4, const float* logz_values,
+                                const float* logz_derivs, int n_knots, float alpha_max, float* scratch9, float* out7,
+                                float* grad_x, void* stream);
+
 /* torch.optim.Adam.step over the trained part of the arena (models/helpers.py:164) followed by the
  * shadow-weight refresh.  `step` is the 1-based step count used for bias correction. */
 int npp_adam_step(NppPlan* plan, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);

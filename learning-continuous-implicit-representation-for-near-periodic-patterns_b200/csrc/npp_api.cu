@@ -1179,6 +1179,33 @@ int npp_mse_fwd_bwd(NppPlan* p, const float* logits, const float* target, const 
   return 0;
 }
 
+int npp_robust_adaptive_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, const float* latent_alpha,
+                                const float* latent_scale, const float* cfg4, const float* logz_values,
+                                const float* logz_derivs, int n_knots, float alpha_max, float* scratch9, float* out7,
+                                float* grad_x, void* stream) {
+  if (!x || !y || !latent_alpha || !latent_scale || !cfg4 || !logz_values || !logz_derivs || !scratch9 || !out7 || !grad_x)
+    return fail("npp_robust_adaptive_fwd_bwd: null argument");
+  if (n <= 0 || n > (1LL << 28)) return fail("npp_robust_adaptive_fwd_bwd: row count out of range");
+  if (n_knots < 4) return fail("npp_robust_adaptive_fwd_bwd: log-partition table too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  RobustCfg cfg;
+  cfg.alpha_lo = cfg4[0]; cfg.alpha_hi = cfg4[1]; cfg.scale_lo = cfg4[2]; cfg.scale_ref = cfg4[3];
+  cfg.n_knots = n_knots; cfg.alpha_max = alpha_max;
+  if (!(cfg.alpha_lo > 0.f) || !(cfg.alpha_hi < 2.f) || !(cfg.alpha_lo < cfg.alpha_hi) || !(cfg.scale_lo < cfg.scale_ref))
+    return fail("npp_robust_adaptive_fwd_bwd: needs 0 < alpha_lo < alpha_hi < 2 and scale_lo < scale_ref");
+  CK(cudaMemsetAsync(scratch9, 0, 9 * sizeof(float), st));
+  const float inv_count = 1.0f / (3.0f * (float)n);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  npp_robust_loss_kernel<<<blocks, 256, 0, st>>>(x, y, mask, (int)n, latent_alpha, latent_scale, cfg, logz_values,
+                                                 logz_derivs, inv_count, grad_x, scratch9);
+  CK(cudaGetLastError());
+  npp_robust_finalize_kernel<<<1, 32, 0, st>>>(scratch9, latent_alpha, latent_scale, cfg, logz_values, logz_derivs,
+                                               inv_count, out7);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int npp_adam_step(NppPlan* p, float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
   if (!p) return fail("null plan");
   p->launches = 0;

@@ -793,6 +793,117 @@ __global__ void __launch_bounds__(256, 2) npp_head_fused_reg_kernel(
   if (threadIdx.x < 3) atomicAdd(head_acc + 3 * W + threadIdx.x, gs[threadIdx.x]);
 }
 
+// ------------------------------------------------------------- adaptive robust pixel loss (Barron)
+// models/mse_calculator.py:24-25 with --loss_type robust_loss_adaptive (the reference default):
+//   d = (x - y) * (m + 0.3 (1 - m));  loss = mean over [N,3] of  rho(d, alpha_c, s_c) + log s_c + log Z(alpha_c)
+//   rho(d, a, s) = (|a-2| / a) * (((d/s)^2 / |a-2| + 1)^(a/2) - 1)            (robust_loss_pytorch/general.py:84-118)
+//   alpha_c = lo + (hi - lo) sigmoid(latent_alpha_c),  s_c = (ref - lo_s) softplus(latent_scale_c + log(e - 1)) + lo_s
+//                                                               (adaptive.py:138-175, util.py:64-95)
+//   log Z: distribution.py:143-171; here a cubic Hermite table of the exact integral (tools/make_robust_logz_table.py).
+struct RobustCfg {
+  float alpha_lo, alpha_hi, scale_lo, scale_ref;
+  int n_knots;
+  float alpha_max;  // table covers [0, alpha_max]
+};
+
+__device__ __forceinline__ void npp_robust_channel(const float* __restrict__ latent_alpha,
+                                                   const float* __restrict__ latent_scale, RobustCfg cfg,
+                                                   const float* __restrict__ zval, const float* __restrict__ zder, int c,
+                                                   float& alpha, float& scale, float& logz, float& dlogz,
+                                                   float& dalpha_dlat, float& dscale_dlat) {
+  const float la = latent_alpha[c], ls = latent_scale[c];
+  const float sg = 1.0f / (1.0f + expf(-la));
+  alpha = cfg.alpha_lo + (cfg.alpha_hi - cfg.alpha_lo) * sg;
+  dalpha_dlat = (cfg.alpha_hi - cfg.alpha_lo) * sg * (1.0f - sg);
+  const float t = ls + 0.541324854612918f;  // inv_softplus(1) = log(e - 1)
+  const float sp = t > 20.0f ? t : log1pf(expf(t));
+  scale = (cfg.scale_ref - cfg.scale_lo) * sp + cfg.scale_lo;
+  dscale_dlat = (cfg.scale_ref - cfg.scale_lo) / (1.0f + expf(-t));
+  // cubic Hermite interpolation of log Z and its derivative
+  const float h = cfg.alpha_max / (float)(cfg.n_knots - 1);
+  float pos = fminf(fmaxf(alpha / h, 0.0f), (float)(cfg.n_knots - 1) - 1e-3f);
+  const int i = (int)pos;
+  const float u = pos - (float)i;
+  const float v0 = zval[i], v1 = zval[i + 1], d0 = zder[i] * h, d1 = zder[i + 1] * h;
+  const float u2 = u * u, u3 = u2 * u;
+  logz = (2 * u3 - 3 * u2 + 1) * v0 + (u3 - 2 * u2 + u) * d0 + (-2 * u3 + 3 * u2) * v1 + (u3 - u2) * d1;
+  dlogz = ((6 * u2 - 6 * u) * v0 + (3 * u2 - 4 * u + 1) * d0 + (-6 * u2 + 6 * u) * v1 + (3 * u2 - 2 * u) * d1) / h;
+}
+
+// acc[0..2] = sum rho, acc[3..5] = sum d rho / d alpha, acc[6..8] = sum d rho / d scale (per channel)
+__global__ void __launch_bounds__(256) npp_robust_loss_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                              const float* __restrict__ mask, int n,
+                                                              const float* __restrict__ latent_alpha,
+                                                              const float* __restrict__ latent_scale, RobustCfg cfg,
+                                                              const float* __restrict__ zval,
+                                                              const float* __restrict__ zder, float inv_count,
+                                                              float* __restrict__ gx, float* __restrict__ acc) {
+  __shared__ float s_alpha[3], s_scale[3];
+  __shared__ float red[8][9];
+  if (threadIdx.x < 3) {
+    float a, s, lz, dlz, da, ds;
+    npp_robust_channel(latent_alpha, latent_scale, cfg, zval, zder, threadIdx.x, a, s, lz, dlz, da, ds);
+    s_alpha[threadIdx.x] = a;
+    s_scale[threadIdx.x] = s;
+  }
+  __syncthreads();
+  float sum[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sum[k] = 0.f;
+  // one row (three channels) per thread and iteration
+  const int stride = gridDim.x * blockDim.x * 3;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) * 3; base < 3 * n; base += stride) {
+    const int row = base / 3;
+    const float m = mask ? mask[row] : 1.0f;
+    const float w = m + (1.0f - m) * 0.3f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = s_alpha[c], s = s_scale[c];
+      const float d = (x[base + c] - y[base + c]) * w;
+      const float b = fmaxf(fabsf(a - 2.0f), 1.1920929e-07f);
+      const float q = (d / s) * (d / s);
+      const float u = q / b + 1.0f;
+      const float lu = logf(u);
+      const float p = expf(0.5f * a * lu);
+      const float pu = p / u;
+      sum[c] += (b / a) * (p - 1.0f);
+      sum[3 + c] += (-2.0f / (a * a)) * (p - 1.0f) + (b / a) * p * (0.5f * lu + 0.5f * a * (q / (b * b)) / u);
+      sum[6 + c] += -(q / s) * pu;
+      gx[base + c] = (d / (s * s)) * pu * w * inv_count;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) red[threadIdx.x >> 5][k] = sum[k];
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float t = 0.f;
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// out[0] = loss, out[1..3] = dL/d latent_alpha, out[4..6] = dL/d latent_scale
+__global__ void npp_robust_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ latent_alpha,
+                                           const float* __restrict__ latent_scale, RobustCfg cfg,
+                                           const float* __restrict__ zval, const float* __restrict__ zder,
+                                           float inv_count, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float loss = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    float a, s, lz, dlz, da, ds;
+    npp_robust_channel(latent_alpha, latent_scale, cfg, zval, zder, c, a, s, lz, dlz, da, ds);
+    loss += inv_count * acc[c] + (logf(s) + lz) * (1.0f / 3.0f);
+    out[1 + c] = (inv_count * acc[3 + c] + dlz * (1.0f / 3.0f)) * da;
+    out[4 + c] = (inv_count * acc[6 + c] + (1.0f / 3.0f) / s) * ds;
+  }
+  out[0] = loss;
+}
+
 // ------------------------------------------------------------- gradients / Adam
 // Sum of the split-K partials of one element in a fixed order; all loads are issued before the adds.
 constexpr int NPP_MAX_SPLITS = 12;

@@ -14,3 +14,4 @@ plan = importlib.import_module(_NAME + ".plan")
 native = importlib.import_module(_NAME + "._native")
 EncoderSpec = plan.EncoderSpec
 Plan = plan.Plan
+NppAdaptiveLoss = importlib.import_module(_NAME + ".robust_loss").NppAdaptiveLoss

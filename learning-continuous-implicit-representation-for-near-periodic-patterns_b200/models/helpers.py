@@ -15,11 +15,10 @@ from .optim import NppAdam
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
-try:  # the adaptive robust pixel loss is vendored by the reference (externel_lib/) and stays PyTorch
-    from externel_lib.robust_loss_pytorch import AdaptiveLossFunction
-    adaptive_pix = AdaptiveLossFunction(num_dims=3, float_dtype=np.float32, device=0)
-except ImportError:  # reference checkout not on sys.path: only --loss_type l2 is usable
-    adaptive_pix = None
+# The adaptive robust pixel loss (reference models/helpers.py:8-9: AdaptiveLossFunction(num_dims=3, float32, device=0)):
+# same parameters and methods, fused CUDA evaluation inside img2mse.
+from ._core import NppAdaptiveLoss as AdaptiveLossFunction  # noqa: E402
+adaptive_pix = AdaptiveLossFunction(num_dims=3, float_dtype=np.float32, device=0) if torch.cuda.is_available() else None
 
 
 def batchify(fn, chunk):

@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from .activations import *  # noqa: F401,F403
+from ._core import NppAdaptiveLoss
 
 
 def img2mse(x, y, loss_type, adaptive, mask=None):
@@ -19,7 +20,10 @@ def img2mse(x, y, loss_type, adaptive, mask=None):
         loss = torch.mean(robust_loss_pytorch.general.lossfun(
             diff, alpha=torch.Tensor([2.]), scale=torch.Tensor([0.1])))
     elif loss_type == 'robust_loss_adaptive':
-        loss = torch.mean(adaptive.lossfun(diff))    # Barron adaptive loss, stays PyTorch on the [N,3] output
+        if isinstance(adaptive, NppAdaptiveLoss) and x.is_cuda and x.dim() == 2 and x.shape[1] == 3 and \
+                adaptive.num_dims == 3 and (mask is None or mask.numel() == x.shape[0]):
+            return adaptive.fused_img2mse(x, y, mask)           # one CUDA pass: loss + every gradient
+        loss = torch.mean(adaptive.lossfun(diff))                # any other AdaptiveLossFunction-like object / shape
     else:
         raise ValueError(loss_type)
     return torch.mean(loss)
