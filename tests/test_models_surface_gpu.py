@@ -162,3 +162,62 @@ def test_foreign_parameters_and_external_weight_edit():
     _ = render(None, coords, args, **kw)
     with pytest.raises(RuntimeError):
         a.sum().backward()
+
+
+def test_default_adaptive_robust_loss_iterations():
+    """The reference's DEFAULT --loss_type (robust_loss_adaptive, options/arg_config.py:34) through the drop-in surface:
+    `adaptive_pix` from models.helpers, `img2mse(pred, gt, 'robust_loss_adaptive', adaptive_pix, mask)` (train.py:205-208),
+    its latent parameters in `grad_vars` (helpers.py:144) updated by the optimizer next to the network.  Checked per
+    iteration against the numpy oracle (network oracle for the prediction, robust oracle for the loss)."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    import models.helpers as H
+    from models.mse_calculator import img2mse
+    from oracle import robust_oracle as R
+
+    torch.manual_seed(1)
+    np.random.seed(1)
+    res = (80, 96)
+    args = _args(3)
+    args.loss_type = 'robust_loss_adaptive'
+    adaptive_pix = H.adaptive_pix
+    assert adaptive_pix is not None and sorted(n for n, _ in adaptive_pix.named_parameters()) == ["latent_alpha", "latent_scale"]
+    with torch.no_grad():   # module-level singleton (like the reference's): start from its initial state
+        adaptive_pix.latent_alpha.zero_()
+        adaptive_pix.latent_scale.zero_()
+    angles = torch.Tensor([[83.0, 172.5], [90.0, 180.0], [41.3, 127.9]])
+    periods = torch.Tensor([[17.2, 14.9], [8.6, 7.45], [34.4, 29.8]])
+    kw, _, _, grad_vars, optimizer, embedder, per = H.create_npp_net(args, angles, periods, res, None)
+    assert any(q is adaptive_pix.latent_alpha for q in grad_vars) and any(q is adaptive_pix.latent_scale for q in grad_vars)
+    model = kw['network_fn']
+    p = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    tabs = [(e.cos_t, e.sin_t, e.period) for e in per]
+    n = 3000
+    coords = torch.stack([torch.randint(0, res[0], (n,)), torch.randint(0, res[1], (n,))], 1).float().cuda()
+    emb = torch.cat([embedder.embed(e.embed(coords.clone())) for e in per], 1)
+    gt = torch.rand(n, 3, device="cuda")
+    mask = (torch.rand(n, 1, device="cuda") > 0.2).float()
+
+    # iteration 1: loss and latent gradients against the oracles, from the same weights
+    pred = H.render(None, emb, args, **kw)
+    optimizer.zero_grad()
+    loss = img2mse(pred, gt, args.loss_type, adaptive_pix, mask)
+    loss.backward()
+    enc = O.encode(coords.cpu().numpy(), tabs, embedder.freqs, res)
+    logits = O.forward(p, enc, topk_model=True)[0]
+    pred_ref = 1.0 / (1.0 + np.exp(-logits.astype(np.float64)))
+    eloss, _, ega, egs = R.adaptive_img2mse(pred_ref, gt.cpu().numpy(), mask.cpu().numpy(), np.zeros(3), np.zeros(3))
+    assert abs(loss.item() - eloss) < 1e-3 * abs(eloss), (loss.item(), eloss)
+    np.testing.assert_allclose(adaptive_pix.latent_alpha.grad.cpu().numpy().ravel(), ega, rtol=2e-2, atol=1e-5)
+    np.testing.assert_allclose(adaptive_pix.latent_scale.grad.cpu().numpy().ravel(), egs, rtol=2e-2, atol=1e-5)
+    optimizer.step()
+    # a few more iterations: the NLL goes down and the foreign parameters move with Adam's step size
+    first = loss.item()
+    for _ in range(5):
+        pred = H.render(None, emb, args, **kw)
+        optimizer.zero_grad()
+        loss = img2mse(pred, gt, args.loss_type, adaptive_pix, mask)
+        loss.backward()
+        optimizer.step()
+    assert torch.isfinite(loss) and loss.item() < first
+    assert 1e-3 < adaptive_pix.latent_scale.abs().max().item() < 6.5 * args.lrate
