@@ -322,6 +322,20 @@ def test_prefetched_encoding_gives_the_same_steps():
         assert d.max().item() < 7 * 5e-4 + 1e-6 and d.mean().item() < mean_tol, (k, d.max().item(), d.mean().item())
 
 
+@pytest.mark.parametrize("topk,n", [(1, 40000), (3, 19001)])
+def test_many_stripes_per_cta_forward_matches_oracle(topk, n):
+    """More than 148 x 128 rows: every CTA walks several stripes through the chain (forwarding barriers keep
+    cycling, phantom stripes at the ragged end).  Logits of a strided sample of rows against the oracle."""
+    plan, params, coords, tabs, freqs, rng = make(topk, n)
+    logits = plan.forward(torch.from_numpy(coords).cuda()).cpu().numpy()
+    assert np.isfinite(logits).all()
+    pick = np.r_[0:256, n // 2 - 64:n // 2 + 64, n - 300:n, rng.integers(0, n, 512)]
+    enc = O.encode(coords[pick], tabs, freqs, RES)
+    ref = O.forward(params, enc, topk_model=topk > 1)[0]
+    err = np.linalg.norm(logits[pick] - ref) / np.linalg.norm(ref)
+    assert err < 1e-3, err
+
+
 def test_linearity_of_backward_in_grad():
     """Size-independent property: the weight gradient is linear in dL/dlogits, including the fp16 delta
     scaling (a power of two, so scaling g by 2^k must scale every gradient exactly by 2^k)."""
