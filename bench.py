@@ -193,7 +193,9 @@ def main():
                            "cfg4": "cfg4: remapping 2048x2048, K=3, 2^18-row batches split data-parallel, NCCL grad all-reduce"}[args.workload],
               "rows_per_step_per_gpu": rows if args.workload != "cfg4" else rows // max(world, 1),
               "l2_policy": "per-step working set (activations+deltas+split-K slabs, ~0.7 GB at 16384 rows) exceeds the 126 MB L2; "
-                           "8 rotating coordinate batches"}
+                           "8 rotating coordinate batches",
+              "input_pipeline": "GPU arm: the next batch's coordinates are encoded on the plan's low-priority side stream while "
+                                "a step runs (npp_encode_prefetch, counted in gpu_launches); steps run on a priority -1 stream"}
 
     if args.impl == "reference":
         if rank != 0:
