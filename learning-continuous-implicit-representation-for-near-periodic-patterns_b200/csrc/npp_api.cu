@@ -590,6 +590,9 @@ static int prepare(NppPlan* p, long long n) {
   if (n <= 0 || n > p->cfg.max_rows)
     return fail("row count " + std::to_string(n) + " outside (0, max_rows=" + std::to_string(p->cfg.max_rows) + "]");
   if (p->prepared_n == n) return 0;
+  // The op tables on the device are about to be overwritten: kernels of an earlier call (any stream, possibly a
+  // non-blocking one that the copies below would not wait for) may still be reading them.
+  CK(cudaDeviceSynchronize());
   const int nb = (int)p->bufs.size();
   p->map_a.assign(nb, CUtensorMap());
   p->map_mn.assign(nb, CUtensorMap());
