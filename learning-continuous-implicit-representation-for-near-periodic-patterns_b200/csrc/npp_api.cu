@@ -678,7 +678,7 @@ static int prepare(NppPlan* p, long long n) {
       k.ldm = P.out;
       k.tmMul = p->map_ep[P.buf_d];
     }
-    k.colsum = getenv("NPP_DEBUG_NO_COLSUM") ? nullptr : p->acc + P.bg_off;   // (timing experiments)
+    k.colsum = p->acc + P.bg_off;
     k.epi = P.act ? EPI_DGRAD_MUL : EPI_DGRAD;
     p->dgrad_params.push_back(k);
   }
