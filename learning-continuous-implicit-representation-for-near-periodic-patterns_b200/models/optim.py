@@ -21,12 +21,10 @@ class NppAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         if self.net is not None and any(p.grad is not None for p in self._own):
             plan = self.net._plan
-            gv = plan.grad_views()
-            for name, p in zip(self.net._param_names, self.net._params):
-                if p.grad is None or name not in gv:
+            for p, g in zip(self.net._params, self.net._grad_view_list):
+                if g is None or p.grad is None or p.grad is g:
                     continue
-                if p.grad.data_ptr() != gv[name].data_ptr():   # autograd cloned or accumulated: copy back
-                    gv[name].copy_(p.grad)
+                g.copy_(p.grad)                              # autograd cloned or accumulated: copy back into the arena
             plan.adam_step(group['lr'], betas=group['betas'], eps=group['eps'])
             self.net.mark_clean()
         if self._foreign is not None:
