@@ -104,6 +104,12 @@ int npp_backward(NppPlan* plan, int64_t n, const float* grad_logits, void* strea
 int npp_mse_fwd_bwd(NppPlan* plan, const float* logits, const float* target, const float* mask, int64_t n,
                     int64_t n_norm, float* pred, float* grad_logits, float* loss, void* stream);
 
+/* img2mse(x, y, 'l2', None, mask) of models/mse_calculator.py:13-27 on the network OUTPUT x [n,3] (after the sigmoid,
+ * as NPP_completion/train.py:205-208 calls it) with its gradient: loss (device float, overwritten) = mean over [n,3] of
+ * ((x - y)(m + 0.3 (1 - m)))^2, grad_x [n,3] = dL/dx.  mask [n,1] or NULL.  No plan needed. */
+int npp_l2_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, float* loss, float* grad_x,
+                   void* stream);
+
 /* Barron's adaptive robust pixel loss, the reference's default --loss_type (models/mse_calculator.py:24-25 ->
  * externel_lib/robust_loss_pytorch/adaptive.py:178-198, distribution.py:173-210, general.py:84-118), forward and
  * backward in one pass over x = network output [n,3] (after the sigmoid), y = target [n,3], mask [n,1] or NULL:

@@ -1182,6 +1182,19 @@ int npp_mse_fwd_bwd(NppPlan* p, const float* logits, const float* target, const 
   return 0;
 }
 
+int npp_l2_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, float* loss, float* grad_x,
+                   void* stream) {
+  if (!x || !y || !loss || !grad_x) return fail("npp_l2_fwd_bwd: null argument");
+  if (n <= 0 || n > (1LL << 28)) return fail("npp_l2_fwd_bwd: row count out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  int blocks = (int)((3 * n + 255) / 256);
+  if (blocks > 592) blocks = 592;
+  npp_l2_kernel<<<blocks, 256, 0, st>>>(x, y, mask, (int)n, 1.0f / (3.0f * (float)n), grad_x, loss);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int npp_robust_adaptive_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, const float* latent_alpha,
                                 const float* latent_scale, const float* cfg4, const float* logz_values,
                                 const float* logz_derivs, int n_knots, float alpha_max, float* scratch9, float* out7,

@@ -793,6 +793,33 @@ __global__ void __launch_bounds__(256, 2) npp_head_fused_reg_kernel(
   if (threadIdx.x < 3) atomicAdd(head_acc + 3 * W + threadIdx.x, gs[threadIdx.x]);
 }
 
+// Masked MSE on the network OUTPUT (after the sigmoid), forward + gradient in one pass: the 'l2' branch of
+// models/mse_calculator.py:13-27 as the reference scripts call it, img2mse(pred, gt, 'l2', None, mask):
+//   d = (x - y) * (m + 0.3 (1 - m));  loss = mean(d^2) over [n,3];  dL/dx = 2 d (m + 0.3 (1 - m)) / (3 n)
+__global__ void __launch_bounds__(256) npp_l2_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                     const float* __restrict__ mask, int n, float inv_count,
+                                                     float* __restrict__ gx, float* __restrict__ loss) {
+  float lsum = 0.f;
+  const int total = 3 * n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const float m = mask ? mask[idx / 3] : 1.0f;
+    const float w = m + (1.0f - m) * 0.3f;
+    const float d = (x[idx] - y[idx]) * w;
+    lsum += d * d;
+    gx[idx] = 2.0f * d * w * inv_count;
+  }
+  __shared__ float ssum[8];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ssum[i];
+    atomicAdd(loss, t * inv_count);
+  }
+}
+
 // ------------------------------------------------------------- adaptive robust pixel loss (Barron)
 // models/mse_calculator.py:24-25 with --loss_type robust_loss_adaptive (the reference default):
 //   d = (x - y) * (m + 0.3 (1 - m));  loss = mean over [N,3] of  rho(d, alpha_c, s_c) + log s_c + log Z(alpha_c)

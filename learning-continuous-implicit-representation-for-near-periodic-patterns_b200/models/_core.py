@@ -15,3 +15,4 @@ native = importlib.import_module(_NAME + "._native")
 EncoderSpec = plan.EncoderSpec
 Plan = plan.Plan
 NppAdaptiveLoss = importlib.import_module(_NAME + ".robust_loss").NppAdaptiveLoss
+fused_l2_img2mse = importlib.import_module(_NAME + ".robust_loss").fused_l2_img2mse

@@ -77,6 +77,34 @@ class _FusedAdaptiveMSE(torch.autograd.Function):
         return g * gx, None, None, gl[0:3].reshape(sa), gl[3:6].reshape(ss), None
 
 
+class _FusedL2(torch.autograd.Function):
+    """img2mse(x, y, 'l2', None, mask) on a CUDA [N,3] prediction: loss and dL/dx in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask):
+        def dense(t):
+            t = t.detach()
+            return t if t.dtype == torch.float32 and t.is_contiguous() else t.contiguous().float()
+
+        xc, yc = dense(x), dense(y)
+        mc = None if mask is None else dense(mask)
+        gx = torch.empty_like(xc)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        nat.check(nat.lib().npp_l2_fwd_bwd(xc.data_ptr(), yc.data_ptr(), nat.ptr(mc), x.shape[0], loss.data_ptr(),
+                                           gx.data_ptr(), nat.current_stream()))
+        ctx.save_for_backward(gx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gx,) = ctx.saved_tensors
+        return g * gx, None, None
+
+
+def fused_l2_img2mse(x, y, mask=None):
+    return _FusedL2.apply(x, y, mask)
+
+
 class NppAdaptiveLoss(nn.Module):
     def __init__(self, num_dims, float_dtype=np.float32, device="cuda", alpha_lo=0.001, alpha_hi=1.999, alpha_init=None,
                  scale_lo=1e-5, scale_init=1.0):

@@ -138,3 +138,27 @@ def test_fused_cuda_full_size_is_additive():
     l1, a1, s1 = run(n // 2, n)
     assert abs(lf - 0.5 * (l0 + l1)) < 1e-5 * abs(lf)
     assert (af - 0.5 * (a0 + a1)).abs().max().item() < 1e-5 and (sf - 0.5 * (s0 + s1)).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,use_mask", [(1, True), (1000, True), (16384, False)])
+def test_fused_l2_matches_formula(n, use_mask):
+    """img2mse(x, y, 'l2', None, mask) fused (npp_l2_fwd_bwd) against the reference formula evaluated in float64
+    (models/mse_calculator.py:14-27): value and gradient, with an upstream factor through backward."""
+    sys.path.insert(0, os.path.join(ROOT, "learning-continuous-implicit-representation-for-near-periodic-patterns_b200"))
+    from models.mse_calculator import img2mse
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.rand(n, 3, device="cuda", generator=g, requires_grad=True)
+    y = torch.rand(n, 3, device="cuda", generator=g)
+    m = (torch.rand(n, 1, device="cuda", generator=g) > 0.4).float() if use_mask else None
+    loss = img2mse(x, y, "l2", None, m) * 3.0
+    loss.backward()
+    xd, yd = x.detach().double(), y.double()
+    d = xd - yd
+    if m is not None:
+        d = d * m.double() + (1 - m.double()) * d * 0.3
+    ref = (d ** 2).mean()
+    w = torch.ones(n, 1, device="cuda", dtype=torch.float64) if m is None else m.double() + (1 - m.double()) * 0.3
+    gref = 2 * d * w / (3 * n)
+    assert abs(loss.item() / 3.0 - ref.item()) <= 2e-6 * abs(ref.item()) + 1e-12
+    assert (x.grad.double() / 3.0 - gref).abs().max().item() <= 1e-6 * gref.abs().max().item() + 1e-12
