@@ -104,6 +104,12 @@ int npp_backward(NppPlan* plan, int64_t n, const float* grad_logits, void* strea
 int npp_mse_fwd_bwd(NppPlan* plan, const float* logits, const float* target, const float* mask, int64_t n,
                     int64_t n_norm, float* pred, float* grad_logits, float* loss, void* stream);
 
+/* torch.optim.Adam single-tensor step (same arithmetic as npp_adam_step) on one caller-owned fp32 tensor of n elements:
+ * the small foreign parameters the reference also hands to its optimizer (adaptive_pix latents and the adaptive LPIPS /
+ * style heads, models/helpers.py:144-151).  step: 1-based count of the steps in which this tensor had a gradient. */
+int npp_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, void* stream);
+
 /* img2mse(x, y, 'l2', None, mask) of models/mse_calculator.py:13-27 on the network OUTPUT x [n,3] (after the sigmoid,
  * as NPP_completion/train.py:205-208 calls it) with its gradient: loss (device float, overwritten) = mean over [n,3] of
  * ((x - y)(m + 0.3 (1 - m)))^2, grad_x [n,3] = dL/dx.  mask [n,1] or NULL.  No plan needed. */

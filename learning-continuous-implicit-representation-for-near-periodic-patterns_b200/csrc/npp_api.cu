@@ -1182,6 +1182,23 @@ int npp_mse_fwd_bwd(NppPlan* p, const float* logits, const float* target, const 
   return 0;
 }
 
+int npp_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail("npp_adam_flat: null argument");
+  if (n <= 0) return 0;
+  if (step < 1) return fail("Adam step must be >= 1");
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 592) blocks = 592;
+  npp_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, beta1,
+                                                                    beta2, (float)((double)lr / bc1),
+                                                                    (float)(1.0 / std::sqrt(bc2)), eps);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int npp_l2_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, float* loss, float* grad_x,
                    void* stream) {
   if (!x || !y || !loss || !grad_x) return fail("npp_l2_fwd_bwd: null argument");

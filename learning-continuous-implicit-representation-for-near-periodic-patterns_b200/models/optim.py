@@ -1,8 +1,11 @@
 """Optimizer returned by create_npp_net: torch.optim.Adam semantics (reference models/helpers.py:164) with the
 NPP-Net parameters updated by one fused kernel over the plan arena and every foreign parameter (adaptive_pix,
-LPIPS adaptive heads, ...) by a plain torch.optim.Adam.  ``param_groups[i]['lr']`` may be rewritten between steps
+LPIPS adaptive heads, ...) by one small CUDA Adam launch each (npp_adam_flat; torch.optim.Adam for anything that is not a
+dense fp32 CUDA tensor).  ``param_groups[i]['lr']`` may be rewritten between steps
 exactly as the reference loop does (NPP_completion/train.py:258-263)."""
 import torch
+
+from ._core import native as _nat
 
 
 class NppAdam(torch.optim.Optimizer):
@@ -13,7 +16,11 @@ class NppAdam(torch.optim.Optimizer):
         own = set(id(p) for p in net._params) if net is not None else set()
         self._own = [p for p in params if id(p) in own]
         foreign = [p for p in params if id(p) not in own]
-        self._foreign = torch.optim.Adam(foreign, lr=lr, betas=betas, eps=eps) if foreign else None
+        # dense fp32 CUDA tensors (every foreign parameter of the reference scripts): one launch each, same arithmetic
+        self._small = [p for p in foreign if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()]
+        self._small_state = {}
+        rest = [p for p in foreign if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous())]
+        self._foreign = torch.optim.Adam(rest, lr=lr, betas=betas, eps=eps) if rest else None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -27,6 +34,17 @@ class NppAdam(torch.optim.Optimizer):
                 g.copy_(p.grad)                              # autograd cloned or accumulated: copy back into the arena
             plan.adam_step(group['lr'], betas=group['betas'], eps=group['eps'])
             self.net.mark_clean()
+        for p in self._small:
+            if p.grad is None:
+                continue                                     # torch.optim skips parameters without a gradient
+            st = self._small_state.get(id(p))
+            if st is None:
+                st = self._small_state[id(p)] = [0, torch.zeros_like(p), torch.zeros_like(p)]
+            st[0] += 1
+            g = p.grad if p.grad.is_contiguous() and p.grad.dtype == torch.float32 else p.grad.contiguous().float()
+            _nat.check(_nat.lib().npp_adam_flat(p.data_ptr(), g.data_ptr(), st[1].data_ptr(), st[2].data_ptr(), p.numel(),
+                                                group['lr'], group['betas'][0], group['betas'][1], group['eps'], st[0],
+                                                _nat.current_stream()))
         if self._foreign is not None:
             for g in self._foreign.param_groups:
                 g['lr'] = group['lr']

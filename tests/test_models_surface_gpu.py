@@ -221,3 +221,33 @@ def test_default_adaptive_robust_loss_iterations():
         optimizer.step()
     assert torch.isfinite(loss) and loss.item() < first
     assert 1e-3 < adaptive_pix.latent_scale.abs().max().item() < 6.5 * args.lrate
+
+
+def test_small_parameter_adam_matches_torch():
+    """Foreign parameters (adaptive_pix latents, adaptive LPIPS / style heads: models/helpers.py:144-151) are stepped by
+    npp_adam_flat: same trajectory as torch.optim.Adam, including a rewritten lr and a step without a gradient."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.optim import NppAdam
+    torch.manual_seed(3)
+    shapes = [(1, 3), (1, 3), (5, 7), (1, 1)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt = NppAdam(ours, lr=5e-4, betas=(0.9, 0.999), net=None)
+    topt = torch.optim.Adam(ref, lr=5e-4, betas=(0.9, 0.999))
+    for it in range(6):
+        lr = 5e-4 * (0.9 ** it)
+        for g in opt.param_groups:
+            g['lr'] = lr
+        for g in topt.param_groups:
+            g['lr'] = lr
+        for i, (a, b) in enumerate(zip(ours, ref)):
+            if it == 2 and i == 1:
+                a.grad = b.grad = None            # skipped by both, step counts stay aligned
+                continue
+            gr = torch.randn_like(a) * (10.0 ** (i - 1))
+            a.grad, b.grad = gr.clone(), gr.clone()
+        opt.step()
+        topt.step()
+        for a, b in zip(ours, ref):
+            torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=1e-8)
