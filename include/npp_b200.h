@@ -30,17 +30,23 @@ extern "C" {
 typedef struct NppPlan NppPlan;
 
 enum { NPP_MODEL_TOPK = 0, /* models/networks.py:8-95   NPP_Net      (p_topk > 1) */
-       NPP_MODEL_TOP1 = 1  /* models/networks.py:99-173 NPP_Net_top1 (p_topk == 1) */ };
+       NPP_MODEL_TOP1 = 1, /* models/networks.py:99-173 NPP_Net_top1 (p_topk == 1) */
+       NPP_MODEL_LIGHT = 2 /* models/networks.py:176-263 NPP_Net_light with len(freq_scales) == 1: the search-stage
+                              fit of NPP_proposal/search.py:85-148 (create_npp_net(is_search=True), helpers.py:91-103).
+                              Encoders in search mode: Embedder_periodic without raw input and without the Fourier
+                              expansion (embedder.py:93-95,140-148; 4*n_aug columns) and the 2-D Embedder on
+                              normalised coordinates (embedder.py:51-56,76-80; 2 + 4*n_freq columns). */ };
 
 typedef struct NppConfig {
   int32_t model;          /* NPP_MODEL_* */
   int32_t topk;           /* number of periodicity proposals K (create_npp_net, models/helpers.py:108-116) */
   int32_t depth;          /* netdepth D (options/arg_config.py:55-74), default 8 */
-  int32_t width;          /* netwidth W; this build requires W == 512 (the reference default) */
+  int32_t width;          /* netwidth W; 512 (the reference default) for NPP_Net / NPP_Net_top1, 256 (the search
+                             default, options/arg_config.py:116) or 512 for NPP_Net_light */
   int32_t skip_layer;     /* skips=[4] (models/helpers.py:90); -1 = none */
   int32_t n_aug;          /* len(freq_scales)*len(freq_offsets)*len(angle_offsets), embedder.py:117-120 */
   int32_t n_freq;         /* multires, number of Gaussian Fourier frequencies (embedder.py:25-26) */
-  int32_t include_input;  /* 1 outside search mode (embedder.py:105-109) */
+  int32_t include_input;  /* 1 outside search mode (embedder.py:105-109); must be 0 for NPP_MODEL_LIGHT */
   int32_t res_h, res_w;   /* image resolution res=(H,W) (NPP_completion/train.py:64) */
   int32_t wgrad_splits;   /* split-K factor of the weight-gradient GEMM, 0 = auto */
   int32_t reserved;
@@ -71,7 +77,8 @@ int npp_plan_destroy(NppPlan* plan);
 int npp_plan_arena_floats(const NppPlan* plan, int64_t* total_floats, int64_t* trained_floats);
 int npp_plan_tensor_count(const NppPlan* plan);
 int npp_plan_tensor_info(const NppPlan* plan, int index, NppTensorInfo* info);
-int npp_plan_encoding_width(const NppPlan* plan); /* K * B * (1+2*n_freq), 1386 at the defaults */
+int npp_plan_encoding_width(const NppPlan* plan); /* K * B * (1+2*n_freq), 1386 at the defaults;
+                                                     NPP_MODEL_LIGHT: (2+4*n_freq) + 4*n_aug = 62 */
 
 /* Bind caller-owned device arenas (fp32, `total_floats` each; grads/exp_avg/exp_avg_sq may be NULL
  * for inference-only use). */
@@ -82,7 +89,9 @@ int npp_plan_bind(NppPlan* plan, float* params, float* grads, float* exp_avg, fl
 int npp_sync_weights(NppPlan* plan, void* stream);
 
 /* Embedder_periodic.embed + Embedder.embed (models/embedder.py:51-56,140-148), materialised in the
- * reference layout [n, K*462] fp32.  coords: device [n,2] fp32 (row y, col x). */
+ * reference layout [n, K*462] fp32.  coords: device [n,2] fp32 (row y, col x).
+ * NPP_MODEL_LIGHT (search mode): [n, 42 + 20] = [embedder.embed(coords) | embedder_periodic.embed(coords)], the two
+ * tensors NPP_proposal/search.py:104-108 builds. */
 int npp_encode(NppPlan* plan, const float* coords, int64_t n, float* out, void* stream);
 
 /* NPP_Net.forward / NPP_Net_top1.forward on raw coordinates (models/networks.py:56-95,145-173);
@@ -90,7 +99,8 @@ int npp_encode(NppPlan* plan, const float* coords, int64_t n, float* out, void* 
 int npp_forward(NppPlan* plan, const float* coords, int64_t n, float* logits, void* stream);
 
 /* Same network on a materialised encoding: enc device [n, K*462] fp32 in the reference layout (rows of the
- * table built at NPP_completion/train.py:93-105), i.e. NPP_Net.forward(None, x_periodic) verbatim. */
+ * table built at NPP_completion/train.py:93-105), i.e. NPP_Net.forward(None, x_periodic) verbatim.
+ * NPP_MODEL_LIGHT: enc is the [n, 62] layout of npp_encode, i.e. NPP_Net_light.forward(x, x_periodic). */
 int npp_forward_encoded(NppPlan* plan, const float* enc, int64_t n, float* logits, void* stream);
 
 /* autograd backward of the forward above: grad_logits device [n,3] fp32 -> bound grads arena

@@ -88,7 +88,8 @@ struct Seg {
 
 struct Layer {
   std::string name;  // reference module path
-  int out = 0, in_ref = 0, kpad = 0;
+  int out = 0, in_ref = 0, kpad = 0;   // out: out_features as the GEMMs see them (out_ref rounded up to the 256 tile)
+  int out_ref = 0;                     // reference out_features (arena shape); padded units have zero weights
   std::vector<Seg> segs;
   int act = 0;  // 1 = snake
   int buf_h = -1, buf_d = -1, buf_delta = -1;
@@ -235,6 +236,8 @@ static int add_layer(NppPlan* p, const std::string& name, int out, int act,
                      const std::vector<std::pair<int, std::pair<int, int>>>& srcs) {
   Layer L;
   L.name = name;
+  L.out_ref = out;
+  out = round_up(out, BN);   // pos_linears.0 of NPP_Net_light at W = 256 has 128 units: the GEMMs run on a zero-padded tile
   L.out = out;
   L.act = act;
   int ref = 0, pad = 0;
@@ -275,11 +278,20 @@ static int build_graph(NppPlan* p) {
   p->Ep = round_up(p->E, 256);
   p->A = p->E * (c.topk - 1);
   p->Ap = round_up(p->A, 64);
+  if (c.model == NPP_MODEL_LIGHT) {
+    // search mode: the periodic encoding has no Fourier expansion (4*n_aug columns) and the second operand buffer
+    // holds the 2-D positional encoding that pos_linears.0 concatenates after feature1 (networks.py:249)
+    p->E = B;
+    p->Ep = round_up(p->E, 64);
+    p->A = 2 + 4 * c.n_freq;
+    p->Ap = round_up(p->A, 64);
+  }
+  const bool second = c.model != NPP_MODEL_TOP1;
   p->head_width = W / 2;
   p->buf_enc1 = add_buf(p, "enc1", p->Ep);
-  if (c.model == NPP_MODEL_TOPK) p->buf_enca = add_buf(p, "enc_aux", p->Ap);
+  if (second) p->buf_enca = add_buf(p, "enc_aux", p->Ap);
   p->buf_enc1_alt = add_buf(p, "enc1_alt", p->Ep);
-  if (c.model == NPP_MODEL_TOPK) p->buf_enca_alt = add_buf(p, "enc_aux_alt", p->Ap);
+  if (second) p->buf_enca_alt = add_buf(p, "enc_aux_alt", p->Ap);
 
   typedef std::pair<int, std::pair<int, int>> S;
   auto src = [](int buf, int w, int prod) { return S(buf, std::make_pair(w, prod)); };
@@ -305,6 +317,9 @@ static int build_graph(NppPlan* p) {
     const int f2 = add_layer(p, "feature_linear2", W, 0, {src(p->layers[s0].buf_h, W, s0)});        // :84
     last = add_layer(p, "pos_linears.0", W / 2, 1,
                      {src(p->layers[f1].buf_h, W, f1), src(p->layers[f2].buf_h, W, f2)});           // :85-92
+  } else if (c.model == NPP_MODEL_LIGHT) {
+    last = add_layer(p, "pos_linears.0", W / 2, 1,
+                     {src(p->layers[f1].buf_h, W, f1), src(p->buf_enca, p->A, -1)});                // :249-258
   } else {
     last = add_layer(p, "pos_linears.0", W / 2, 1, {src(p->layers[f1].buf_h, W, f1)});              // :161-170
   }
@@ -312,13 +327,19 @@ static int build_graph(NppPlan* p) {
 
   // arena: trained tensors first, in reference module order within that group
   for (auto& L : p->layers) {
-    add_tensor(p, L.name + ".weight", L.out, L.in_ref, 0, 1, &L.w_off);
-    add_tensor(p, L.name + ".bias", 1, L.out, 1, 1, &L.b_off);
+    add_tensor(p, L.name + ".weight", L.out_ref, L.in_ref, 0, 1, &L.w_off);
+    add_tensor(p, L.name + ".bias", 1, L.out_ref, 1, 1, &L.b_off);
   }
   add_tensor(p, "rgb_linear.weight", 3, W / 2, 0, 1, &p->rgb_w_off);
   add_tensor(p, "rgb_linear.bias", 1, 3, 1, 1, &p->rgb_b_off);
   p->arena_trained = p->arena_total;
   if (c.model == NPP_MODEL_TOP1) {  // allocated but unused by NPP_Net_top1.forward (networks.py:135)
+    add_tensor(p, "feature_linear2.weight", W, W, 0, 0, nullptr);
+    add_tensor(p, "feature_linear2.bias", 1, W, 1, 0, nullptr);
+  }
+  if (c.model == NPP_MODEL_LIGHT) {  // the scale branch is skipped when len(freq_scales) == 1 (networks.py:236-250)
+    add_tensor(p, "scale_linears.0.weight", W, W, 0, 0, nullptr);   // scale_dim == 0: Linear(W, W), networks.py:204
+    add_tensor(p, "scale_linears.0.bias", 1, W, 1, 0, nullptr);
     add_tensor(p, "feature_linear2.weight", W, W, 0, 0, nullptr);
     add_tensor(p, "feature_linear2.bias", 1, W, 1, 0, nullptr);
   }
@@ -425,7 +446,7 @@ static int alloc_plan_memory(NppPlan* p) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_reg, npp_head_fused_reg_kernel, 256, 0));
     if (per_sm_reg < per_sm) per_sm = per_sm_reg;
     if (per_sm > 2) per_sm = 2;
-    p->head_fused_blocks = coop && p->head_width == 256 ? per_sm * p->num_sms : 0;
+    p->head_fused_blocks = coop && p->head_width <= 256 ? per_sm * p->num_sms : 0;
   }
   CK(cudaMalloc(&p->logits_buf, (size_t)R * 3 * sizeof(float)));
 
@@ -438,7 +459,7 @@ static int alloc_plan_memory(NppPlan* p) {
     f.b_off = L.b_off;
     f.pg_off = L.pg_off;
     f.bg_off = L.bg_off;
-    f.out = L.out;
+    f.out = L.out_ref;
     f.in_ref = L.in_ref;
     f.kpad = L.kpad;
     f.split_col = L.segs.size() > 1 ? L.segs[1].ref_lo : L.in_ref;
@@ -448,7 +469,8 @@ static int alloc_plan_memory(NppPlan* p) {
     ShadowLayer s;
     memset(&s, 0, sizeof(s));
     s.w_off = L.w_off;
-    s.out = L.out;
+    s.out = L.out_ref;
+    s.wt_ld = L.out;
     s.in_ref = L.in_ref;
     s.kpad = L.kpad;
     s.split_col = f.split_col;
@@ -482,7 +504,7 @@ static int alloc_plan_memory(NppPlan* p) {
       u.w_off = fin[i].w_off; u.b_off = fin[i].b_off; u.pg_off = fin[i].pg_off; u.bg_off = fin[i].bg_off;
       u.out = fin[i].out; u.in_ref = fin[i].in_ref; u.kpad = fin[i].kpad;
       u.split_col = fin[i].split_col; u.off0 = fin[i].off0; u.off1 = fin[i].off1;
-      u.wf = sh[i].wf; u.wt = sh[i].wt;
+      u.wf = sh[i].wf; u.wt = sh[i].wt; u.wt_ld = sh[i].wt_ld;
       u.t_lo = sh[i].t_lo; u.t_hi = sh[i].t_hi; u.t_row0 = sh[i].t_row0;
       u.t_lo2 = sh[i].t_lo2; u.t_hi2 = sh[i].t_hi2; u.t_row02 = sh[i].t_row02;
       up.push_back(u);
@@ -846,6 +868,18 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
 // Encodes `coords` into encoding set `set` (0: enc1 / enc_aux, 1: their alternates).  zero_loss != nullptr: the kernel
 // also clears the step accumulators and *zero_loss (first kernel of a fused train step).
 static int launch_encode(NppPlan* p, const float* coords, long long n, int set, cudaStream_t st, float* zero_loss) {
+  if (p->cfg.model == NPP_MODEL_LIGHT) {
+    const int b1 = set ? p->buf_enc1_alt : p->buf_enc1;
+    const int bp = set ? p->buf_enca_alt : p->buf_enca;
+    const long long items = n * (2 * p->cfg.n_aug + 1 + p->cfg.n_freq);
+    unsigned blocks = (unsigned)std::min<long long>((items + 255) / 256, (long long)p->num_sms * 8);
+    npp_encode_search_kernel<<<blocks, 256, 0, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, p->bufs[bp].ptr,
+                                                     p->Ap, zero_loss ? p->acc : nullptr,
+                                                     zero_loss ? (int)p->acc_floats : 0, zero_loss);
+    CK(cudaGetLastError());
+    ++p->launches;
+    return 0;
+  }
   const int width = p->E;
   const int B = 2 * (p->cfg.include_input + 2 * p->cfg.n_aug);
   const int rows = std::max(1, ENC_THREADS / (B / 2));   // one thread per (row, base-feature pair)
@@ -875,7 +909,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     }
     p->enc_set = 0;
     __half* enca = p->buf_enca >= 0 ? p->bufs[p->buf_enca].ptr : nullptr;
-    npp_load_encoding_kernel<<<p->num_sms * 8, 256, 0, st>>>(enc_f32, (int)n, p->cfg.topk, p->E,
+    npp_load_encoding_kernel<<<p->num_sms * 8, 256, 0, st>>>(enc_f32, (int)n, npp_plan_encoding_width(p), p->E,
                                                              p->bufs[p->buf_enc1].ptr, p->Ep, enca, p->Ap);
     CK(cudaGetLastError());
     ++p->launches;
@@ -1007,11 +1041,21 @@ int npp_abi_version(void) { return 1; }
 int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   if (!cfg || !out) return fail("npp_plan_create: null argument");
   *out = nullptr;
-  if (cfg->model != NPP_MODEL_TOPK && cfg->model != NPP_MODEL_TOP1) return fail("unknown model kind");
+  if (cfg->model != NPP_MODEL_TOPK && cfg->model != NPP_MODEL_TOP1 && cfg->model != NPP_MODEL_LIGHT)
+    return fail("unknown model kind");
+  if (cfg->model == NPP_MODEL_LIGHT) {
+    if (cfg->topk != 1) return fail("NPP_Net_light takes one proposal (topk == 1)");
+    if (cfg->include_input != 0) return fail("NPP_Net_light uses the search-mode encoders (include_input == 0)");
+    if (cfg->n_freq < 1) return fail("NPP_Net_light needs the positional frequencies (n_freq >= 1)");
+  }
   if (cfg->model == NPP_MODEL_TOPK && cfg->topk < 2) return fail("NPP_Net (top-K) needs topk >= 2");
   if (cfg->model == NPP_MODEL_TOP1 && cfg->topk != 1) return fail("NPP_Net_top1 needs topk == 1");
   if (cfg->topk > MAX_TOPK) return fail("topk exceeds MAX_TOPK=8");
-  if (cfg->width != 512) return fail("this build supports netwidth == 512 only (the reference default)");
+  if (cfg->model == NPP_MODEL_LIGHT) {
+    if (cfg->width != 256 && cfg->width != 512) return fail("NPP_Net_light: netwidth must be 256 (the search default) or 512");
+  } else if (cfg->width != 512) {
+    return fail("this build supports netwidth == 512 only (the reference default)");
+  }
   if (cfg->depth < 2 || cfg->depth > 16) return fail("netdepth must be in [2,16]");
   if (cfg->skip_layer >= cfg->depth - 1) return fail("skip layer must be < depth-1");
   if (cfg->n_aug < 1 || cfg->n_aug > MAX_AUG) return fail("n_aug out of range");
@@ -1094,7 +1138,10 @@ int npp_plan_tensor_info(const NppPlan* p, int i, NppTensorInfo* info) {
   *info = p->tensors[i];
   return 0;
 }
-int npp_plan_encoding_width(const NppPlan* p) { return p ? p->E * p->cfg.topk : 0; }
+int npp_plan_encoding_width(const NppPlan* p) {
+  if (!p) return 0;
+  return p->cfg.model == NPP_MODEL_LIGHT ? p->E + p->A : p->E * p->cfg.topk;
+}
 
 int npp_plan_bind(NppPlan* p, float* params, float* grads, float* m, float* v) {
   if (!p || !params) return fail("npp_plan_bind: params arena is required");
@@ -1115,7 +1162,10 @@ int npp_sync_weights(NppPlan* p, void* stream) {
 int npp_encode(NppPlan* p, const float* coords, int64_t n, float* out, void* stream) {
   if (!p || !coords || !out) return fail("npp_encode: null argument");
   if (n <= 0) return 0;
-  npp_encode_f32_kernel<<<p->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(coords, (int)n, p->enc, out);
+  if (p->cfg.model == NPP_MODEL_LIGHT)
+    npp_encode_search_f32_kernel<<<p->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(coords, (int)n, p->enc, out);
+  else
+    npp_encode_f32_kernel<<<p->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(coords, (int)n, p->enc, out);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1255,7 +1305,10 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   // the encode kernel clears the accumulators and the loss scalar of this step
   CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false, nullptr, loss));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
-  const bool fused_head = p->head_fused_blocks > 0 && !getenv("NPP_SPLIT_HEAD");
+  // The fused head is a cooperative launch with a grid barrier.  Two such grids running at the same time (two plans
+  // on two streams) can each hold part of the SMs and wait for the rest: search-stage fits are meant to run several
+  // candidates side by side (NPP_proposal/search.py:85 loops over up to 9), so NPP_Net_light takes the two-kernel head.
+  const bool fused_head = p->head_fused_blocks > 0 && p->cfg.model != NPP_MODEL_LIGHT && !getenv("NPP_SPLIT_HEAD");
   if (fused_head) {
     // head forward + loss + head backward in one cooperative launch (grid barrier around the max|g| reduction)
     CKI(prepare(p, n));
@@ -1280,7 +1333,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     const int want = (int)((n + 7) / 8);   // at least one row per warp
     if (blocks > want) blocks = want;
     int rows_per_block = (int)((n + blocks - 1) / blocks);
-    if (rows_per_block <= 8 * HEAD_MAXR && !getenv("NPP_HEAD_GENERIC")) {
+    if (rows_per_block <= 8 * HEAD_MAXR && width == 256 && !getenv("NPP_HEAD_GENERIC")) {
       void* rargs[] = {&hp, &dp, &ld, &ni, &w, &b, &target, &mask, &ic, &logits, &g, &loss, &amax,
                        &delta, &ldd, &head_acc, &bias_acc, &bar, &rows_per_block};
       CK(cudaLaunchCooperativeKernel((const void*)npp_head_fused_reg_kernel, dim3((unsigned)blocks), dim3(256), rargs, 0,

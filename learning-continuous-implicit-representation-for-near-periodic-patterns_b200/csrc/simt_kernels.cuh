@@ -231,15 +231,96 @@ __global__ void npp_encode_f32_kernel(const float* __restrict__ coords, int n, E
   }
 }
 
-// Materialised mode: a caller-supplied fp32 encoding [n, topk*width] (reference layout, e.g. rows gathered
-// from the reference's precomputed table, NPP_completion/train.py:166-181) -> the fp16 operand buffers.
-__global__ void npp_load_encoding_kernel(const float* __restrict__ enc, int n, int topk, int width,
-                                         __half* __restrict__ enc1, int ld1, __half* __restrict__ enca, int lda) {
-  const long long total = (long long)n * topk * width;
+// ---------------------------------------------------------------- search mode (NPP_Net_light)
+// create_npp_net(is_search=True) (models/helpers.py:87-103) builds two encoders:
+//   Embedder_periodic without raw input and without the Fourier expansion (embedder.py:93-95): 4*n_aug columns,
+//     fn_x list then fn_y list, each [sin phi_0, cos phi_0, sin phi_1, ...]  (npp_base_feature with include_input 0);
+//   the 2-D Embedder on coordinates normalised in place, row first (embedder.py:51-56,76-80): 2 + 4*n_freq columns
+//     [yn, xn, sin(f_0 yn), sin(f_0 xn), cos(f_0 yn), cos(f_0 xn), sin(f_1 yn), ...].
+// Work item = (row, group): groups [0, 2*n_aug) are the (sin, cos) pairs of one phase, group 2*n_aug is the raw
+// normalised pair, the following n_freq groups are the four values of one frequency.
+__device__ __forceinline__ float npp_search_norm(const EncTable& t, int d, float y, float x) {
+  // ((inputs[:, d] / res[d]) - 0.5) * 2   embedder.py:53-54 (d = 0: row / H, d = 1: col / W)
+  const float v = d == 0 ? __fdiv_rn(y, t.res_h) : __fdiv_rn(x, t.res_w);
+  return __fmul_rn(__fsub_rn(v, 0.5f), 2.0f);
+}
+
+template <typename T>
+__device__ __forceinline__ void npp_search_store2(T* p, float a, float b);
+template <>
+__device__ __forceinline__ void npp_search_store2<__half>(__half* p, float a, float b) {
+  *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
+}
+template <>
+__device__ __forceinline__ void npp_search_store2<float>(float* p, float a, float b) {
+  p[0] = a;
+  p[1] = b;
+}
+
+template <typename T>
+__device__ __forceinline__ void npp_search_item(const EncTable& t, int g, float y, float x, T* per, T* pos) {
+  const int n_pairs = 2 * t.n_aug;
+  if (g < n_pairs) {
+    const int dir = g / t.n_aug, aug = g - dir * t.n_aug;
+    const float phi = npp_phase(t, 0, dir, aug, y, x);
+    npp_search_store2<T>(per + 2 * g, sinf(phi), cosf(phi));
+  } else {
+    const float yn = npp_search_norm(t, 0, y, x), xn = npp_search_norm(t, 1, y, x);
+    const int k = g - n_pairs - 1;
+    if (k < 0) {
+      npp_search_store2<T>(pos, yn, xn);
+    } else {
+      const float ay = __fmul_rn(yn, t.freq[k]), ax = __fmul_rn(xn, t.freq[k]);
+      npp_search_store2<T>(pos + 2 + 4 * k, sinf(ay), sinf(ax));
+      npp_search_store2<T>(pos + 4 + 4 * k, cosf(ay), cosf(ax));
+    }
+  }
+}
+
+// fp16 operand buffers of the fused path: per = enc1 [n, ld1], pos = the second K segment of pos_linears.0 [n, ldp].
+__global__ void __launch_bounds__(256) npp_encode_search_kernel(const float* __restrict__ coords, int n, EncTable t,
+                                                                __half* __restrict__ enc1, int ld1,
+                                                                __half* __restrict__ pos, int ldp,
+                                                                float* __restrict__ zero_a, int zero_a_n,
+                                                                float* __restrict__ zero_b) {
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < zero_a_n; i += blockDim.x) zero_a[i] = 0.f;
+    if (zero_b != nullptr && threadIdx.x == 0) *zero_b = 0.f;
+  }
+  const int groups = 2 * t.n_aug + 1 + t.n_freq;
+  const long long total = (long long)n * groups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / (topk * width);
-    const int c = (int)(idx - row * (topk * width));
+    const long long row = idx / groups;
+    const int g = (int)(idx - row * groups);
+    npp_search_item<__half>(t, g, coords[2 * row], coords[2 * row + 1], enc1 + row * ld1, pos + row * ldp);
+  }
+}
+
+// fp32 materialised search encodings: out [n, 4*n_aug + 2 + 4*n_freq] = [periodic | positional].
+__global__ void npp_encode_search_f32_kernel(const float* __restrict__ coords, int n, EncTable t,
+                                             float* __restrict__ out) {
+  const int groups = 2 * t.n_aug + 1 + t.n_freq;
+  const int wper = 4 * t.n_aug, width = wper + 2 + 4 * t.n_freq;
+  const long long total = (long long)n * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / groups;
+    const int g = (int)(idx - row * groups);
+    float* o = out + row * width;
+    npp_search_item<float>(t, g, coords[2 * row], coords[2 * row + 1], o, o + wper);
+  }
+}
+
+// Materialised mode: a caller-supplied fp32 encoding [n, topk*width] (reference layout, e.g. rows gathered
+// from the reference's precomputed table, NPP_completion/train.py:166-181) -> the fp16 operand buffers.
+__global__ void npp_load_encoding_kernel(const float* __restrict__ enc, int n, int cols, int width,
+                                         __half* __restrict__ enc1, int ld1, __half* __restrict__ enca, int lda) {
+  const long long total = (long long)n * cols;   // columns [0, width) feed enc1, [width, cols) the second buffer
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cols;
+    const int c = (int)(idx - row * cols);
     const __half v = __float2half_rn(enc[idx]);
     if (c < width) enc1[row * ld1 + c] = v;
     else enca[row * lda + (c - width)] = v;
@@ -487,19 +568,21 @@ __device__ __forceinline__ void npp_head_bwd_part(const float* g, const __half* 
   const int row_begin = blockIdx.x * rows_per_block;
   const int row_end = min(row_begin + rows_per_block, n);
   float gsum[3] = {0.f, 0.f, 0.f};
-  for (int k0 = lane * 8; k0 < width; k0 += 256) {   // one pass for width == 256
+  for (int kb = 0; kb < width; kb += 256) {   // one pass for width <= 256; the barriers below are block-wide
+    const int k0 = kb + lane * 8;
+    const bool active = k0 < width;           // width is a multiple of 8: a lane's eight columns are all in or all out
     float wr[3][8], aw[3][8], ab[8];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        wr[c][i] = w[c * width + k0 + i];
+        wr[c][i] = active ? w[c * width + k0 + i] : 0.f;
         aw[c][i] = 0.f;
       }
 #pragma unroll
     for (int i = 0; i < 8; ++i) ab[i] = 0.f;
 #pragma unroll 4
-    for (int row = row_begin + wib; row < row_end; row += 8) {
+    for (int row = row_begin + wib; row < row_end && active; row += 8) {
       const float g0 = __ldcg(g + 3 * (size_t)row), g1 = __ldcg(g + 3 * (size_t)row + 1),
                   g2 = __ldcg(g + 3 * (size_t)row + 2);
       const uint4 hraw = *reinterpret_cast<const uint4*>(hp + (size_t)row * ld + k0);
@@ -527,14 +610,14 @@ __device__ __forceinline__ void npp_head_bwd_part(const float* g, const __half* 
         aw[2][2 * i + 1] = fmaf(g2, h.y, aw[2][2 * i + 1]);
       }
       *reinterpret_cast<uint4*>(delta + (size_t)row * ldd + k0) = outv;
-      if (k0 == lane * 8 && lane == 0) {
+      if (kb == 0 && lane == 0) {
         gsum[0] += g0;
         gsum[1] += g1;
         gsum[2] += g2;
       }
     }
     // block reduction over the 8 warps (column k0+i of accumulator a lives at red[warp][a*256 + ...])
-    if (k0 < 256) {
+    if (kb == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         red[wib][0 * 256 + lane * 8 + i] = aw[0][i];
@@ -978,10 +1061,11 @@ __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLa
 // Replaces grad_finalize + adam + shadow (3 kernels, ~2x the bytes) when nobody needs the gradient arena.
 struct UpdateLayer {
   long long w_off, b_off, pg_off, bg_off;
-  int out, in_ref, kpad;
+  int out, in_ref, kpad;       // out: reference out_features (rows of the arena tensor)
   int split_col, off0, off1;
   __half* wf;
   __half* wt;
+  int wt_ld;                   // row pitch of wt: out rounded up to the GEMM tile (256)
   int t_lo, t_hi, t_row0;
   int t_lo2, t_hi2, t_row02;
 };
@@ -1167,7 +1251,7 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
       if (cc >= L.t_lo && cc < L.t_hi) trow = L.t_row0 + (cc - L.t_lo);
       else if (cc >= L.t_lo2 && cc < L.t_hi2) trow = L.t_row02 + (cc - L.t_lo2);
       if (trow >= 0)
-        *reinterpret_cast<__half2*>(L.wt + (long long)trow * L.out + r0 + rp) =
+        *reinterpret_cast<__half2*>(L.wt + (long long)trow * L.wt_ld + r0 + rp) =
             __floats2half2_rn(tile[rp][pcl], tile[rp + 1][pcl]);
     }
   }
@@ -1226,7 +1310,8 @@ struct ShadowLayer {
   int out, in_ref, kpad;
   int split_col, off0, off1;  // reference column -> padded column (same rule as FinalizeLayer)
   __half* wf;                 // [out, kpad]
-  __half* wt;                 // [wt_rows, out] or null
+  __half* wt;                 // [wt_rows, wt_ld] or null
+  int wt_ld;                  // out rounded up to the GEMM tile (256); columns >= out stay zero
   int t_lo, t_hi, t_row0;     // reference columns [t_lo, t_hi) go to wt rows t_row0 + (c - t_lo)
   int t_lo2, t_hi2, t_row02;  // optional second range
 };
@@ -1260,7 +1345,7 @@ __global__ void __launch_bounds__(256) npp_shadow_kernel(const ShadowLayer* __re
         int trow = -1;
         if (c >= L.t_lo && c < L.t_hi) trow = L.t_row0 + (c - L.t_lo);
         else if (c >= L.t_lo2 && c < L.t_hi2) trow = L.t_row02 + (c - L.t_lo2);
-        if (trow >= 0) L.wt[(long long)trow * L.out + r] = __float2half_rn(tile[tx][ty + 8 * i]);
+        if (trow >= 0) L.wt[(long long)trow * L.wt_ld + r] = __float2half_rn(tile[tx][ty + 8 * i]);
       }
     }
   }

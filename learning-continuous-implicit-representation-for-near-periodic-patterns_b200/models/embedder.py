@@ -34,14 +34,34 @@ class FourierEmbedder:
         return torch.cat(outs, -1)
 
 
-class PeriodicEmbedder:
-    """Embedder_periodic of the reference (embedder.py:94-148): constants only."""
+class SearchPositionalEmbedder(FourierEmbedder):
+    """Embedder(input_dims=2, is_search=True) of the reference (embedder.py:51-56,76-80): [N,2] coordinates,
+    normalised in place, then [u, sin(u f_0), cos(u f_0), ...] -> 2 + 4*multires columns."""
 
-    def __init__(self, res, selected_angles, selected_periods, freq_scales, freq_offsets, angle_offsets):
+    def __init__(self, multires, res):
+        super().__init__(multires, res)
+        self.out_dim = 2 + 4 * multires
+        self.is_search = True
+
+    def embed(self, inputs):
+        if _registry.mode() == "coords":
+            return inputs          # NPP_Net_light encodes inside the kernels (npp_encode_search_kernel)
+        inputs[:, 0] = ((inputs[:, 0] / self.res[0]) - 0.5) * 2
+        inputs[:, 1] = ((inputs[:, 1] / self.res[1]) - 0.5) * 2
+        return super().embed(inputs)
+
+
+class PeriodicEmbedder:
+    """Embedder_periodic of the reference (embedder.py:94-148): constants only.  include_input is False in search
+    mode (embedder.py:93-95)."""
+
+    def __init__(self, res, selected_angles, selected_periods, freq_scales, freq_offsets, angle_offsets,
+                 include_input=True):
         self.res = tuple(int(r) for r in res)
         self.cos_t, self.sin_t, self.period = EncoderSpec.proposal_tables(
             selected_angles, selected_periods, freq_scales, freq_offsets, angle_offsets)
-        self.out_dim = 2 * (1 + 2 * self.cos_t.shape[1])
+        self.include_input = bool(include_input)
+        self.out_dim = 2 * (int(self.include_input) + 2 * self.cos_t.shape[1])
         self.index = _registry.add_periodic(self)
         self._plan = None
 
@@ -53,7 +73,7 @@ class PeriodicEmbedder:
         # table mode: the 22 base features of this proposal, computed by the CUDA encoder (n_freq = 0)
         if self._plan is None:
             spec = EncoderSpec(res=self.res, cos_t=self.cos_t[None], sin_t=self.sin_t[None], period=self.period[None],
-                               freqs=np.zeros((0,), np.float32))
+                               freqs=np.zeros((0,), np.float32), include_input=self.include_input)
             self._plan = Plan(spec, max_rows=128, training=False)
         return self._plan.encode(inputs)
 
@@ -62,16 +82,12 @@ def get_embedder(multires, i=0, res=None, selected_angles=None, selected_periods
                  freq_scales=None, freq_offsets=None, angle_offsets=None, is_search=False):
     if i == -1:
         return nn.Identity(), 3
-    if is_search:
-        # periodicity search (NPP_Net_light) stays reference PyTorch (BASELINE.json north_star)
-        from ._reference import reference_module
-        return reference_module("embedder").get_embedder(multires, i, res, selected_angles, selected_periods,
-                                                         freq_scales, freq_offsets, angle_offsets, is_search)
     if selected_periods is None and selected_angles is None:
-        e = FourierEmbedder(multires, res)
+        e = SearchPositionalEmbedder(multires, res) if is_search else FourierEmbedder(multires, res)
         _registry.begin_session(e)
         return e, e.out_dim
-    e = PeriodicEmbedder(res, selected_angles, selected_periods, freq_scales, freq_offsets, angle_offsets)
+    e = PeriodicEmbedder(res, selected_angles, selected_periods, freq_scales, freq_offsets, angle_offsets,
+                         include_input=not is_search)
     return e, e.out_dim
 
 
@@ -82,4 +98,5 @@ def current_encoder_spec() -> EncoderSpec:
                            "proposal (as create_npp_net does, reference models/helpers.py:87,108-116)")
     per = _registry.periodic
     return EncoderSpec(res=per[0].res, cos_t=np.stack([p.cos_t for p in per]), sin_t=np.stack([p.sin_t for p in per]),
-                       period=np.stack([p.period for p in per]), freqs=_registry.nerf.freqs)
+                       period=np.stack([p.period for p in per]), freqs=_registry.nerf.freqs,
+                       include_input=per[0].include_input)

@@ -9,7 +9,7 @@ import torch.nn.functional as F  # noqa: F401
 from .mse_calculator import *  # noqa: F401,F403
 from .embedder import *  # noqa: F401,F403
 from .networks import *  # noqa: F401,F403
-from .networks import NPP_Net, NPP_Net_top1
+from .networks import NPP_Net, NPP_Net_top1, NPP_Net_light
 from .embedder import get_embedder
 from .optim import NppAdam
 
@@ -52,27 +52,33 @@ def render(select_coords_emb, select_coords_emb_periodic, args, network_query_fn
 def create_npp_net(args, selected_angles, selected_periods, res, percep_net, is_search=False, style_net=None):
     """Same 7-tuple as the reference (models/helpers.py:75-175).  The model is never wrapped in nn.DataParallel:
     this framework runs one process per GPU (data parallelism is an NCCL all-reduce of the gradient arena)."""
+    embedder, freq_nerf = get_embedder(args.multires, args.i_embed, res, is_search=is_search)
     if is_search:
-        from ._reference import reference_module
-        return reference_module("helpers").create_npp_net(args, selected_angles, selected_periods, res, percep_net,
-                                                          is_search=True, style_net=style_net)
-    embedder, freq_nerf = get_embedder(args.multires, args.i_embed, res, is_search=False)
-    embedder_periodics, input_ch_periodics = [], []
-    for i in range(args.p_topk):
-        e, ch = get_embedder(args.multires, args.i_embed, res, selected_angles=selected_angles[i],
-                             selected_periods=selected_periods[i], freq_scales=args.freq_scales,
-                             freq_offsets=args.freq_offsets, angle_offsets=args.angle_offsets)
-        embedder_periodics.append(e)
-        input_ch_periodics.append(ch)
-    input_ch_periodics = np.array(input_ch_periodics)
-    common = dict(D=args.netdepth, W=args.netwidth, freq_nerf=freq_nerf, freq_scales=args.freq_scales,
-                  freq_offsets=args.freq_offsets, angle_offsets=args.angle_offsets, output_ch=3, skips=[4],
-                  activation=args.activation)
-    if args.p_topk > 1:
-        model = NPP_Net(input_ch_periodic=input_ch_periodics[:1].sum(),
-                        input_ch_periodic_aux=input_ch_periodics[1:].sum(), **common)
+        # one candidate periodicity, no top-K in the model (helpers.py:91-103)
+        embedder_periodics, input_ch_periodic = get_embedder(
+            args.multires, args.i_embed, res, selected_angles=selected_angles, selected_periods=selected_periods,
+            freq_scales=args.freq_scales, freq_offsets=args.freq_offsets, angle_offsets=args.angle_offsets,
+            is_search=True)
+        model = NPP_Net_light(D=args.netdepth, W=args.netwidth, input_ch=freq_nerf, input_ch_periodic=input_ch_periodic,
+                              freq_scales=args.freq_scales, freq_offsets=args.freq_offsets,
+                              angle_offsets=args.angle_offsets, output_ch=3, skips=[4], activation=args.activation)
     else:
-        model = NPP_Net_top1(input_ch_periodic=input_ch_periodics[:1].sum(), **common)
+        embedder_periodics, input_ch_periodics = [], []
+        for i in range(args.p_topk):
+            e, ch = get_embedder(args.multires, args.i_embed, res, selected_angles=selected_angles[i],
+                                 selected_periods=selected_periods[i], freq_scales=args.freq_scales,
+                                 freq_offsets=args.freq_offsets, angle_offsets=args.angle_offsets)
+            embedder_periodics.append(e)
+            input_ch_periodics.append(ch)
+        input_ch_periodics = np.array(input_ch_periodics)
+        common = dict(D=args.netdepth, W=args.netwidth, freq_nerf=freq_nerf, freq_scales=args.freq_scales,
+                      freq_offsets=args.freq_offsets, angle_offsets=args.angle_offsets, output_ch=3, skips=[4],
+                      activation=args.activation)
+        if args.p_topk > 1:
+            model = NPP_Net(input_ch_periodic=input_ch_periodics[:1].sum(),
+                            input_ch_periodic_aux=input_ch_periodics[1:].sum(), **common)
+        else:
+            model = NPP_Net_top1(input_ch_periodic=input_ch_periodics[:1].sum(), **common)
 
     grad_vars = list(model.parameters())
     if adaptive_pix is not None:

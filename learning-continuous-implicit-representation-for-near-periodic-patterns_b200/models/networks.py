@@ -1,6 +1,6 @@
 """NPP_Net / NPP_Net_top1 with the reference constructor and forward signatures (models/networks.py:8-173),
 executed by libnpp_b200 (tcgen05 GEMMs with fused bias / snake epilogues, recomputation-free backward, see
-DESIGN.md).  NPP_Net_light (periodicity search) stays reference PyTorch and is loaded from the reference checkout.
+DESIGN.md), and NPP_Net_light (:176-263), the search-stage network, on the same kernels.
 
 Parameters are ``nn.Parameter`` views into one flat fp32 arena owned by the plan, under the reference's state_dict
 names, so ``model.parameters()``, ``state_dict()`` / ``load_state_dict()`` and foreign optimisers keep working.
@@ -11,7 +11,7 @@ import torch.nn.functional as F  # noqa: F401  (re-exported like the reference m
 
 from .activations import *  # noqa: F401,F403
 from . import embedder as _embedder
-from ._core import Plan, native
+from ._core import Plan, native, plan as _planmod
 
 
 class _NppFunction(torch.autograd.Function):
@@ -59,7 +59,7 @@ class _ArenaLinear(nn.Module):
 
 
 class _FusedNet(nn.Module):
-    def _build(self, topk_model, D, W, skips, activation, output_ch, reference_order):
+    def _build(self, topk_model, D, W, skips, activation, output_ch, reference_order, light=False):
         if activation != 'snake':
             raise NotImplementedError("the B200 path implements activation='snake' (the reference default, "
                                       "options/arg_config.py:29); relu is not built")
@@ -69,8 +69,16 @@ class _FusedNet(nn.Module):
         spec = _embedder.current_encoder_spec()
         if (spec.topk > 1) != topk_model:
             raise ValueError("number of registered proposals does not match the network class")
+        if light != (not spec.include_input):
+            raise ValueError("NPP_Net_light goes with the search-mode embedders (get_embedder(..., is_search=True)) "
+                             "and the other networks with the regular ones")
         self._spec = spec
-        self._plan = Plan(spec, depth=D, width=W, skip_layer=skips[0], max_rows=1 << 15)
+        # `i in skips` is tested for i < D (forward) and i < D-1 (constructor): a skip index beyond the trunk is inert
+        # (the search default D=4 with skips=[4], options/arg_config.py:114)
+        self._skip_layer = skips[0] if skips[0] < D - 1 else -1
+        self._model_kind = _planmod.MODEL_LIGHT if light else None
+        self._plan = Plan(spec, depth=D, width=W, skip_layer=self._skip_layer, max_rows=1 << 15,
+                          model=self._model_kind)
         self._generation = 0
         views = self._plan.param_views()
         # Initialise exactly like the reference: construct nn.Linear modules in the reference's order
@@ -85,7 +93,7 @@ class _FusedNet(nn.Module):
             return _ArenaLinear(views[name + ".weight"], views[name + ".bias"])
 
         self.periodic_linears = nn.ModuleList([holder(f"periodic_linears.{i}") for i in range(D)])
-        if topk_model:
+        if topk_model or light:
             self.scale_linears = nn.ModuleList([holder("scale_linears.0")])
         self.pos_linears = nn.ModuleList([holder("pos_linears.0")])
         self.feature_linear1 = holder("feature_linear1")
@@ -107,8 +115,8 @@ class _FusedNet(nn.Module):
         if n > self._plan.max_rows:
             old = self._plan
             cap = 1 << (int(n) - 1).bit_length()
-            self._plan = Plan(self._spec, depth=self.D, width=self.W, skip_layer=self.skips[0], max_rows=cap,
-                              arenas=(old.params, old.grads, old.exp_avg, old.exp_avg_sq))
+            self._plan = Plan(self._spec, depth=self.D, width=self.W, skip_layer=self._skip_layer, max_rows=cap,
+                              arenas=(old.params, old.grads, old.exp_avg, old.exp_avg_sq), model=self._model_kind)
             self._plan.adam_steps = old.adam_steps
             self._plan.sync_weights()
             old.close()
@@ -194,8 +202,31 @@ class NPP_Net_top1(_FusedNet):
         assert self._plan.encoding_width == ch
 
 
-def __getattr__(name):
-    if name == "NPP_Net_light":      # periodicity search stays reference PyTorch
-        from ._reference import reference_module
-        return reference_module("networks").NPP_Net_light
-    raise AttributeError(name)
+class NPP_Net_light(_FusedNet):
+    """The search-stage network (networks.py:176-263) for len(freq_scales) == 1, where the scale MLP is skipped:
+    periodic trunk -> feature_linear1 -> cat(feature1, x) -> pos_linears.0 -> rgb_linear.  `x` is the 2-D positional
+    encoding and `x_periodic` the periodic one; in 'coords' embed mode both are the raw [N,2] coordinates."""
+
+    def __init__(self, input_ch_periodic, freq_scales, freq_offsets, angle_offsets, D=8, W=256, input_ch=3,
+                 output_ch=3, skips=[4], activation='relu'):
+        super().__init__()
+        self.scale, self.offset, self.angle_offset = len(freq_scales), len(freq_offsets), len(angle_offsets)
+        if self.scale != 1:
+            raise NotImplementedError("NPP_Net_light is built for len(freq_scales) == 1 (the reference default, "
+                                      "options/arg_config.py:18), where the scale MLP is not executed")
+        ch = 2 * (2 * self.offset * self.angle_offset)            # networks.py:188
+        if int(input_ch_periodic) != ch:
+            raise ValueError(f"input_ch_periodic={input_ch_periodic} but the search-mode periodic encoding has {ch} columns")
+        self.input_ch, self.input_ch_periodic = int(input_ch), ch
+        order = [(f"periodic_linears.{i}", (W, ch if i == 0 else (W + ch if (i - 1) in skips else W))) for i in range(D)]
+        order += [("scale_linears.0", (W, W)), ("pos_linears.0", (W // 2, self.input_ch + W)),
+                  ("feature_linear1", (W, W)), ("feature_linear2", (W, W)), ("alpha_linear", (1, W)),
+                  ("rgb_linear", (output_ch, W // 2))]
+        self._build(False, D, W, list(skips), activation, output_ch, order, light=True)
+        assert self._plan.encoding_width == ch + self.input_ch, "embedder widths do not match input_ch(_periodic)"
+
+    def forward(self, x, x_periodic):
+        if x_periodic.shape[1] == 2:
+            return super().forward(None, x_periodic)
+        # materialised encodings: the kernels take [periodic | positional] (npp_forward_encoded)
+        return super().forward(None, torch.cat([x_periodic.float(), x.float().to(x_periodic.device)], -1))

@@ -15,6 +15,7 @@ from . import _native as nat
 
 MODEL_TOPK = 0
 MODEL_TOP1 = 1
+MODEL_LIGHT = 2      # NPP_Net_light with the search-mode encoders (include/npp_b200.h)
 
 
 @dataclass
@@ -89,7 +90,8 @@ class Plan:
     """One fused NPP-Net instance on the current CUDA device."""
 
     def __init__(self, enc: EncoderSpec, *, depth: int = 8, width: int = 512, skip_layer: int = 4,
-                 max_rows: int = 1 << 16, wgrad_splits: int = 0, training: bool = True, arenas=None):
+                 max_rows: int = 1 << 16, wgrad_splits: int = 0, training: bool = True, arenas=None,
+                 model: Optional[int] = None):
         if not torch.cuda.is_available():
             raise nat.NppError("npp_b200 needs a CUDA device (B200, sm_100); there is no CPU fallback")
         self.lib = nat.lib()
@@ -97,7 +99,7 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.max_rows = int(max_rows)
         self.topk = enc.topk
-        self.model = MODEL_TOPK if enc.topk > 1 else MODEL_TOP1
+        self.model = (MODEL_TOPK if enc.topk > 1 else MODEL_TOP1) if model is None else int(model)
         cfg = nat.NppConfig()
         cfg.model = self.model
         cfg.topk = enc.topk

@@ -268,3 +268,109 @@ def init_params(rng, topk=3, width=512, depth=8, skips=(4,), ch=462):
     lin("alpha_linear", 1, width)
     lin("rgb_linear", 3, width // 2)
     return p
+
+
+# ------------------------------------------------------------- search stage (NPP_Net_light)
+def encode_search_positional(coords, freqs, res):
+    """Embedder.embed in search mode (models/embedder.py:51-56 with input_dims=2, :76-80):
+    coordinates normalised in place, row by res[0] and column by res[1], then
+    cat([u, sin(u f_0), cos(u f_0), ...], -1) on the [N,2] matrix -> [N, 2 + 4*n_freq]."""
+    c = np.asarray(coords, F32)
+    u = np.stack([((c[:, 0] / F32(res[0])).astype(F32) - F32(0.5)) * F32(2),
+                  ((c[:, 1] / F32(res[1])).astype(F32) - F32(0.5)) * F32(2)], 1).astype(F32)
+    return encode_fourier(u, freqs)
+
+
+def encode_search(coords, table, freqs, res):
+    """The two tensors NPP_proposal/search.py:104-108 builds for one candidate periodicity:
+    (embedder.embed(coords) [N,42], embedder_periodic.embed(coords) [N,20]); the periodic encoder has
+    neither the raw input nor the Fourier expansion in search mode (embedder.py:93-95)."""
+    cos_t, sin_t, period = table
+    return (encode_search_positional(coords, freqs, res),
+            encode_periodic(coords, cos_t, sin_t, period, res, include_input=False))
+
+
+def forward_light(p, pos, per, depth=4, skips=(4,)):
+    """NPP_Net_light.forward with len(freq_scales) == 1 (models/networks.py:222-263): the scale MLP is
+    skipped, `pos` (x) joins after feature_linear1.  Same cache layout as `forward`."""
+    pos = np.asarray(pos, F32)
+    per = np.asarray(per, F32)
+    c = {"enc1": per, "pos": pos, "a": {}, "z": {}, "h": {}}
+    h = per
+    for i in range(depth):
+        name = f"periodic_linears.{i}"
+        c["a"][name] = h
+        z = _lin(p, name, h)
+        c["z"][name] = z
+        h = snake(z)
+        c["h"][name] = h
+        if i in skips:
+            h = np.concatenate([per, h], -1)                       # networks.py:234-235
+    c["a"]["feature_linear1"] = h
+    f1 = _lin(p, "feature_linear1", h)                             # networks.py:237
+    c["h"]["feature_linear1"] = f1
+    a = np.concatenate([f1, pos], -1)                              # networks.py:250
+    c["a"]["pos_linears.0"] = a
+    z = _lin(p, "pos_linears.0", a)
+    c["z"]["pos_linears.0"] = z
+    hp = snake(z)
+    c["h"]["pos_linears.0"] = hp
+    c["a"]["rgb_linear"] = hp
+    logits = _lin(p, "rgb_linear", hp)                             # networks.py:262
+    c["logits"] = logits
+    return logits, c
+
+
+def backward_light(p, c, g_logits, depth=4, skips=(4,)):
+    """Hand-derived backward of `forward_light` (reference: loss.backward(), NPP_proposal/search.py:135)."""
+    ch1 = c["enc1"].shape[1]
+    W = p["feature_linear1.weight"].shape[0]
+    grads, deltas = {}, {}
+
+    def lin_bwd(name, delta):
+        deltas[name] = delta
+        grads[name + ".weight"] = (delta.T @ c["a"][name]).astype(F32)
+        grads[name + ".bias"] = delta.sum(0, dtype=np.float64).astype(F32)
+        return (delta @ p[name + ".weight"]).astype(F32)
+
+    d_hp = lin_bwd("rgb_linear", np.asarray(g_logits, F32))
+    d_a = lin_bwd("pos_linears.0", (d_hp * snake_grad(c["z"]["pos_linears.0"])).astype(F32))
+    d_h = lin_bwd("feature_linear1", d_a[:, :W])                   # the positional columns need no gradient
+    for i in reversed(range(depth)):
+        name = f"periodic_linears.{i}"
+        if i in skips:
+            d_h = d_h[:, ch1:]
+        d_h = lin_bwd(name, (d_h * snake_grad(c["z"][name])).astype(F32))
+    return grads, deltas
+
+
+def train_step_light(p, m, v, step, pos, per, target, lr, depth=4, skips=(4,)):
+    """One search iteration with --loss_type l2 and no mask (NPP_proposal/search.py:112-136)."""
+    logits, c = forward_light(p, pos, per, depth, skips)
+    pred = sigmoid(logits)
+    loss = mse_l2(pred, target, None)
+    g = mse_l2_grad_logits(logits, target, None)
+    grads, _ = backward_light(p, c, g, depth, skips)
+    adam_step(p, grads, m, v, step, lr)
+    return loss, pred
+
+
+def init_params_light(rng, width=256, depth=4, skips=(4,), ch=20, ch_pos=42):
+    """nn.Linear default init for NPP_Net_light (models/networks.py:198-214, scale_dim == 0)."""
+    p = {}
+
+    def lin(name, out, inp):
+        b = 1.0 / np.sqrt(inp)
+        p[name + ".weight"] = rng.uniform(-b, b, (out, inp)).astype(F32)
+        p[name + ".bias"] = rng.uniform(-b, b, (out,)).astype(F32)
+
+    lin("periodic_linears.0", width, ch)
+    for i in range(1, depth):
+        lin(f"periodic_linears.{i}", width, width + ch if (i - 1) in skips else width)
+    lin("scale_linears.0", width, width)
+    lin("pos_linears.0", width // 2, ch_pos + width)
+    lin("feature_linear1", width, width)
+    lin("feature_linear2", width, width)
+    lin("alpha_linear", 1, width)
+    lin("rgb_linear", 3, width // 2)
+    return p

@@ -1,0 +1,131 @@
+"""Timing of search-stage fits (NPP_Net_light, 2048 rows/step; NPP_proposal/search.py:85-148):
+one fit alone, and 9 candidate fits (the reference ranks up to 9 candidates one after the other) interleaved on 9
+streams with one plan each.  Not a test; run on the GPU box: python tests/diag_search_fit.py"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import npp_b200  # noqa: E402,F401
+from npp_b200.plan import EncoderSpec, Plan, MODEL_LIGHT  # noqa: E402
+
+RES = (512, 512)
+N, ITERS = 2048, 300
+
+
+def make(seed, period):
+    rng = np.random.default_rng(seed)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(RES, [[83.0, 172.5]], [[period, 0.9 * period]], freqs, include_input=False)
+    plan = Plan(enc, depth=4, width=256, skip_layer=-1, max_rows=N, model=MODEL_LIGHT)
+    plan.reset_parameters(seed)
+    return plan
+
+
+def batches(k):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    return [(torch.stack([torch.randint(0, RES[0], (N,), device="cuda", generator=g),
+                          torch.randint(0, RES[1], (N,), device="cuda", generator=g)], 1).float().contiguous(),
+             torch.rand(N, 3, device="cuda", generator=g)) for _ in range(k)]
+
+
+def main():
+    data = batches(8)
+    plan = make(0, 42.7)
+    loss = torch.zeros((), device="cuda")
+    for i in range(20):
+        plan.train_step(*data[i % 8], None, 5e-4, loss)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(ITERS):
+        plan.train_step(*data[i % 8], None, 5e-4, loss)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / ITERS
+    print(f"one search fit: {ms * 1e3:.1f} us/step  {N / ms / 1e3:.2f} M samples/s  "
+          f"({ITERS} iterations = {ms * ITERS:.1f} ms; launches/step {plan.launch_count()})")
+    plan.profile(True)
+    for i in range(50):
+        plan.train_step(*data[i % 8], None, 5e-4, loss)
+    prof = plan.profile_read()
+    plan.profile(False)
+    print("  per class us/step:", {k: round(v[0] / 50 * 1e3, 1) for k, v in prof.items() if v[1]})
+
+    # 9 candidates: one plan and one stream each, iterations issued round-robin
+    K = 9
+    plans = [make(s, 30.0 + 3 * s) for s in range(K)]
+    streams = [torch.cuda.Stream() for _ in range(K)]
+    losses = [torch.zeros((), device="cuda") for _ in range(K)]
+    torch.cuda.synchronize()
+    for it in range(10):
+        for k in range(K):
+            with torch.cuda.stream(streams[k]):
+                plans[k].train_step(*data[(it + k) % 8], None, 5e-4, losses[k])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a.record()
+    for it in range(ITERS):
+        for k in range(K):
+            with torch.cuda.stream(streams[k]):
+                plans[k].train_step(*data[(it + k) % 8], None, 5e-4, losses[k])
+    for s in streams:
+        torch.cuda.current_stream().wait_stream(s)
+    b.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = a.elapsed_time(b)
+    print(f"{K} candidate fits on {K} streams: {ms:.1f} ms for {ITERS} iterations each (wall {wall:.1f} ms) = "
+          f"{ms / ITERS / K * 1e3:.1f} us per fit-step, {K * ITERS * N / ms / 1e3:.2f} M samples/s")
+
+    print("losses:", [round(l.item(), 5) for l in losses])
+
+    # the same layer stack in plain torch (eager fp32 and TF32) on this GPU: what the reference's NPP_Net_light costs
+    # per iteration of NPP_proposal/search.py:112-146 once its encodings are precomputed
+    import torch.nn as nn
+
+    class Light(nn.Module):
+        def __init__(self, W=256, D=4):
+            super().__init__()
+            self.trunk = nn.ModuleList([nn.Linear(20, W)] + [nn.Linear(W, W) for _ in range(D - 1)])
+            self.f1, self.pos, self.rgb = nn.Linear(W, W), nn.Linear(W + 42, W // 2), nn.Linear(W // 2, 3)
+
+        def forward(self, x, xp):
+            h = xp
+            for l in self.trunk:
+                h = l(h)
+                h = h + torch.sin(h) ** 2
+            h = self.pos(torch.cat([self.f1(h), x], -1))
+            return self.rgb(h + torch.sin(h) ** 2)
+
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        net = Light().cuda()
+        opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+        x, xp, y = torch.randn(N, 42, device="cuda"), torch.randn(N, 20, device="cuda"), torch.rand(N, 3, device="cuda")
+
+        def step():
+            pred = torch.sigmoid(net(x, xp))
+            opt.zero_grad()
+            loss = torch.mean((pred - y) ** 2)
+            loss.backward()
+            opt.step()
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(100):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 100
+        print(f"torch eager {'tf32' if tf32 else 'fp32'} (same layer stack, encodings precomputed): {ms * 1e3:.0f} us/step  "
+              f"{N / ms / 1e3:.2f} M samples/s")
+
+
+if __name__ == "__main__":
+    main()

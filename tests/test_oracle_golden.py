@@ -81,3 +81,41 @@ def test_forward_backward_adam(tag, topk):
 def test_lr_schedule():
     assert O.lr_schedule(1) == 5e-4 and O.lr_schedule(2) == 5e-4
     assert abs(O.lr_schedule(3) - 5e-4 * 0.1 ** (1 / 50000)) < 1e-12
+
+
+def test_search_mode_encoders_and_light_network():
+    """NPP_Net_light and the search-mode encoders (tests/golden/make_golden_light.py)."""
+    g = np.load(os.path.join(G, "golden_light.npz"))
+    res = tuple(g["res"])
+    c_, s_, p_ = O.encoder_tables(g["angles"], g["periods"], [1], [0, -1, 1, 0.5, -0.5], [0])
+    np.testing.assert_allclose(c_, g["cos_t"], atol=1e-7)
+    np.testing.assert_allclose(s_, g["sin_t"], atol=1e-7)
+    np.testing.assert_array_equal(p_, g["period"])
+    pos, per = O.encode_search(g["coords"], (g["cos_t"], g["sin_t"], g["period"]), g["freqs"], res)
+    assert pos.shape == g["pos"].shape == (48, 42) and per.shape == g["per"].shape == (48, 20)
+    np.testing.assert_allclose(per, g["per"], atol=2e-6)
+    np.testing.assert_allclose(pos, g["pos"], atol=5e-6)      # |f u| <= ~25: a few ulp of the argument
+
+    p = {k[5:]: g[k].copy() for k in g.files if k.startswith("init/")}
+    logits, c = O.forward_light(p, g["pos"], g["per"])
+    for k in [k for k in g.files if k.startswith("z/")]:
+        name = k[2:]
+        ours = logits if name == "rgb_linear" else c["z"].get(name, c["h"].get(name))
+        assert ours is not None, name
+        assert rel(ours, g[k]) < 2e-5, name
+    np.testing.assert_allclose(logits, g["logits"], atol=2e-6)
+    grads, _ = O.backward_light(p, c, O.mse_l2_grad_logits(logits, g["target"], None))
+    gkeys = [k[5:] for k in g.files if k.startswith("grad/")]
+    assert sorted(gkeys) == sorted(grads.keys())     # scale_linears / feature_linear2 / alpha_linear never train
+    for k in gkeys:
+        assert rel(grads[k], g["grad/" + k]) < 2e-5, k
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in p.items()}
+    losses = []
+    for it in range(1, 4):
+        l, _ = O.train_step_light(p, m, v, it, g["pos"], g["per"], g["target"], O.lr_schedule(it))
+        losses.append(l)
+    np.testing.assert_allclose(losses, g["losses"], rtol=2e-5)
+    for k in p:
+        assert np.abs(p[k] - g["final/" + k]).max() < 2e-4, k
+        assert rel(p[k], g["final/" + k]) < 5e-4, k
