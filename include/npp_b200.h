@@ -149,6 +149,17 @@ int npp_train_step(NppPlan* plan, const float* coords, const float* target, cons
                    int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
                    void* stream);
 
+/* A run of `iters` train steps without returning to the caller in between: the loop of
+ * NPP_proposal/search.py:110-146 (and of NPP_completion/train.py:150-263 when every batch is known up front).
+ * Step i (0-based) reads coords_all[i] ([iters, n, 2]), target_all[i] ([iters, n, 3]) and, if given, mask_all[i]
+ * ([iters, n, 1]); its loss goes to losses[i] (device, [iters]).  The learning rate follows the scripts' rewrite
+ * (search.py:139-144, train.py:258-263: applied AFTER optimizer.step() with the pre-increment global_step), i.e.
+ * Adam step k = first_step + i uses lrate * decay_rate ^ (max(k - 2, 0) / decay_steps).  The calling thread only
+ * enqueues kernels: several plans can be driven from several host threads onto several streams at once. */
+int npp_fit_run(NppPlan* plan, const float* coords_all, const float* target_all, const float* mask_all, int64_t n,
+                int64_t iters, float lrate, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                int64_t first_step, float* losses, void* stream);
+
 /* Optional input pipelining for npp_train_step (the data-loader analogue of NPP_completion/train.py:164-181, where
  * the reference gathers the next batch's rows of the encoding table): encodes `coords` of a FUTURE step into the
  * plan's second encoding buffer on an internal stream.  It waits for everything already enqueued on `stream`

@@ -69,6 +69,8 @@ SIGNATURES = {
     "npp_robust_adaptive_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
     "npp_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, _P, _P]),
+    "npp_fit_run": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                              C.c_float, C.c_float, C.c_int64, _P, _P]),
     "npp_set_keep_grads": (C.c_int, [_P, C.c_int]),
     "npp_last_launch_count": (C.c_int, [_P]),
     "npp_profile_enable": (C.c_int, [_P, C.c_int]),

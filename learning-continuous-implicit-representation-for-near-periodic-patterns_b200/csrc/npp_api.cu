@@ -1389,6 +1389,25 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   return 0;
 }
 
+int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, const float* mask_all, int64_t n,
+                int64_t iters, float lrate, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                int64_t first_step, float* losses, void* stream) {
+  if (!p || !coords_all || !target_all || !losses) return fail("npp_fit_run: null argument");
+  if (iters < 0 || first_step < 1) return fail("npp_fit_run: iters must be >= 0 and first_step >= 1");
+  if (!(decay_steps > 0.f) || !(decay_rate > 0.f)) return fail("npp_fit_run: decay_rate and decay_steps must be positive");
+  int launches = 0;
+  for (int64_t i = 0; i < iters; ++i) {
+    const int64_t k = first_step + i;
+    const double expo = (double)(k > 2 ? k - 2 : 0) / (double)decay_steps;
+    const float lr = (float)((double)lrate * std::pow((double)decay_rate, expo));
+    CKI(npp_train_step(p, coords_all + i * n * 2, target_all + i * n * 3, mask_all ? mask_all + i * n : nullptr, n, n, lr,
+                       beta1, beta2, eps, k, losses + i, stream));
+    launches += p->launches;
+  }
+  p->launches = launches;
+  return 0;
+}
+
 int npp_last_launch_count(const NppPlan* p) { return p ? p->launches : 0; }
 
 int npp_set_keep_grads(NppPlan* p, int on) {

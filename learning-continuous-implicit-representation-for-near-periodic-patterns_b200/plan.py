@@ -268,6 +268,31 @@ class Plan:
                                           n if n_norm is None else int(n_norm), lr, betas[0], betas[1], eps, step,
                                           loss_out.data_ptr(), nat.current_stream()))
 
+    def fit_run(self, coords_all: torch.Tensor, target_all: torch.Tensor, mask_all: Optional[torch.Tensor] = None, *,
+                lrate: float = 5e-4, lrate_decay: float = 500, decay_rate: float = 0.1, betas=(0.9, 0.999),
+                eps: float = 1e-8, losses: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> torch.Tensor:
+        """`iters` train steps in one call (npp_fit_run): coords_all [iters, n, 2], target_all [iters, n, 3], optional
+        mask_all [iters, n, 1], contiguous fp32 CUDA tensors.  The learning rate follows the reference loops' rewrite
+        (decay_steps = lrate_decay * 100, NPP_proposal/search.py:139-144).  Returns the per-step losses [iters]."""
+        iters, n = int(coords_all.shape[0]), int(coords_all.shape[1])
+        for t, last in ((coords_all, 2), (target_all, 3)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[:2] == (iters, n)
+                    and t.shape[2] == last):
+                raise ValueError("fit_run needs contiguous fp32 CUDA tensors [iters, n, 2] and [iters, n, 3]")
+        if mask_all is not None and not (mask_all.is_cuda and mask_all.dtype == torch.float32 and
+                                         mask_all.is_contiguous() and mask_all.numel() == iters * n):
+            raise ValueError("mask_all must be a contiguous fp32 CUDA tensor [iters, n, 1]")
+        if n > self.max_rows:
+            raise ValueError(f"{n} rows exceed the plan capacity max_rows={self.max_rows}")
+        if losses is None:
+            losses = torch.zeros(iters, device=self.device)
+        first = self.adam_steps + 1
+        nat.check(self.lib.npp_fit_run(self.handle, coords_all.data_ptr(), target_all.data_ptr(), nat.ptr(mask_all), n,
+                                       iters, lrate, decay_rate, float(lrate_decay) * 100.0, betas[0], betas[1], eps,
+                                       first, losses.data_ptr(), nat.current_stream() if stream is None else stream))
+        self.adam_steps += iters
+        return losses
+
     def prefetch_encode(self, coords: torch.Tensor):
         """Encode the coordinates of a FUTURE `train_step` on the plan's side stream, so that it overlaps with the
         step that is enqueued next (call this first, then that step).  `coords` must be the very tensor (same storage,

@@ -1,0 +1,68 @@
+"""Concurrent search-stage fits: the candidate loop of NPP_proposal/search.py:85-148 run side by side.
+
+The reference fits one fresh NPP_Net_light per candidate periodicity, one after the other, with the same seeds
+(search.py:91-92), i.e. every candidate sees the same sequence of pixel batches.  A fit at 2048 rows keeps only 16 of
+the 148 SMs busy and is bound by the latency of its dependent kernels, so the candidates are independent work that
+fits on the GPU at the same time: one plan, one CUDA stream and one host thread per candidate (the C ABI releases the
+GIL for the whole `npp_fit_run` call, so the threads enqueue kernels in parallel).  There is no data-path collective.
+
+Scoring the fitted candidates (LPIPS + contextual loss on the held-out region, search.py:150-196) stays with the
+caller; `Plan.forward` / `NPP_Net_light.forward` under ``torch.no_grad()`` renders the pixels it needs.
+"""
+from __future__ import annotations
+
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+
+from .plan import Plan
+
+
+def gather_batches(image: torch.Tensor, train_coords: torch.Tensor, indices: torch.Tensor):
+    """Batches of a whole fit: image [H, W, 3] fp32 CUDA, train_coords [P, 2] (row, col), indices [iters, n] int64 into
+    train_coords (the `select_inds` of search.py:116, drawn by the caller -- host RNG for parity with the script, any
+    device RNG otherwise).  Returns (coords_all [iters, n, 2] fp32, target_all [iters, n, 3] fp32)."""
+    tc = train_coords.to(image.device).long()
+    sel = tc[indices.to(image.device)]                                   # [iters, n, 2]
+    target = image[sel[..., 0], sel[..., 1], :].contiguous()             # search.py:118
+    return sel.float().contiguous(), target.float()
+
+
+def run_fits(plans: Sequence[Plan], coords_all: torch.Tensor, target_all: torch.Tensor, *, lrate: float = 5e-4,
+             lrate_decay: float = 500, streams: Optional[Sequence[torch.cuda.Stream]] = None,
+             threads: bool = True) -> torch.Tensor:
+    """Fit every plan on the same batches (or on its own, if coords_all / target_all are lists), concurrently.
+    Returns the losses [len(plans), iters]; the call returns once the current stream waits for every fit."""
+    k = len(plans)
+    per_plan = isinstance(coords_all, (list, tuple))
+    iters = int((coords_all[0] if per_plan else coords_all).shape[0])
+    dev = plans[0].device
+    losses = torch.zeros(k, iters, device=dev)
+    streams = list(streams) if streams is not None else [torch.cuda.Stream(device=dev) for _ in range(k)]
+    cur = torch.cuda.current_stream(dev)
+    errors: List[BaseException] = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(dev)
+            streams[i].wait_stream(cur)
+            plans[i].fit_run(coords_all[i] if per_plan else coords_all, target_all[i] if per_plan else target_all,
+                             lrate=lrate, lrate_decay=lrate_decay, losses=losses[i], stream=streams[i].cuda_stream)
+        except BaseException as e:   # surfaced in the calling thread below
+            errors.append(e)
+
+    if threads and k > 1:
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(k)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    else:
+        for i in range(k):
+            work(i)
+    if errors:
+        raise errors[0]
+    for s in streams:
+        cur.wait_stream(s)
+    return losses

@@ -83,6 +83,33 @@ def main():
 
     print("losses:", [round(l.item(), 5) for l in losses])
 
+    # the same nine fits through search_fits.run_fits: one npp_fit_run call per candidate, one host thread each
+    from npp_b200.search_fits import run_fits
+    coords_all = torch.stack([d[0] for d in data] * ((ITERS + 7) // 8))[:ITERS].contiguous()
+    target_all = torch.stack([d[1] for d in data] * ((ITERS + 7) // 8))[:ITERS].contiguous()
+    for threads in (False, True):
+        plans2 = [make(s, 30.0 + 3 * s) for s in range(K)]
+        run_fits(plans2, coords_all[:10], target_all[:10], streams=streams, threads=threads)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.record()
+        out = run_fits(plans2, coords_all, target_all, streams=streams, threads=threads)
+        b.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = a.elapsed_time(b)
+        print(f"run_fits, {K} candidates x {ITERS} iterations, host threads={threads}: {ms:.1f} ms (wall {wall:.1f} ms) = "
+              f"{ms / ITERS / K * 1e3:.1f} us per fit-step, {K * ITERS * N / ms / 1e3:.2f} M samples/s; "
+              f"final losses {[round(v, 4) for v in out[:, -1].tolist()][:3]}...")
+    one = make(0, 42.7)
+    one.fit_run(coords_all[:10], target_all[:10])
+    torch.cuda.synchronize()
+    a.record()
+    one.fit_run(coords_all, target_all)
+    b.record()
+    torch.cuda.synchronize()
+    print(f"fit_run, one candidate: {a.elapsed_time(b):.1f} ms for {ITERS} iterations = {a.elapsed_time(b) / ITERS * 1e3:.1f} us/step")
+
     # the same layer stack in plain torch (eager fp32 and TF32) on this GPU: what the reference's NPP_Net_light costs
     # per iteration of NPP_proposal/search.py:112-146 once its encodings are precomputed
     import torch.nn as nn

@@ -244,3 +244,69 @@ def test_create_npp_net_search_mode_runs_the_search_loop_body(monkeypatch):
     with torch.no_grad():      # validation render of search.py:152-170, 20000-row chunks
         out = render(i_train_emb[:20000], i_train_emb_periodic[:20000], args, **kw_train)
     assert out.shape == (20000, 3) and torch.isfinite(out).all()
+
+
+def _fit_data(iters, n, seed=3):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    coords = torch.stack([torch.randint(0, RES[0], (iters, n), device="cuda", generator=g),
+                          torch.randint(0, RES[1], (iters, n), device="cuda", generator=g)], -1).float().contiguous()
+    target = (0.5 + 0.4 * torch.sin(coords[..., :1] * 0.23 + coords[..., 1:] * 0.11 +
+                                    torch.arange(3, device="cuda") * 2.0)).contiguous()
+    return coords, target
+
+
+def test_fit_run_equals_stepwise_train_steps():
+    """npp_fit_run is the loop of train steps with the scripts' learning-rate rewrite (search.py:139-144)."""
+    iters, n = 12, 2048
+    coords, target = _fit_data(iters, n)
+    a, params, *_ = make(n, seed=11)
+    b, _, *_ = make(n, seed=11)
+    loss = torch.zeros((), device="cuda")
+    step_losses = []
+    for i in range(iters):
+        a.train_step(coords[i], target[i], None, O.lr_schedule(i + 1, lrate=5e-4, lrate_decay=0.02), loss)
+        step_losses.append(loss.item())
+    run_losses = b.fit_run(coords, target, lrate=5e-4, lrate_decay=0.02)     # decays 10x every 2 steps: LR rule visible
+    assert b.launch_count() == 7 * iters and b.adam_steps == iters
+    np.testing.assert_allclose(run_losses.cpu().numpy(), step_losses, rtol=1e-4)
+    sa, sb = a.state(), b.state()
+    for k in sa:
+        assert (sa[k] - sb[k]).abs().max().item() < 2e-4, k
+    assert step_losses[-1] < step_losses[0]
+
+
+def test_concurrent_candidate_fits_match_fits_run_alone():
+    """search_fits.run_fits: one plan / stream / host thread per candidate periodicity, same batches for all
+    (search.py:91-92 re-seeds per candidate), against the same fits run one after the other."""
+    from npp_b200.search_fits import run_fits, gather_batches
+    from npp_b200.plan import EncoderSpec, Plan, MODEL_LIGHT
+    iters, n, K = 60, 2048, 5
+    rng = np.random.default_rng(0)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    H, W_ = RES
+    yy, xx = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W_, device="cuda"), indexing="ij")
+    image = torch.stack([0.5 + 0.4 * torch.sin(2 * np.pi * xx / 27.2), 0.5 + 0.4 * torch.cos(2 * np.pi * yy / 24.9),
+                         0.5 + 0.3 * torch.sin(2 * np.pi * (xx + yy) / 27.2)], -1).float()
+    train_coords = torch.stack([yy.reshape(-1), xx.reshape(-1)], 1)
+    idx = torch.from_numpy(np.stack([rng.choice(H * W_, n, replace=False) for _ in range(iters)]))
+    coords_all, target_all = gather_batches(image, train_coords, idx)
+    assert coords_all.shape == (iters, n, 2) and target_all.shape == (iters, n, 3)
+    assert torch.equal(target_all[3, 5], image[int(coords_all[3, 5, 0]), int(coords_all[3, 5, 1])])
+
+    def plans():
+        out = []
+        for k in range(K):
+            enc = EncoderSpec.from_proposals(RES, [ANGLES], [[27.2 + 4 * k, 24.9 - 3 * k]], freqs, include_input=False)
+            p = Plan(enc, depth=4, width=256, skip_layer=-1, max_rows=n, model=MODEL_LIGHT)
+            p.reset_parameters(seed=0)       # same initial weights for every candidate, like torch.manual_seed(0)
+            out.append(p)
+        return out
+
+    together = run_fits(plans(), coords_all, target_all).cpu().numpy()
+    alone = np.stack([p.fit_run(coords_all, target_all).cpu().numpy() for p in plans()])
+    assert together.shape == (K, iters)
+    np.testing.assert_allclose(together, alone, rtol=2e-3)
+    # the true periodicity (candidate 0) is the one that fits best -- what the search ranks by
+    final = together[:, -10:].mean(1)
+    assert final.argmin() == 0, final
+    assert (together[:, -1] < together[:, 0]).all()
