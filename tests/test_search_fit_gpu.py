@@ -310,3 +310,21 @@ def test_concurrent_candidate_fits_match_fits_run_alone():
     final = together[:, -10:].mean(1)
     assert final.argmin() == 0, final
     assert (together[:, -1] < together[:, 0]).all()
+
+
+def test_fit_run_as_one_cuda_graph(monkeypatch):
+    """NPP_FIT_GRAPH=1: the same run captured into one CUDA graph (opt-in, see npp_fit_run) gives the same fit."""
+    iters, n = 10, 1024
+    coords, target = _fit_data(iters, n, seed=9)
+    a, *_ = make(n, seed=21)
+    b, *_ = make(n, seed=21)
+    direct = a.fit_run(coords, target).cpu().numpy()
+    monkeypatch.setenv("NPP_FIT_GRAPH", "1")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        graphed = b.fit_run(coords, target)
+        again = b.fit_run(coords, target)          # second run: the first graph is retired, Adam steps continue
+    torch.cuda.current_stream().wait_stream(s)
+    np.testing.assert_allclose(graphed.cpu().numpy(), direct, rtol=1e-4)
+    assert b.adam_steps == 2 * iters and again[-1].item() < graphed[0].item()
