@@ -163,6 +163,10 @@ struct NppPlan {
   int cluster = 2;   // 2: the chain kernel runs on CTA pairs with cta_group::2 UMMAs; 1: single-CTA UMMAs
   int wg_cluster = 2;  // same choice for the weight-gradient kernel (256 x 256 tile per CTA pair)
 
+  int* d_step = nullptr;                // step index read by the kernels of npp_fit_run's re-launched step graph
+  AdamScalars* d_ad_table = nullptr;    // Adam scalars per step of the current npp_fit_run
+  long long ad_table_cap = 0;
+  bool step_mode = false;               // launches take their batch / scalars through d_step
   cudaEvent_t tables_evt = nullptr;     // recorded after the last kernels that read the device op tables
   bool capturing = false;               // npp_fit_run is recording into side_stream
   cudaGraphExec_t fit_exec = nullptr;   // the last npp_fit_run, captured as one graph (kept until the next run / destroy)
@@ -440,6 +444,8 @@ static int alloc_plan_memory(NppPlan* p) {
   CK(cudaMalloc(&p->acc, p->acc_floats * sizeof(float)));
   CK(cudaMemset(p->acc, 0, p->acc_floats * sizeof(float)));
   CK(cudaMalloc(&p->g_buf, (size_t)R * 3 * sizeof(float)));
+  CK(cudaMalloc(&p->d_step, sizeof(int)));
+  CK(cudaMemset(p->d_step, 0, sizeof(int)));
   CK(cudaMalloc(&p->d_barrier, 2 * sizeof(unsigned int)));
   CK(cudaMemset(p->d_barrier, 0, 2 * sizeof(unsigned int)));
   {
@@ -889,7 +895,8 @@ static int launch_encode(NppPlan* p, const float* coords, long long n, int set, 
     unsigned blocks = (unsigned)std::min<long long>((items + 255) / 256, (long long)p->num_sms * 8);
     npp_encode_search_kernel<<<blocks, 256, 0, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, p->bufs[bp].ptr,
                                                      p->Ap, zero_loss ? p->acc : nullptr,
-                                                     zero_loss ? (int)p->acc_floats : 0, zero_loss);
+                                                     zero_loss ? (int)p->acc_floats : 0, zero_loss,
+                                                     p->step_mode ? p->d_step : nullptr);
     CK(cudaGetLastError());
     ++p->launches;
     return 0;
@@ -1120,22 +1127,25 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
 
 int npp_plan_destroy(NppPlan* p) {
   if (!p) return 0;
+  if (p->fit_exec) {
+    cudaStreamSynchronize(p->fit_stream);
+    cudaGraphExecDestroy(p->fit_exec);
+    p->fit_exec = nullptr;
+  }
   cudaFree(p->workspace);
   cudaFree(p->shadow_mem);
   cudaFree(p->partial);
   cudaFree(p->acc);
   cudaFree(p->g_buf);
   cudaFree(p->d_barrier);
+  cudaFree(p->d_step);
+  cudaFree(p->d_ad_table);
   cudaFree(p->logits_buf);
   cudaFree(p->d_fin);
   cudaFree(p->d_shadow);
   cudaFree(p->d_update);
   cudaFree(p->d_fwd_ops);
   cudaFree(p->d_fwd_ops_alt);
-  if (p->fit_exec) {
-    cudaStreamSynchronize(p->fit_stream);
-    cudaGraphExecDestroy(p->fit_exec);
-  }
   if (p->side_stream) cudaStreamDestroy(p->side_stream);
   if (p->pref_fork) cudaEventDestroy(p->pref_fork);
   if (p->tables_evt) cudaEventDestroy(p->tables_evt);
@@ -1372,7 +1382,8 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     npp_head_loss_kernel<<<blocks, 256, 0, st>>>(p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)n,
                                                  p->params + p->rgb_w_off, p->params + p->rgb_b_off, target, mask,
                                                  inv_count, p->logits_buf, p->g_buf, loss,
-                                                 reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
+                                                 reinterpret_cast<unsigned int*>(p->acc + p->amax_off),
+                                                 p->step_mode ? p->d_step : nullptr);
     CK(cudaGetLastError());
     ++p->launches;
   }
@@ -1395,7 +1406,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     npp_fused_update_kernel<S_><<<blocks, 256, 0, st>>>(                                                             \
         p->update_table, p->partial, p->slab_stride, p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,    \
         p->head_width, reinterpret_cast<unsigned int*>(p->acc + p->amax_off), p->params,                             \
-        p->keep_grads ? p->grads : nullptr, p->m, p->v, ad);                                                         \
+        p->keep_grads ? p->grads : nullptr, p->m, p->v, ad, p->step_mode ? p->d_ad_table : nullptr, p->d_step);      \
     break;
     switch (p->wg_params.n_splits) {
       NPP_UPDATE_CASE(1) NPP_UPDATE_CASE(2) NPP_UPDATE_CASE(3) NPP_UPDATE_CASE(4) NPP_UPDATE_CASE(5) NPP_UPDATE_CASE(6)
@@ -1417,28 +1428,25 @@ int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, co
   if (iters < 0 || first_step < 1) return fail("npp_fit_run: iters must be >= 0 and first_step >= 1");
   if (!(decay_steps > 0.f) || !(decay_rate > 0.f)) return fail("npp_fit_run: decay_rate and decay_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  auto lr_of = [&](int64_t k) {   // Adam step k (1-based) of the scripts' loop, see the header
+    const double expo = (double)(k > 2 ? k - 2 : 0) / (double)decay_steps;
+    return (float)((double)lrate * std::pow((double)decay_rate, expo));
+  };
+  // NPP_FIT_GRAPH: 0 = plain launches (default), 1 = the whole run captured into one graph, 2 = one step captured and
+  // re-launched `iters` times (per-step scalars through device memory).  Measured on B200, NPP_Net_light, 300
+  // iterations of 2048 rows (profiles/r01/search_fit_timing.txt): one fit 32.9 / 39.6 / 29.7 ms in modes 0 / 1 / 2,
+  // but nine fits from nine host threads 95 / 140 / 131 ms: graph launches from different streams did not overlap the
+  // way plain launches do, and a one-shot 2100-node graph costs ~7 ms to build.  Hence plain launches by default.
+  const char* genv = getenv("NPP_FIT_GRAPH");
+  int mode = genv ? atoi(genv) : 0;
+  if (p->profiling || iters < 4 || p->cfg.model != NPP_MODEL_LIGHT) mode = 0;   // (the cooperative head cannot be captured)
   int launches = 0;
-  auto enqueue = [&](cudaStream_t into) -> int {
+  if (mode == 0) {
     for (int64_t i = 0; i < iters; ++i) {
-      const int64_t k = first_step + i;
-      const double expo = (double)(k > 2 ? k - 2 : 0) / (double)decay_steps;
-      const float lr = (float)((double)lrate * std::pow((double)decay_rate, expo));
       CKI(npp_train_step(p, coords_all + i * n * 2, target_all + i * n * 3, mask_all ? mask_all + i * n : nullptr, n, n,
-                         lr, beta1, beta2, eps, k, losses + i, into));
+                         lr_of(first_step + i), beta1, beta2, eps, first_step + i, losses + i, st));
       launches += p->launches;
     }
-    return 0;
-  };
-  // NPP_FIT_GRAPH=1: every launch parameter of the run is known now (batch pointers, learning rates, Adam bias
-  // corrections), so the whole run can be captured into one CUDA graph and launched once.  Measured on B200 it does
-  // not pay for a graph that is used once: capture + instantiation of 2100 kernel nodes costs ~7 ms per fit (39.6 ms
-  // against 32.9 ms for one 300-iteration fit, 140 ms against 95 ms for nine fits from nine threads), so it is opt-in.
-  // The capture records into the plan's own non-blocking stream (nothing executes there): a capture on the caller's
-  // stream would be invalidated by any activity on the legacy default stream, which blocking streams synchronise with.
-  const char* genv = getenv("NPP_FIT_GRAPH");
-  const bool graph = iters >= 4 && !p->profiling && genv && atoi(genv) == 1 && p->cfg.model == NPP_MODEL_LIGHT;
-  if (!graph) {
-    CKI(enqueue(st));
     p->launches = launches;
     return 0;
   }
@@ -1450,11 +1458,54 @@ int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, co
     CK(cudaGraphExecDestroy(p->fit_exec));
     p->fit_exec = nullptr;
   }
+  // The capture records into the plan's own non-blocking stream (nothing executes there): a capture on the caller's
+  // stream would be invalidated by any activity on the legacy default stream, which blocking streams synchronise with.
   p->pref[0].valid = p->pref[1].valid = false;   // a pending prefetch lives on the capture stream's real timeline
   CK(cudaStreamSynchronize(p->side_stream));
+  if (mode == 2) {
+    // Per-step scalars go through device memory so that ONE captured step can be launched `iters` times: the kernels
+    // read the batch index from d_step (advanced by the graph's last node) and Adam's scalars from a table.
+    if (p->ad_table_cap < iters) {
+      cudaFree(p->d_ad_table);
+      p->d_ad_table = nullptr;
+      CK(cudaMalloc(&p->d_ad_table, (size_t)iters * sizeof(AdamScalars)));
+      p->ad_table_cap = iters;
+    }
+    std::vector<AdamScalars> tab((size_t)iters);
+    for (int64_t i = 0; i < iters; ++i) {
+      const int64_t k = first_step + i;
+      const double bc1 = 1.0 - std::pow((double)beta1, (double)k);
+      const double bc2 = 1.0 - std::pow((double)beta2, (double)k);
+      tab[i].beta1 = beta1;
+      tab[i].beta2 = beta2;
+      tab[i].step_size = (float)((double)lr_of(k) / bc1);
+      tab[i].inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+      tab[i].eps = eps;
+    }
+    // pageable source: the call returns once the table sits in the driver's staging buffer
+    CK(cudaMemcpyAsync(p->d_ad_table, tab.data(), tab.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
+  }
   CK(cudaStreamBeginCapture(p->side_stream, cudaStreamCaptureModeThreadLocal));
   p->capturing = true;
-  const int rc = enqueue(p->side_stream);
+  int rc = 0;
+  if (mode == 2) {
+    p->step_mode = true;
+    rc = npp_train_step(p, coords_all, target_all, mask_all, n, n, lrate, beta1, beta2, eps, first_step, losses,
+                        p->side_stream);
+    if (rc == 0) {
+      npp_step_advance_kernel<<<1, 1, 0, p->side_stream>>>(p->d_step);
+      ++p->launches;
+    }
+    launches = p->launches * (int)iters;
+    p->step_mode = false;
+  } else {
+    for (int64_t i = 0; i < iters && rc == 0; ++i) {
+      rc = npp_train_step(p, coords_all + i * n * 2, target_all + i * n * 3, mask_all ? mask_all + i * n : nullptr, n, n,
+                          lr_of(first_step + i), beta1, beta2, eps, first_step + i, losses + i, p->side_stream);
+      launches += p->launches;
+    }
+  }
   p->capturing = false;
   cudaGraph_t g = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(p->side_stream, &g);
@@ -1463,14 +1514,15 @@ int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, co
     return rc;
   }
   if (ce != cudaSuccess) return fail(std::string("npp_fit_run: stream capture failed: ") + cudaGetErrorString(ce));
-  cudaError_t ie = cudaGraphInstantiate(&p->fit_exec, g, 0ULL);
+  const cudaError_t ie = cudaGraphInstantiate(&p->fit_exec, g, 0ULL);
   cudaGraphDestroy(g);
   if (ie != cudaSuccess) {
     p->fit_exec = nullptr;
     return fail(std::string("npp_fit_run: cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
   }
   p->fit_stream = st;
-  CK(cudaGraphLaunch(p->fit_exec, st));
+  const int64_t graph_launches = mode == 2 ? iters : 1;
+  for (int64_t i = 0; i < graph_launches; ++i) CK(cudaGraphLaunch(p->fit_exec, st));
   CKI(mark_busy(p, st));
   p->launches = launches;
   return 0;

@@ -282,7 +282,14 @@ __global__ void __launch_bounds__(256) npp_encode_search_kernel(const float* __r
                                                                 __half* __restrict__ enc1, int ld1,
                                                                 __half* __restrict__ pos, int ldp,
                                                                 float* __restrict__ zero_a, int zero_a_n,
-                                                                float* __restrict__ zero_b) {
+                                                                float* __restrict__ zero_b,
+                                                                const int* __restrict__ step) {
+  // step != nullptr (npp_fit_run's re-launched step graph): batch *step of a [iters, n, 2] array, loss slot *step
+  if (step != nullptr) {
+    const int sidx = *step;
+    coords += (size_t)sidx * n * 2;
+    if (zero_b != nullptr) zero_b += sidx;
+  }
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < zero_a_n; i += blockDim.x) zero_a[i] = 0.f;
     if (zero_b != nullptr && threadIdx.x == 0) *zero_b = 0.f;
@@ -535,9 +542,19 @@ __global__ void __launch_bounds__(256) npp_head_loss_kernel(const __half* __rest
                                                             const float* __restrict__ target,
                                                             const float* __restrict__ mask, float inv_count,
                                                             float* __restrict__ logits, float* __restrict__ g,
-                                                            float* __restrict__ loss, unsigned int* __restrict__ amax_bits) {
+                                                            float* __restrict__ loss, unsigned int* __restrict__ amax_bits,
+                                                            const int* __restrict__ step) {
+  if (step != nullptr) {   // re-launched step graph: batch *step of [iters, n, 3] targets / [iters, n] masks / [iters] losses
+    const int sidx = *step;
+    target += (size_t)sidx * n * 3;
+    if (mask != nullptr) mask += (size_t)sidx * n;
+    loss += sidx;
+  }
   npp_head_loss_part(hp, ld, width, n, w, b, target, mask, inv_count, logits, g, loss, amax_bits);
 }
+
+// Last node of the re-launched step graph.
+__global__ void npp_step_advance_kernel(int* step) { *step += 1; }
 
 // max |g| of an externally supplied gradient (autograd path).
 __global__ void __launch_bounds__(256) npp_amax_kernel(const float* __restrict__ g, int total,
@@ -1100,8 +1117,12 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
                                                                const unsigned int* __restrict__ amax_bits,
                                                                float* __restrict__ params, float* __restrict__ grads,
                                                                float* __restrict__ m, float* __restrict__ v,
-                                                               AdamScalars ad) {
+                                                               AdamScalars ad_arg,
+                                                               const AdamScalars* __restrict__ ad_table,
+                                                               const int* __restrict__ step) {
   __shared__ float tile[32][129];
+  // re-launched step graph: the scalars of Adam step *step come from a table filled by npp_fit_run
+  const AdamScalars ad = ad_table != nullptr ? ad_table[*step] : ad_arg;
   const int total_tiles = tab.tile_begin[tab.n_layers];
   if ((int)blockIdx.x >= total_tiles) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
     const int total = 3 * head_width + 3;

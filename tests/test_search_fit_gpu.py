@@ -312,14 +312,18 @@ def test_concurrent_candidate_fits_match_fits_run_alone():
     assert (together[:, -1] < together[:, 0]).all()
 
 
-def test_fit_run_as_one_cuda_graph(monkeypatch):
-    """NPP_FIT_GRAPH=1: the same run captured into one CUDA graph (opt-in, see npp_fit_run) gives the same fit."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fit_run_graph_modes_equal_plain_launches(monkeypatch, mode):
+    """NPP_FIT_GRAPH: 1 = the whole run as one CUDA graph, 2 = one captured step re-launched with its per-step scalars
+    in device memory, 0 = plain launches (default).  Same fit in every mode."""
     iters, n = 10, 1024
     coords, target = _fit_data(iters, n, seed=9)
     a, *_ = make(n, seed=21)
     b, *_ = make(n, seed=21)
+    monkeypatch.setenv("NPP_FIT_GRAPH", "0")
     direct = a.fit_run(coords, target).cpu().numpy()
-    monkeypatch.setenv("NPP_FIT_GRAPH", "1")
+    assert a.launch_count() == 7 * iters
+    monkeypatch.setenv("NPP_FIT_GRAPH", mode)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
