@@ -37,6 +37,9 @@ enum { NPP_MODEL_TOPK = 0, /* models/networks.py:8-95   NPP_Net      (p_topk > 1
                               expansion (embedder.py:93-95,140-148; 4*n_aug columns) and the 2-D Embedder on
                               normalised coordinates (embedder.py:51-56,76-80; 2 + 4*n_freq columns). */ };
 
+enum { NPP_ACT_SNAKE = 0, /* SnakeActivation, models/activations.py:29-35 */
+       NPP_ACT_RELU = 1 };
+
 typedef struct NppConfig {
   int32_t model;          /* NPP_MODEL_* */
   int32_t topk;           /* number of periodicity proposals K (create_npp_net, models/helpers.py:108-116) */
@@ -49,7 +52,8 @@ typedef struct NppConfig {
   int32_t include_input;  /* 1 outside search mode (embedder.py:105-109); must be 0 for NPP_MODEL_LIGHT */
   int32_t res_h, res_w;   /* image resolution res=(H,W) (NPP_completion/train.py:64) */
   int32_t wgrad_splits;   /* split-K factor of the weight-gradient GEMM, 0 = auto */
-  int32_t reserved;
+  int32_t activation;     /* NPP_ACT_SNAKE (activation == 'snake', the default of options/arg_config.py:29) or
+                             NPP_ACT_RELU (any other value: F.relu, models/networks.py:51-54,66-69) */
   int64_t max_rows;       /* workspace capacity in coordinate rows per step */
   const float* cos_t;     /* host [topk][2][n_aug]  cos(deg2rad(angle+offset))   embedder.py:123-124 */
   const float* sin_t;     /* host [topk][2][n_aug]  sin(...)                                         */

@@ -30,7 +30,7 @@ class NppConfig(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("topk", C.c_int32), ("depth", C.c_int32), ("width", C.c_int32),
         ("skip_layer", C.c_int32), ("n_aug", C.c_int32), ("n_freq", C.c_int32), ("include_input", C.c_int32),
-        ("res_h", C.c_int32), ("res_w", C.c_int32), ("wgrad_splits", C.c_int32), ("reserved", C.c_int32),
+        ("res_h", C.c_int32), ("res_w", C.c_int32), ("wgrad_splits", C.c_int32), ("activation", C.c_int32),
         ("max_rows", C.c_int64),
         ("cos_t", C.POINTER(C.c_float)), ("sin_t", C.POINTER(C.c_float)),
         ("period", C.POINTER(C.c_float)), ("freq", C.POINTER(C.c_float)),

@@ -121,6 +121,7 @@ struct ChainParams {
   float* zero_a;        // optional: accumulators (and *zero_b) that CTA 0 clears before the chain starts (fused train step
   int zero_n;           //   whose encoding was prefetched: the encode kernel, which normally does this, did not run)
   float* zero_b;
+  int relu;             // host side only: selects the npp_gemm_kmajor<CLUSTER, true> instantiation
 };
 
 struct WgUnit {
@@ -291,7 +292,10 @@ struct EpiArgs {
   bool leader;      // this CTA owns the UMMA-side barriers (always true without clusters)
 };
 
-template <int EPI>
+// RELU: EPI_SNAKE ops apply F.relu instead (activation != 'snake', models/networks.py:51-54,66-69).  A template
+// parameter of the kernel, not a run-time flag: a warp-uniform branch inside the snake epilogue made ptxas spill
+// (200 B of stores per thread) and cost the snake path 9 % of its forward time.
+template <int EPI, bool RELU>
 __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiArgs ea, const GemmSmem& s,
                                               uint32_t tmem_acc, int m0,
                                               int n0, int M, int warp, int lane, uint32_t& ld_phase,
@@ -371,7 +375,14 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
         for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
       uint32_t hd[16], dd[16];
-      if (EPI == EPI_SNAKE) {
+      if (EPI == EPI_SNAKE && RELU) {
+        // F.relu(h) (networks.py:66-67): out0 = max(z, 0), out1 = d/dz = [z > 0] (torch's relu backward)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          hd[i >> 1] = pack_h2(fmaxf(v[i], 0.f), fmaxf(v[i + 1], 0.f));
+          dd[i >> 1] = pack_h2(v[i] > 0.f ? 1.f : 0.f, v[i + 1] > 0.f ? 1.f : 0.f);
+        }
+      } else if (EPI == EPI_SNAKE) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float h2[2], d2[2];
@@ -506,7 +517,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
 //   row stripe 2p + r, keeps its own A tile and HALF of every weight tile in its shared memory, and the leader
 //   (rank 0) issues the MMAs for both.  Per SM that halves the B bytes written by TMA and read by the tensor core,
 //   which is what lifts the shared-memory-port ceiling of the single-CTA SS-mode mainloop.
-template <int CLUSTER>
+template <int CLUSTER, bool RELU = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_constant__ ChainParams cp) {
   constexpr int NST = CLUSTER == 1 ? STAGES : PAIR_STAGES;
   constexpr int B_BYTES = B_STAGE_BYTES / CLUSTER;       // this CTA's share of a weight tile
@@ -781,19 +792,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                               (final_group && oi == cp.n_ops - 1 && sl == gi - 1 && last_of_stripe_op);
             switch (epi) {
               case EPI_LINEAR:
-                epilogue_tile<EPI_LINEAR>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_LINEAR, false>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                           last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               case EPI_SNAKE:
-                epilogue_tile<EPI_SNAKE>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_SNAKE, RELU>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                          last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               case EPI_DGRAD_MUL:
-                epilogue_tile<EPI_DGRAD_MUL>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
+                epilogue_tile<EPI_DGRAD_MUL, false>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
                                              seq, last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
               default:
-                epilogue_tile<EPI_DGRAD>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
+                epilogue_tile<EPI_DGRAD, false>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                          last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
             }

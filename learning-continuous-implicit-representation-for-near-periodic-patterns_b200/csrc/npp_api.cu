@@ -759,6 +759,8 @@ static int set_smem_attrs() {
   if (g_smem_attr_done) return 0;
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_kmajor<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_PAIR_SMEM_BYTES));
   g_smem_attr_done = 1;
@@ -769,7 +771,7 @@ static int set_smem_attrs() {
 // cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
 static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, int n_ops, int M, int num_sms,
                         cudaStream_t st, int subs_per_stripe, int cluster = 1, float* zero_a = nullptr, int zero_n = 0,
-                        float* zero_b = nullptr) {
+                        float* zero_b = nullptr, int relu = 0) {
   CKI(set_smem_attrs());
   if (n_ops > MAX_CHAIN_OPS) return fail("chain longer than MAX_CHAIN_OPS");
   ChainParams cp;
@@ -793,6 +795,7 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   cp.zero_a = zero_a;
   cp.zero_n = zero_n;
   cp.zero_b = zero_b;
+  cp.relu = relu;
   cp.n_ops = n_ops;
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
@@ -802,7 +805,8 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   cp.dbg_warp = getenv("NPP_DEBUG_STAMP_WARP") ? atoi(getenv("NPP_DEBUG_STAMP_WARP")) : 2;
   int grid = cp.tiles_m < num_sms ? cp.tiles_m : num_sms;
   if (cluster == 1) {
-    npp_gemm_kmajor<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
+    if (relu) npp_gemm_kmajor<1, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
+    else npp_gemm_kmajor<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(cp);
     CK(cudaGetLastError());
     return 0;
   }
@@ -852,7 +856,8 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
     cudaFree(d_dbg);
     return 0;
   }
-  CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
+  if (relu) CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2, true>, cp));
+  else CK(cudaLaunchKernelEx(&cfg, npp_gemm_kmajor<2>, cp));
   return 0;
 }
 
@@ -968,7 +973,7 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     CKI(launch_chain(alt ? p->d_fwd_ops_alt : p->d_fwd_ops, alt ? p->fwd_params_alt.data() : p->fwd_params.data(),
                      (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs, p->cluster,
                      prefetched && zero_loss ? p->acc : nullptr, prefetched && zero_loss ? (int)p->acc_floats : 0,
-                     prefetched ? zero_loss : nullptr));
+                     prefetched ? zero_loss : nullptr, p->cfg.activation));
     ++p->launches;
   }
   CKI(mark_busy(p, st));
@@ -1082,6 +1087,7 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   } else if (cfg->width != 512) {
     return fail("this build supports netwidth == 512 only (the reference default)");
   }
+  if (cfg->activation != NPP_ACT_SNAKE && cfg->activation != NPP_ACT_RELU) return fail("unknown activation");
   if (cfg->depth < 2 || cfg->depth > 16) return fail("netdepth must be in [2,16]");
   if (cfg->skip_layer >= cfg->depth - 1) return fail("skip layer must be < depth-1");
   if (cfg->n_aug < 1 || cfg->n_aug > MAX_AUG) return fail("n_aug out of range");

@@ -60,9 +60,6 @@ class _ArenaLinear(nn.Module):
 
 class _FusedNet(nn.Module):
     def _build(self, topk_model, D, W, skips, activation, output_ch, reference_order, light=False):
-        if activation != 'snake':
-            raise NotImplementedError("the B200 path implements activation='snake' (the reference default, "
-                                      "options/arg_config.py:29); relu is not built")
         if output_ch != 3 or len(skips) != 1:
             raise NotImplementedError("output_ch=3 and a single skip connection are required")
         self.D, self.W, self.skips = D, W, skips
@@ -77,8 +74,9 @@ class _FusedNet(nn.Module):
         # (the search default D=4 with skips=[4], options/arg_config.py:114)
         self._skip_layer = skips[0] if skips[0] < D - 1 else -1
         self._model_kind = _planmod.MODEL_LIGHT if light else None
+        self._activation = 'snake' if activation == 'snake' else 'relu'     # networks.py:51-54: anything else is relu
         self._plan = Plan(spec, depth=D, width=W, skip_layer=self._skip_layer, max_rows=1 << 15,
-                          model=self._model_kind)
+                          model=self._model_kind, activation=self._activation)
         self._generation = 0
         views = self._plan.param_views()
         # Initialise exactly like the reference: construct nn.Linear modules in the reference's order
@@ -100,7 +98,7 @@ class _FusedNet(nn.Module):
         self.feature_linear2 = holder("feature_linear2")
         self.alpha_linear = holder("alpha_linear")
         self.rgb_linear = holder("rgb_linear")
-        self.snakes = SnakeActivation()
+        self.snakes = SnakeActivation() if self._activation == 'snake' else None
         named = dict(self.named_parameters())
         self._param_names = list(named.keys())
         self._params = [named[k] for k in self._param_names]
@@ -116,7 +114,8 @@ class _FusedNet(nn.Module):
             old = self._plan
             cap = 1 << (int(n) - 1).bit_length()
             self._plan = Plan(self._spec, depth=self.D, width=self.W, skip_layer=self._skip_layer, max_rows=cap,
-                              arenas=(old.params, old.grads, old.exp_avg, old.exp_avg_sq), model=self._model_kind)
+                              arenas=(old.params, old.grads, old.exp_avg, old.exp_avg_sq), model=self._model_kind,
+                              activation=self._activation)
             self._plan.adam_steps = old.adam_steps
             self._plan.sync_weights()
             old.close()

@@ -91,7 +91,7 @@ class Plan:
 
     def __init__(self, enc: EncoderSpec, *, depth: int = 8, width: int = 512, skip_layer: int = 4,
                  max_rows: int = 1 << 16, wgrad_splits: int = 0, training: bool = True, arenas=None,
-                 model: Optional[int] = None):
+                 model: Optional[int] = None, activation: str = "snake"):
         if not torch.cuda.is_available():
             raise nat.NppError("npp_b200 needs a CUDA device (B200, sm_100); there is no CPU fallback")
         self.lib = nat.lib()
@@ -111,6 +111,8 @@ class Plan:
         cfg.include_input = int(enc.include_input)
         cfg.res_h, cfg.res_w = int(enc.res[0]), int(enc.res[1])
         cfg.wgrad_splits = wgrad_splits
+        cfg.activation = 0 if activation == "snake" else 1      # anything else is relu (models/networks.py:51-54)
+        self.activation = "snake" if activation == "snake" else "relu"
         cfg.max_rows = self.max_rows
         keep = [np.ascontiguousarray(a, np.float32) for a in (enc.cos_t, enc.sin_t, enc.period, enc.freqs)]
         fp = C.POINTER(C.c_float)

@@ -106,17 +106,32 @@ def snake_grad(z):
     return (F32(1) + np.sin(F32(2) * z, dtype=F32)).astype(F32)
 
 
+def relu(z):
+    """F.relu (models/networks.py:66-67), used when activation != 'snake'."""
+    return np.maximum(z, F32(0)).astype(F32)
+
+
+def relu_grad(z):
+    return (z > 0).astype(F32)
+
+
+def _act(activation):
+    """(function, derivative) of the hidden activation: 'snake' or, like the reference, relu for anything else."""
+    return (snake, snake_grad) if activation == "snake" else (relu, relu_grad)
+
+
 def _lin(p, name, x):
     return (x @ p[name + ".weight"].T + p[name + ".bias"]).astype(F32)
 
 
-def forward(p, enc, depth=8, skips=(4,), topk_model=True, ch1=None):
+def forward(p, enc, depth=8, skips=(4,), topk_model=True, ch1=None, activation="snake"):
     """NPP_Net.forward (models/networks.py:56-95) / NPP_Net_top1.forward (:145-173).
 
     p: dict of float32 arrays keyed like the reference state_dict.  enc [N, K*462].
     Returns (logits, cache) where cache holds every pre-/post-activation (for the backward and
     for per-layer parity checks)."""
     enc = np.asarray(enc, F32)
+    snake = _act(activation)[0]        # shadows the module-level function inside this forward
     if ch1 is None:
         ch1 = p["periodic_linears.0.weight"].shape[1]
     enc1, enc_aux = enc[:, :ch1], enc[:, ch1:]
@@ -179,12 +194,13 @@ def mse_l2_grad_logits(logits, target, mask=None, n_norm=None):
     return (g_pred * yh * (F32(1) - yh)).astype(F32)
 
 
-def backward(p, c, g_logits, depth=8, skips=(4,), topk_model=True):
+def backward(p, c, g_logits, depth=8, skips=(4,), topk_model=True, activation="snake"):
     """Hand-derived backward of `forward` (the reference uses autograd: loss.backward(),
     NPP_completion/train.py:253).  Returns (grads dict, deltas dict) -- deltas[name] is dL/dz of
     that layer (dL/d output for the activation-free feature_linear1/2)."""
     ch1 = c["enc1"].shape[1]
     W = p["feature_linear1.weight"].shape[0]
+    snake_grad = _act(activation)[1]
     grads, deltas = {}, {}
 
     def lin_bwd(name, delta):
@@ -233,13 +249,13 @@ def lr_schedule(step_index, lrate=5e-4, lrate_decay=500):
     return lrate * (0.1 ** (max(step_index - 2, 0) / (lrate_decay * 100)))
 
 
-def train_step(p, m, v, step, enc, target, mask, lr, depth=8, skips=(4,), topk_model=True):
+def train_step(p, m, v, step, enc, target, mask, lr, depth=8, skips=(4,), topk_model=True, activation="snake"):
     """One whole reference iteration with --loss_type l2 (NPP_completion/train.py:187-254)."""
-    logits, c = forward(p, enc, depth, skips, topk_model)
+    logits, c = forward(p, enc, depth, skips, topk_model, activation=activation)
     pred = sigmoid(logits)
     loss = mse_l2(pred, target, mask)
     g = mse_l2_grad_logits(logits, target, mask)
-    grads, _ = backward(p, c, g, depth, skips, topk_model)
+    grads, _ = backward(p, c, g, depth, skips, topk_model, activation=activation)
     adam_step(p, grads, m, v, step, lr)
     return loss, pred
 

@@ -12,6 +12,7 @@ inputs and writes small .npz fixtures next to this file:
   golden_encoding.npz   Embedder_periodic + Embedder outputs for integer coordinates
   golden_topk.npz       NPP_Net      (K=3, W=64): per-layer activations, loss, grads, Adam trajectory
   golden_top1.npz       NPP_Net_top1 (K=1, W=64): same
+  golden_relu.npz       NPP_Net (K=3, W=64) with activation='relu' (models/networks.py:51-54,66-69): same
 
 W=64 keeps the fixtures small; the reference modules and the oracle are width-agnostic.
 """
@@ -80,26 +81,31 @@ def main():
     base = [e.embed(torch.from_numpy(coords).clone()) for e in periodic]
     full = torch.cat([nerf.embed(b) for b in base], 1)
     tabs = [tables_from_embedder(e, n_aug) for e in periodic]
-    np.savez_compressed(
-        os.path.join(HERE, "golden_encoding.npz"), coords=coords, res=np.array(res), freqs=freqs,
-        angles=angles.numpy(), periods=periods.numpy(),
-        cos_t=np.stack([t[0] for t in tabs]), sin_t=np.stack([t[1] for t in tabs]),
-        period=np.stack([t[2] for t in tabs]),
-        base=torch.cat(base, 1).numpy(), full=full.numpy())
+    if not os.environ.get("NPP_GOLDEN_ONLY"):
+        np.savez_compressed(
+            os.path.join(HERE, "golden_encoding.npz"), coords=coords, res=np.array(res), freqs=freqs,
+            angles=angles.numpy(), periods=periods.numpy(),
+            cos_t=np.stack([t[0] for t in tabs]), sin_t=np.stack([t[1] for t in tabs]),
+            period=np.stack([t[2] for t in tabs]),
+            base=torch.cat(base, 1).numpy(), full=full.numpy())
 
     # ------------------------------------------------------------------- models
-    for tag, topk in (("topk", 3), ("top1", 1)):
+    for tag, topk in (("topk", 3), ("top1", 1), ("relu", 3)):
+        only = os.environ.get("NPP_GOLDEN_ONLY")       # regenerate one fixture without touching the others
+        if only and only != tag:
+            continue
+        activation = "relu" if tag == "relu" else "snake"
         torch.manual_seed(1)
         np.random.seed(1)
         W = 64
         if topk > 1:
             model = net.NPP_Net(D=8, W=W, freq_nerf=21, input_ch_periodic=22, input_ch_periodic_aux=22 * (topk - 1),
                                 freq_scales=freq_scales, freq_offsets=freq_offsets, angle_offsets=angle_offsets,
-                                output_ch=3, skips=[4], activation="snake")
+                                output_ch=3, skips=[4], activation=activation)
         else:
             model = net.NPP_Net_top1(D=8, W=W, freq_nerf=21, input_ch_periodic=22, freq_scales=freq_scales,
                                      freq_offsets=freq_offsets, angle_offsets=angle_offsets, output_ch=3,
-                                     skips=[4], activation="snake")
+                                     skips=[4], activation=activation)
         enc = full[:, : 462 * topk].clone()
         target = torch.rand(n, 3)
         mask = (torch.rand(n, 1) > 0.3).float()

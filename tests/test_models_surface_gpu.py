@@ -251,3 +251,33 @@ def test_small_parameter_adam_matches_torch():
         topt.step()
         for a, b in zip(ours, ref):
             torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=1e-8)
+
+
+def test_relu_activation_on_the_dropin_surface(monkeypatch):
+    """args.activation='relu' (anything but 'snake', reference networks.py:51-54): NPP_Net builds, trains and has no
+    `snakes` module, like the reference object."""
+    monkeypatch.delenv("NPP_B200_EMBED", raising=False)
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net, render
+    from models.mse_calculator import img2mse
+    args = _args(3)
+    args.activation = 'relu'
+    torch.manual_seed(0)
+    angles = torch.Tensor([[83.0, 172.5], [90.0, 180.0], [41.3, 127.9]])
+    periods = torch.Tensor([[42.7, 38.4], [21.35, 19.2], [85.4, 76.8]])
+    kw, _, _, grad_vars, optimizer, embedder, embedder_periodics = create_npp_net(args, angles, periods, (512, 512), None)
+    model = kw["network_fn"]
+    assert model.snakes is None
+    coords = torch.stack([torch.randint(0, 512, (4096,)), torch.randint(0, 512, (4096,))], 1).float().cuda()
+    target = (0.5 + 0.4 * torch.sin(coords[:, :1] * 0.147 + torch.arange(3, device="cuda"))).contiguous()
+    enc = torch.cat([e.embed(coords.clone()) for e in embedder_periodics], 1)
+    losses = []
+    for _ in range(30):
+        pred = render(None, enc, args, **kw)
+        optimizer.zero_grad()
+        loss = img2mse(pred, target, 'l2', None, None)
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.8 * losses[0], losses[::6]

@@ -38,11 +38,12 @@ def test_encoder_tables_and_encoding():
     np.testing.assert_allclose(full[:, 22 * 3 + 5], np.sin(u[:, 5] * g["freqs"][1]), atol=5e-5)
 
 
-@pytest.mark.parametrize("tag,topk", [("topk", 3), ("top1", 1)])
+@pytest.mark.parametrize("tag,topk", [("topk", 3), ("top1", 1), ("relu", 3)])
 def test_forward_backward_adam(tag, topk):
     g = np.load(os.path.join(G, f"golden_{tag}.npz"))
+    act = "relu" if tag == "relu" else "snake"
     p = {k[5:]: g[k].copy() for k in g.files if k.startswith("init/")}
-    logits, c = O.forward(p, g["enc"], topk_model=topk > 1)
+    logits, c = O.forward(p, g["enc"], topk_model=topk > 1, activation=act)
     for k in [k for k in g.files if k.startswith("z/")]:
         name = k[2:]
         if name == "rgb_linear":
@@ -57,7 +58,8 @@ def test_forward_backward_adam(tag, topk):
     np.testing.assert_allclose(O.sigmoid(logits), g["pred"], atol=1e-6)
     loss = O.mse_l2(O.sigmoid(logits), g["target"], g["mask"])
     assert abs(loss - g["losses"][0]) < 1e-6
-    grads, _ = O.backward(p, c, O.mse_l2_grad_logits(logits, g["target"], g["mask"]), topk_model=topk > 1)
+    grads, _ = O.backward(p, c, O.mse_l2_grad_logits(logits, g["target"], g["mask"]), topk_model=topk > 1,
+                          activation=act)
     gkeys = [k[5:] for k in g.files if k.startswith("grad/")]
     assert sorted(gkeys) == sorted(grads.keys())          # same set of trained parameters
     for k in gkeys:
@@ -68,7 +70,8 @@ def test_forward_backward_adam(tag, topk):
     v = {k: np.zeros_like(v_) for k, v_ in p.items()}
     losses = []
     for it in range(1, 4):
-        l, _ = O.train_step(p, m, v, it, g["enc"], g["target"], g["mask"], O.lr_schedule(it), topk_model=topk > 1)
+        l, _ = O.train_step(p, m, v, it, g["enc"], g["target"], g["mask"], O.lr_schedule(it), topk_model=topk > 1,
+                            activation=act)
         losses.append(l)
     np.testing.assert_allclose(losses, g["losses"], rtol=2e-5)
     for k in p:

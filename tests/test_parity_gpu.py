@@ -220,6 +220,59 @@ def test_shallow_network_depth4():
         assert rel(gv[k].cpu().numpy(), ref) < 2e-3, k
 
 
+@pytest.mark.parametrize("topk", [3, 1])
+def test_relu_activation_parity(topk):
+    """activation != 'snake' selects F.relu (models/networks.py:51-54,66-69): forward, backward and fused train steps
+    against the oracle.  relu'(z) flips between 0 and 1 where fp16-operand rounding moves z across zero (< 0.1 % of the
+    units; each flip moves a gradient by a whole delta x input term, ~2 % of a weight gradient's norm in total), so the
+    gradients are compared against the oracle backward evaluated with the kernel's own masks."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(7)
+    n = 600
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(RES, ANGLES[:topk], PERIODS[:topk], freqs)
+    plan = Plan(enc, max_rows=n, activation="relu")
+    params = O.init_params(rng, topk=topk)
+    plan.load_state(params)
+    coords = np.stack([rng.integers(0, RES[0], n), rng.integers(0, RES[1], n)], 1).astype(np.float32)
+    tabs = [(enc.cos_t[j], enc.sin_t[j], enc.period[j]) for j in range(topk)]
+    e = O.encode(coords, tabs, freqs, RES)
+    logits_ref, c = O.forward(params, e, topk_model=topk > 1, activation="relu")
+    cd = torch.from_numpy(coords).cuda()
+    logits = plan.forward(cd)
+    assert rel(logits.cpu().numpy(), logits_ref) < TOL
+    h0 = plan.debug("h0", n).cpu().numpy()
+    assert h0.min() == 0.0 and rel(h0, c["h"]["periodic_linears.0"]) < TOL
+    d0 = plan.debug("d0", n).cpu().numpy()
+    assert set(np.unique(d0)) <= {0.0, 1.0} and (d0 != O.relu_grad(c["z"]["periodic_linears.0"])).mean() < 1e-3
+    target = rng.random((n, 3), dtype=np.float32)
+    g = O.mse_l2_grad_logits(logits_ref, target)
+    # the oracle backward with OUR 0/1 masks (relu' only looks at the sign of z): what remains is fp16-operand rounding
+    c2 = dict(c)
+    c2["z"] = {name: plan.debug(f"d{i}", n).cpu().numpy() - 0.5
+               for i, name in enumerate(plan.layer_names) if name in c["z"]}
+    flips = sum(((c2["z"][k] > 0) != (c["z"][k] > 0)).sum() for k in c2["z"]) / sum(v.size for v in c2["z"].values())
+    assert flips < 1e-3, flips
+    grads_ref, _ = O.backward(params, c2, g, topk_model=topk > 1, activation="relu")
+    plan.backward(n, torch.from_numpy(g).cuda())
+    gv = plan.grad_views()
+    assert sorted(gv) == sorted(grads_ref)
+    for k, ref in grads_ref.items():
+        assert rel(gv[k].cpu().numpy(), ref) < 2e-3, (k, rel(gv[k].cpu().numpy(), ref))
+    # fused train steps
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in p.items()}
+    td = torch.from_numpy(target).cuda()
+    loss = torch.zeros((), device="cuda")
+    for step in range(1, 5):
+        plan.train_step(cd, td, None, O.lr_schedule(step), loss, step=step)
+        l_ref, _ = O.train_step(p, m, v, step, e, target, None, O.lr_schedule(step), topk_model=topk > 1,
+                                activation="relu")
+        assert abs(loss.item() - l_ref) < 2e-3 * l_ref, (step, loss.item(), l_ref)
+
+
 def test_mse_kernel():
     plan, params, coords, tabs, freqs, rng = make(1, 333)
     logits = torch.randn(333, 3, device="cuda") * 2
