@@ -44,8 +44,8 @@ typedef struct NppConfig {
   int32_t model;          /* NPP_MODEL_* */
   int32_t topk;           /* number of periodicity proposals K (create_npp_net, models/helpers.py:108-116) */
   int32_t depth;          /* netdepth D (options/arg_config.py:55-74), default 8 */
-  int32_t width;          /* netwidth W; 512 (the reference default) for NPP_Net / NPP_Net_top1, 256 (the search
-                             default, options/arg_config.py:116) or 512 for NPP_Net_light */
+  int32_t width;          /* netwidth W: 512 (options/arg_config.py:57) or 256 (the constructors' default and the
+                             search default, options/arg_config.py:116) */
   int32_t skip_layer;     /* skips=[4] (models/helpers.py:90); -1 = none */
   int32_t n_aug;          /* len(freq_scales)*len(freq_offsets)*len(angle_offsets), embedder.py:117-120 */
   int32_t n_freq;         /* multires, number of Gaussian Fourier frequencies (embedder.py:25-26) */

@@ -1082,11 +1082,8 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   if (cfg->model == NPP_MODEL_TOPK && cfg->topk < 2) return fail("NPP_Net (top-K) needs topk >= 2");
   if (cfg->model == NPP_MODEL_TOP1 && cfg->topk != 1) return fail("NPP_Net_top1 needs topk == 1");
   if (cfg->topk > MAX_TOPK) return fail("topk exceeds MAX_TOPK=8");
-  if (cfg->model == NPP_MODEL_LIGHT) {
-    if (cfg->width != 256 && cfg->width != 512) return fail("NPP_Net_light: netwidth must be 256 (the search default) or 512");
-  } else if (cfg->width != 512) {
-    return fail("this build supports netwidth == 512 only (the reference default)");
-  }
+  if (cfg->width != 256 && cfg->width != 512)
+    return fail("netwidth must be 512 (the reference default) or 256 (the class default and the search-stage default)");
   if (cfg->activation != NPP_ACT_SNAKE && cfg->activation != NPP_ACT_RELU) return fail("unknown activation");
   if (cfg->depth < 2 || cfg->depth > 16) return fail("netdepth must be in [2,16]");
   if (cfg->skip_layer >= cfg->depth - 1) return fail("skip layer must be < depth-1");

@@ -273,6 +273,47 @@ def test_relu_activation_parity(topk):
         assert abs(loss.item() - l_ref) < 2e-3 * l_ref, (step, loss.item(), l_ref)
 
 
+@pytest.mark.parametrize("topk", [3, 1])
+def test_netwidth_256(topk):
+    """W = 256 (the constructors' default, models/networks.py:9): one N tile per layer, pos_linears.0 on a zero-padded
+    half tile, 128-wide RGB head.  Forward, backward and fused train steps against the oracle."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    rng = np.random.default_rng(11)
+    n, W = 900, 256
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    enc = EncoderSpec.from_proposals(RES, ANGLES[:topk], PERIODS[:topk], freqs)
+    plan = Plan(enc, width=W, max_rows=n)
+    params = O.init_params(rng, topk=topk, width=W)
+    plan.load_state(params)
+    assert {s.name: tuple(s.shape) for s in plan.slots} == {k: tuple(v.shape) for k, v in params.items()}
+    coords = np.stack([rng.integers(0, RES[0], n), rng.integers(0, RES[1], n)], 1).astype(np.float32)
+    tabs = [(enc.cos_t[j], enc.sin_t[j], enc.period[j]) for j in range(topk)]
+    e = O.encode(coords, tabs, freqs, RES)
+    logits_ref, c = O.forward(params, e, topk_model=topk > 1)
+    cd = torch.from_numpy(coords).cuda()
+    assert rel(plan.forward(cd).cpu().numpy(), logits_ref) < TOL
+    target = rng.random((n, 3), dtype=np.float32)
+    mask = (rng.random((n, 1)) > 0.3).astype(np.float32)
+    g = O.mse_l2_grad_logits(logits_ref, target, mask)
+    grads_ref, _ = O.backward(params, c, g, topk_model=topk > 1)
+    plan.backward(n, torch.from_numpy(g).cuda())
+    gv = plan.grad_views()
+    assert sorted(gv) == sorted(grads_ref)
+    for k, ref in grads_ref.items():
+        assert rel(gv[k].cpu().numpy(), ref) < 2e-3, (k, rel(gv[k].cpu().numpy(), ref))
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in p.items()}
+    td, md = torch.from_numpy(target).cuda(), torch.from_numpy(mask).cuda()
+    loss = torch.zeros((), device="cuda")
+    for step in range(1, 5):
+        plan.train_step(cd, td, md, O.lr_schedule(step), loss, step=step)
+        l_ref, _ = O.train_step(p, m, v, step, e, target, mask, O.lr_schedule(step), topk_model=topk > 1)
+        assert abs(loss.item() - l_ref) < 1e-3 * l_ref, (step, loss.item(), l_ref)
+    assert plan.launch_count() == 6
+
+
 def test_mse_kernel():
     plan, params, coords, tabs, freqs, rng = make(1, 333)
     logits = torch.randn(333, 3, device="cuda") * 2
