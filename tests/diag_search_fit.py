@@ -110,6 +110,25 @@ def main():
     torch.cuda.synchronize()
     print(f"fit_run, one candidate: {a.elapsed_time(b):.1f} ms for {ITERS} iterations = {a.elapsed_time(b) / ITERS * 1e3:.1f} us/step")
 
+    # the numpy port of the same step on the host cores (oracle/npp_oracle.py train_step_light; a bounded sample)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import npp_oracle as O
+    rng = np.random.default_rng(0)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    table = O.encoder_tables([83.0, 172.5], [42.7, 38.4], [1], [0, -1, 1, 0.5, -0.5], [0])
+    p_ = O.init_params_light(rng)
+    m_ = {k: np.zeros_like(v) for k, v in p_.items()}
+    v_ = {k: np.zeros_like(v) for k, v in p_.items()}
+    cpu_coords = data[0][0].cpu().numpy()
+    cpu_target = data[0][1].cpu().numpy()
+    t0 = time.perf_counter()
+    steps = 20
+    for it in range(1, steps + 1):
+        pos, per = O.encode_search(cpu_coords, table, freqs, RES)
+        O.train_step_light(p_, m_, v_, it, pos, per, cpu_target, 5e-4)
+    dt = (time.perf_counter() - t0) / steps
+    print(f"numpy port on {os.cpu_count()} host cores (encode + step): {dt * 1e3:.2f} ms/step  {N / dt / 1e6:.3f} M samples/s")
+
     # the same layer stack in plain torch (eager fp32 and TF32) on this GPU: what the reference's NPP_Net_light costs
     # per iteration of NPP_proposal/search.py:112-146 once its encodings are precomputed
     import torch.nn as nn
