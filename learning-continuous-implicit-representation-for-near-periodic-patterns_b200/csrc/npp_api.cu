@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -168,6 +169,7 @@ struct NppPlan {
   long long ad_table_cap = 0;
   bool step_mode = false;               // launches take their batch / scalars through d_step
   cudaEvent_t tables_evt = nullptr;     // recorded after the last kernels that read the device op tables
+  cudaEvent_t coop_evt = nullptr;       // recorded after this plan's last cooperative head launch (see coop_head_allowed)
   bool capturing = false;               // npp_fit_run is recording into side_stream
   cudaGraphExec_t fit_exec = nullptr;   // the last npp_fit_run, captured as one graph (kept until the next run / destroy)
   cudaStream_t fit_stream = nullptr;    // stream it was launched on
@@ -538,6 +540,7 @@ static int alloc_plan_memory(NppPlan* p) {
   CK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&p->pref_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&p->tables_evt, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&p->coop_evt, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&p->pref[i].done, cudaEventDisableTiming));
   CK(cudaMalloc(&p->d_dgrad_ops, (p->dgrads.size() + 1) * sizeof(KmajorParams)));
   CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
@@ -887,6 +890,21 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   return 0;
 }
 
+// The fused head is a cooperative launch with a grid barrier.  Two such grids in flight at the same time (two plans
+// stepping on two streams) can each hold part of the SMs and wait for the rest -- observed as a hang with nine
+// concurrent fits.  One cooperative head may be in flight per process: a plan that finds another plan's head still
+// running takes the two-kernel head for that step.  Steps of ONE plan are ordered by construction (they share the
+// activation workspace), so the common single-plan case never leaves the cooperative path.
+static std::mutex g_coop_mu;
+static NppPlan* g_coop_plan = nullptr;   // plan that launched the last cooperative head
+static bool coop_head_allowed(NppPlan* p) {   // g_coop_mu held
+  if (g_coop_plan == nullptr || g_coop_plan == p) return true;
+  const cudaError_t q = cudaEventQuery(g_coop_plan->coop_evt);
+  if (q == cudaSuccess) return true;
+  cudaGetLastError();   // cudaErrorNotReady is not sticky, but keep the error state clean
+  return false;
+}
+
 // After the last kernel of a call that reads the device op tables (see prepare()).
 static int mark_busy(NppPlan* p, cudaStream_t st) {
   if (!p->capturing) CK(cudaEventRecord(p->tables_evt, st));
@@ -1133,6 +1151,13 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
 
 int npp_plan_destroy(NppPlan* p) {
   if (!p) return 0;
+  {
+    std::lock_guard<std::mutex> g(g_coop_mu);
+    if (g_coop_plan == p) {
+      cudaEventSynchronize(p->coop_evt);
+      g_coop_plan = nullptr;
+    }
+  }
   if (p->fit_exec) {
     cudaStreamSynchronize(p->fit_stream);
     cudaGraphExecDestroy(p->fit_exec);
@@ -1155,6 +1180,7 @@ int npp_plan_destroy(NppPlan* p) {
   if (p->side_stream) cudaStreamDestroy(p->side_stream);
   if (p->pref_fork) cudaEventDestroy(p->pref_fork);
   if (p->tables_evt) cudaEventDestroy(p->tables_evt);
+  if (p->coop_evt) cudaEventDestroy(p->coop_evt);
   for (int i = 0; i < 2; ++i) if (p->pref[i].done) cudaEventDestroy(p->pref[i].done);
   cudaFree(p->d_dgrad_ops);
   cudaFree(p->d_units);
@@ -1345,7 +1371,15 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   // The fused head is a cooperative launch with a grid barrier.  Two such grids running at the same time (two plans
   // on two streams) can each hold part of the SMs and wait for the rest: search-stage fits are meant to run several
   // candidates side by side (NPP_proposal/search.py:85 loops over up to 9), so NPP_Net_light takes the two-kernel head.
-  const bool fused_head = p->head_fused_blocks > 0 && p->cfg.model != NPP_MODEL_LIGHT && !getenv("NPP_SPLIT_HEAD");
+  bool fused_head = p->head_fused_blocks > 0 && p->cfg.model != NPP_MODEL_LIGHT && !getenv("NPP_SPLIT_HEAD");
+  std::unique_lock<std::mutex> coop_lock(g_coop_mu, std::defer_lock);
+  if (fused_head) {
+    coop_lock.lock();
+    if (!coop_head_allowed(p)) {
+      fused_head = false;
+      coop_lock.unlock();
+    }
+  }
   if (fused_head) {
     // head forward + loss + head backward in one cooperative launch (grid barrier around the max|g| reduction)
     CKI(prepare(p, n));
@@ -1380,6 +1414,9 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
                                      st));
     }
     ++p->launches;
+    CK(cudaEventRecord(p->coop_evt, st));
+    g_coop_plan = p;
+    coop_lock.unlock();
   } else {
     ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
     const Layer& last = p->layers.back();

@@ -314,6 +314,50 @@ def test_netwidth_256(topk):
     assert plan.launch_count() == 6
 
 
+def test_two_plans_stepping_concurrently():
+    """Two fits on two streams from two host threads.  The fused head is a cooperative launch (grid barrier); two of
+    them in flight at once can dead-lock, so a plan that finds another plan's head still running takes the two-kernel
+    head for that step (coop_head_allowed in npp_api.cu).  Both fits must finish and match the same fits run alone."""
+    import threading
+    steps, n = 40, 4096
+    made = [make(1, n, seed=s) for s in (31, 32)]
+    data = []
+    for plan, params, coords, tabs, freqs, rng in made:
+        data.append((torch.from_numpy(coords).cuda(), torch.from_numpy(rng.random((n, 3), dtype=np.float32)).cuda()))
+
+    def run(plan, cd, td, out, stream):
+        loss, early = torch.zeros((), device="cuda"), torch.zeros((), device="cuda")
+        with torch.cuda.stream(stream):
+            for i in range(steps):
+                plan.train_step(cd, td, None, 5e-4, early if i < 6 else loss, step=i + 1)
+            out.extend([early, loss])
+
+    alone = []
+    for (plan, params, *_), (cd, td) in zip(made, data):
+        out = []
+        run(plan, cd, td, out, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        alone.append((out[0].item(), out[1].item()))
+        plan.load_state(params)                      # back to the initial weights
+        plan.exp_avg.zero_()
+        plan.exp_avg_sq.zero_()
+    torch.cuda.synchronize()
+    outs, threads, streams = [[], []], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for k in range(2):
+        th = threading.Thread(target=run, args=(made[k][0], *data[k], outs[k], streams[k]))
+        threads.append(th)
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    for k in range(2):
+        early, last = outs[k][0].item(), outs[k][1].item()
+        # step 6: same trajectory whichever head ran; step 40: the fits have moved far (loss halves) and fp16 / atomic
+        # ordering noise has been amplified by Adam, so only the level is compared
+        assert abs(early - alone[k][0]) < 2e-3 * alone[k][0], (k, early, alone[k][0])
+        assert abs(last - alone[k][1]) < 0.15 * alone[k][1], (k, last, alone[k][1])
+
+
 def test_mse_kernel():
     plan, params, coords, tabs, freqs, rng = make(1, 333)
     logits = torch.randn(333, 3, device="cuda") * 2
