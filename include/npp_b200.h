@@ -102,6 +102,13 @@ int npp_encode(NppPlan* plan, const float* coords, int64_t n, float* out, void* 
  * writes the pre-sigmoid logits [n,3] fp32 and keeps the activations needed by npp_backward. */
 int npp_forward(NppPlan* plan, const float* coords, int64_t n, float* logits, void* stream);
 
+/* Full-image inference (NPP_completion/train.py:277-309: render the train / val pixel pools in chunks and scatter them
+ * into an image): forward on `n` coordinate rows (any n; processed in max_rows chunks), sigmoid (normalize_type 1) or
+ * tanh (2) as models/helpers.py:55-58, written to image[y, x, :] of a device [img_h, img_w, 3] fp32 image.  Pixels not
+ * named by a row are left untouched; rows outside the image are skipped. */
+int npp_render_into(NppPlan* plan, const float* coords, int64_t n, float* image, int32_t img_h, int32_t img_w,
+                    int32_t normalize_type, void* stream);
+
 /* Same network on a materialised encoding: enc device [n, K*462] fp32 in the reference layout (rows of the
  * table built at NPP_completion/train.py:93-105), i.e. NPP_Net.forward(None, x_periodic) verbatim.
  * NPP_MODEL_LIGHT: enc is the [n, 62] layout of npp_encode, i.e. NPP_Net_light.forward(x, x_periodic). */

@@ -60,6 +60,7 @@ SIGNATURES = {
     "npp_encode": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "npp_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "npp_forward_encoded": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "npp_render_into": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "npp_backward": (C.c_int, [_P, C.c_int64, _P, _P]),
     "npp_mse_fwd_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "npp_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),

@@ -1266,6 +1266,28 @@ int npp_forward(NppPlan* p, const float* coords, int64_t n, float* logits, void*
   return run_forward(p, coords, n, logits, (cudaStream_t)stream);
 }
 
+int npp_render_into(NppPlan* p, const float* coords, int64_t n, float* image, int32_t img_h, int32_t img_w,
+                    int32_t normalize_type, void* stream) {
+  if (!p || !coords || !image) return fail("npp_render_into: null argument");
+  if (img_h <= 0 || img_w <= 0) return fail("npp_render_into: image size must be positive");
+  if (normalize_type != 1 && normalize_type != 2) return fail("npp_render_into: normalize_type must be 1 (sigmoid) or 2 (tanh)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  const Layer& last = p->layers.back();
+  for (int64_t r0 = 0; r0 < n; r0 += p->cfg.max_rows) {      // any number of pixels: workspace-sized chunks
+    const int64_t rows = std::min<int64_t>(p->cfg.max_rows, n - r0);
+    p->launches = 0;
+    CKI(run_forward(p, coords + 2 * r0, rows, nullptr, st, /*with_head=*/false));
+    npp_head_render_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(
+        p->bufs[last.buf_h].ptr, last.out, p->head_width, (int)rows, p->params + p->rgb_w_off, p->params + p->rgb_b_off,
+        coords + 2 * r0, image, img_h, img_w, normalize_type);
+    CK(cudaGetLastError());
+    launches += p->launches + 1;
+  }
+  p->launches = launches;
+  return 0;
+}
+
 int npp_forward_encoded(NppPlan* p, const float* enc, int64_t n, float* logits, void* stream) {
   if (!p || !enc || !logits) return fail("npp_forward_encoded: null argument");
   p->launches = 0;

@@ -369,6 +369,46 @@ __global__ void __launch_bounds__(256) npp_head_fwd_kernel(const __half* __restr
   }
 }
 
+// Inference: RGB head + squashing (models/helpers.py:55-58: sigmoid for normalize_type 1, tanh for 2), written straight
+// into an [H, W, 3] image at the pixel each coordinate row names -- the scatter of NPP_completion/train.py:288-296
+// (pred_img[:, coord[:, 0], coord[:, 1], :] = pred) without the intermediate [n, 3] tensor.  One warp per row.
+__global__ void __launch_bounds__(256) npp_head_render_kernel(const __half* __restrict__ hp, int ld, int width, int n,
+                                                              const float* __restrict__ w, const float* __restrict__ b,
+                                                              const float* __restrict__ coords,
+                                                              float* __restrict__ image, int img_h, int img_w,
+                                                              int normalize_type) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const __half* h = hp + (size_t)warp * ld;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = lane * 8; k < width; k += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(h + k);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      const int kk = k + 2 * i;
+      a0 = fmaf(f.x, w[kk], fmaf(f.y, w[kk + 1], a0));
+      a1 = fmaf(f.x, w[width + kk], fmaf(f.y, w[width + kk + 1], a1));
+      a2 = fmaf(f.x, w[2 * width + kk], fmaf(f.y, w[2 * width + kk + 1], a2));
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+  }
+  if (lane < 3) {
+    const int y = (int)coords[2 * (size_t)warp], x = (int)coords[2 * (size_t)warp + 1];
+    if (y < 0 || y >= img_h || x < 0 || x >= img_w) return;
+    const float z = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + b[lane];
+    const float v = normalize_type == 2 ? tanhf(z) : 1.0f / (1.0f + expf(-z));
+    image[((size_t)y * img_w + x) * 3 + lane] = v;
+  }
+}
+
 // Power-of-two gradient scale so that fp16 deltas sit in the middle of the half range:
 // amax * scale == 2^10 (rounded down to a power of two).  Exact to undo in fp32.
 __device__ __forceinline__ float npp_grad_scale(float amax) {

@@ -156,6 +156,15 @@ class _FusedNet(nn.Module):
         self.mark_clean()
         return out
 
+    @torch.no_grad()
+    def render_into(self, coords, image, normalize_type=1):
+        """Inference straight into an image (the evaluation loop of NPP_completion/train.py:277-309 in one call):
+        image[..., y, x, :] = sigmoid / tanh of the network output for every (row, col) in `coords` [N,2]."""
+        plan = self._plan_for(min(int(coords.shape[0]), self._plan.max_rows))
+        self._sync_if_dirty(self._params)
+        self._generation += 1          # the activations of a pending forward are overwritten
+        return plan.render_into(coords, image, normalize_type)
+
     def forward(self, x, x_periodic):
         """x is ignored (None) exactly like the reference; x_periodic is either [N,2] coordinates ('coords' embed
         mode) or the materialised [N, K*462] encoding."""

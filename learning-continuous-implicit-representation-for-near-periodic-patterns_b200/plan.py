@@ -224,6 +224,21 @@ class Plan:
             nat.check(self.lib.npp_forward(self.handle, c.data_ptr(), c.shape[0], logits.data_ptr(), nat.current_stream()))
         return logits
 
+    def render_into(self, coords: torch.Tensor, image: torch.Tensor, normalize_type: int = 1) -> torch.Tensor:
+        """Inference straight into an image: image[y, x, :] = sigmoid(net(y, x)) for every coordinate row (any number
+        of rows).  image: contiguous fp32 CUDA [H, W, 3] (or [1, H, W, 3] as the train scripts hold it)."""
+        c = coords.to(self.device, torch.float32).contiguous()
+        if c.dim() != 2 or c.shape[1] != 2:
+            raise ValueError("coords must be [N,2] (row, col)")
+        if not (image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and image.shape[-1] == 3
+                and image.dim() in (3, 4) and (image.dim() == 3 or image.shape[0] == 1)):
+            raise ValueError("image must be a contiguous fp32 CUDA tensor [H, W, 3] or [1, H, W, 3]")
+        h, w = int(image.shape[-3]), int(image.shape[-2])
+        if c.shape[0]:
+            nat.check(self.lib.npp_render_into(self.handle, c.data_ptr(), c.shape[0], image.data_ptr(), h, w,
+                                               int(normalize_type), nat.current_stream()))
+        return image
+
     def forward_encoded(self, enc: torch.Tensor) -> torch.Tensor:
         """Forward on a materialised [N, K*462] fp32 encoding (reference layout)."""
         e = enc.to(self.device, torch.float32).contiguous()

@@ -358,6 +358,29 @@ def test_two_plans_stepping_concurrently():
         assert abs(last - alone[k][1]) < 0.15 * alone[k][1], (k, last, alone[k][1])
 
 
+def test_render_into_image():
+    """npp_render_into: chunked forward + sigmoid / tanh scattered straight into an [H, W, 3] image
+    (NPP_completion/train.py:277-309), against plan.forward + torch ops; ragged last chunk."""
+    plan, params, _, tabs, freqs, rng = make(3, 128, max_rows=4096)
+    n = 10000
+    flat = rng.choice(RES[0] * RES[1], n, replace=False)
+    coords = torch.from_numpy(np.stack([flat // RES[1], flat % RES[1]], 1).astype(np.float32)).cuda()
+    logits = torch.cat([plan.forward(coords[i:i + 4096]) for i in range(0, n, 4096)])
+    yy, xx = coords[:, 0].long(), coords[:, 1].long()
+    for nt, fn in ((1, torch.sigmoid), (2, torch.tanh)):
+        image = torch.full((1, RES[0], RES[1], 3), -7.0, device="cuda")
+        out = plan.render_into(coords, image, normalize_type=nt)
+        assert out is image
+        ref = torch.full_like(image, -7.0)
+        ref[0, yy, xx, :] = fn(logits)
+        assert (image[0, yy, xx, :] - ref[0, yy, xx, :]).abs().max().item() < 2e-6
+        untouched = torch.ones(RES, dtype=torch.bool, device="cuda")
+        untouched[yy, xx] = False
+        assert (image[0][untouched] == -7.0).all()
+    with pytest.raises(Exception):
+        plan.render_into(coords, torch.zeros(RES[0], RES[1], 4, device="cuda"))
+
+
 def test_mse_kernel():
     plan, params, coords, tabs, freqs, rng = make(1, 333)
     logits = torch.randn(333, 3, device="cuda") * 2
