@@ -16,7 +16,32 @@ from typing import List, Optional, Sequence
 
 import torch
 
+import torch.distributed as dist
+
 from .plan import Plan
+
+
+def assign_candidates(n_candidates: int, rank: int, world: int) -> List[int]:
+    """Candidates of `rank` when a search is spread over several GPUs (one process per GPU): round-robin, so that the
+    first candidates -- the most plausible periodicities, NPP_proposal/search.py ranks them in that order -- land on
+    different GPUs.  Fits are independent; nothing is exchanged while they run."""
+    return list(range(int(rank), int(n_candidates), int(world)))
+
+
+def gather_scores(local: dict) -> dict:
+    """{candidate index: score} of every rank merged on every rank (the search's ranking step,
+    search.py:199-207, needs all distances); a plain dict in a single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return dict(local)
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, dict(local))
+    merged = {}
+    for part in parts:
+        for k, v in part.items():
+            if k in merged:
+                raise ValueError(f"candidate {k} was fitted by two ranks")
+            merged[k] = v
+    return merged
 
 
 def gather_batches(image: torch.Tensor, train_coords: torch.Tensor, indices: torch.Tensor):

@@ -67,3 +67,36 @@ def test_dp_gradient_equals_single_process(tmp_path):
     grads, _ = O.backward(params, c, O.mse_l2_grad_logits(logits, target, mask))
     ref = np.concatenate([grads[k].ravel() for k in sorted(grads)])
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
+
+
+def _search_worker(rank, world, port, n_candidates, out_dir):
+    sys.path.insert(0, ROOT)
+    import npp_b200  # noqa: F401
+    from npp_b200 import search_fits
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = search_fits.assign_candidates(n_candidates, rank, world)
+    scores = search_fits.gather_scores({k: float(10 * k + rank) for k in mine})      # stand-in for the fitted distances
+    if rank == 1:
+        np.save(os.path.join(out_dir, "scores.npy"), np.array([scores[k] for k in range(n_candidates)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_search_candidates_sharded_over_ranks(tmp_path):
+    """Independent search-stage fits over N GPUs: round-robin assignment, no data-path collective, one gather of the
+    per-candidate scores at the end (gloo, world_size 2)."""
+    sys.path.insert(0, ROOT)
+    import npp_b200  # noqa: F401
+    from npp_b200 import search_fits
+    for n, w in [(9, 2), (9, 8), (3, 4), (0, 2)]:
+        parts = [search_fits.assign_candidates(n, r, w) for r in range(w)]
+        assert sorted(k for p_ in parts for k in p_) == list(range(n))
+        assert max(len(p_) for p_ in parts) - min(len(p_) for p_ in parts) <= 1
+    assert search_fits.gather_scores({0: 1.5}) == {0: 1.5}                           # single process: identity
+    world, port = 2, 31000 + os.getpid() % 2000
+    mp.spawn(_search_worker, args=(world, port, 9, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "scores.npy")
+    assert got.tolist() == [10.0 * k + (k % 2) for k in range(9)]
