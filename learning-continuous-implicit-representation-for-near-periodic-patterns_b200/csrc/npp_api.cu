@@ -1274,8 +1274,17 @@ int npp_render_into(NppPlan* p, const float* coords, int64_t n, float* image, in
   cudaStream_t st = (cudaStream_t)stream;
   int launches = 0;
   const Layer& last = p->layers.back();
-  for (int64_t r0 = 0; r0 < n; r0 += p->cfg.max_rows) {      // any number of pixels: workspace-sized chunks
-    const int64_t rows = std::min<int64_t>(p->cfg.max_rows, n - r0);
+  // Any number of pixels, in chunks that fit the workspace.  A chunk is a whole number of waves of the persistent chain
+  // kernel (one 128-row stripe per SM: 18 944 rows on 148 SMs) when the workspace allows it -- 32 768-row chunks would
+  // run a full wave and a 73 % full one.  The last chunk is moved back so that it has the same row count (the pixels it
+  // shares with its predecessor are simply written twice): the per-row-count setup is not redone for a ragged tail.
+  const int64_t wave = (int64_t)(p->num_sms / p->cluster * p->cluster) * BM;
+  int64_t chunk = p->cfg.max_rows / wave * wave;
+  if (chunk == 0) chunk = p->cfg.max_rows;
+  if (chunk > n) chunk = n;
+  for (int64_t done = 0; done < n; done += chunk) {
+    const int64_t r0 = std::min<int64_t>(done, n - chunk);
+    const int64_t rows = chunk;
     p->launches = 0;
     CKI(run_forward(p, coords + 2 * r0, rows, nullptr, st, /*with_head=*/false));
     npp_head_render_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(

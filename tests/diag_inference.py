@@ -37,7 +37,7 @@ def script_loop(chunk=20000):
         image[:, cl[:, 0], cl[:, 1], :] = pred
 
 
-for name, fn in (("render_into (fused, 32768-row chunks)", fused), ("script loop (20000-row chunks, sigmoid, index_put)", script_loop)):
+for name, fn in (("render_into (fused, wave-aligned 18944-row chunks)", fused), ("script loop (20000-row chunks, sigmoid, index_put)", script_loop)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
