@@ -332,3 +332,34 @@ def test_fit_run_graph_modes_equal_plain_launches(monkeypatch, mode):
     torch.cuda.current_stream().wait_stream(s)
     np.testing.assert_allclose(graphed.cpu().numpy(), direct, rtol=1e-4)
     assert b.adam_steps == 2 * iters and again[-1].item() < graphed[0].item()
+
+
+def test_search_mode_table_embedding_matches_coords_mode(monkeypatch):
+    """NPP_B200_EMBED=table: the search-mode embedders materialise the reference's [N,42] / [N,20] encodings (checked
+    against the oracle) and NPP_Net_light.forward(x, x_periodic) on them equals the coordinate path."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net
+    args = types.SimpleNamespace(multires=10, i_embed=0, freq_scales=[1], freq_offsets=[0, -1, 1, 0.5, -0.5],
+                                 angle_offsets=[0], netdepth=4, netwidth=256, activation='snake', lrate=5e-4,
+                                 netchunk=1024 * 64, normalize_type=1, p_topk=1)
+    torch.manual_seed(4)
+    monkeypatch.delenv("NPP_B200_EMBED", raising=False)
+    kw, _, _, _, _, embedder, embedder_periodic = create_npp_net(args, torch.Tensor(ANGLES), torch.Tensor(PERIODS), RES,
+                                                                 percep_net=None, is_search=True)
+    model = kw["network_fn"]
+    rng = np.random.default_rng(1)
+    coords = torch.from_numpy(np.stack([rng.integers(0, RES[0], 500), rng.integers(0, RES[1], 500)], 1).astype(np.float32))
+    with torch.no_grad():
+        ref = model(embedder.embed(coords.clone()), embedder_periodic.embed(coords)).cpu().numpy()
+    monkeypatch.setenv("NPP_B200_EMBED", "table")
+    pos = embedder.embed(coords.clone().cuda())
+    per = embedder_periodic.embed(coords.cuda())
+    assert pos.shape == (500, 42) and per.shape == (500, 20)
+    table = (embedder_periodic.cos_t, embedder_periodic.sin_t, embedder_periodic.period)
+    pos_ref, per_ref = O.encode_search(coords.numpy(), table, embedder.freqs, RES)
+    np.testing.assert_allclose(per.cpu().numpy(), per_ref, atol=2e-6)
+    np.testing.assert_allclose(pos.cpu().numpy(), pos_ref, atol=2e-5)       # torch sin/cos on the GPU vs numpy
+    with torch.no_grad():
+        out = model(pos, per).cpu().numpy()
+    assert rel(out, ref) < 1e-3
