@@ -171,6 +171,12 @@ int npp_fit_run(NppPlan* plan, const float* coords_all, const float* target_all,
                 int64_t iters, float lrate, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
                 int64_t first_step, float* losses, void* stream);
 
+/* Patch crops of GridPatchSampler (models/sampler.py:262-296; utils/extract_glimpse.py:7-79 with mode='nearest',
+ * padding_mode='zeros'): out[m, c, i, j] = img[rows[m, i], cols[m, j], c], zero outside the image.  img: device
+ * [img_h, img_w, channels] fp32; rows [m, h], cols [m, w] device int64 index tables; out: device [m, channels, h, w]. */
+int npp_gather_windows(const float* img, int32_t img_h, int32_t img_w, int32_t channels, const int64_t* rows,
+                       const int64_t* cols, int64_t m, int32_t h, int32_t w, float* out, void* stream);
+
 /* Optional input pipelining for npp_train_step (the data-loader analogue of NPP_completion/train.py:164-181, where
  * the reference gathers the next batch's rows of the encoding table): encodes `coords` of a FUTURE step into the
  * plan's second encoding buffer on an internal stream.  It waits for everything already enqueued on `stream`

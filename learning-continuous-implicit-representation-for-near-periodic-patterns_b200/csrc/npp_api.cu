@@ -1343,6 +1343,23 @@ int npp_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
   return 0;
 }
 
+int npp_gather_windows(const float* img, int32_t img_h, int32_t img_w, int32_t channels, const int64_t* rows,
+                       const int64_t* cols, int64_t m, int32_t h, int32_t w, float* out, void* stream) {
+  if (!img || !rows || !cols || !out) return fail("npp_gather_windows: null argument");
+  if (img_h <= 0 || img_w <= 0 || channels <= 0 || h <= 0 || w <= 0) return fail("npp_gather_windows: sizes must be positive");
+  if (m <= 0) return 0;
+  const long long total = (long long)m * channels * h * w;
+  if (m > (1LL << 24) || total > (1LL << 40)) return fail("npp_gather_windows: too many windows");
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  static_assert(sizeof(long long) == sizeof(int64_t), "index tables are int64");
+  npp_gather_windows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      img, img_h, img_w, channels, reinterpret_cast<const long long*>(rows), reinterpret_cast<const long long*>(cols),
+      (int)m, h, w, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int npp_l2_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, float* loss, float* grad_x,
                    void* stream) {
   if (!x || !y || !loss || !grad_x) return fail("npp_l2_fwd_bwd: null argument");

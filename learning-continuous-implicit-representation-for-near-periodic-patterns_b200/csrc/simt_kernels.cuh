@@ -409,6 +409,28 @@ __global__ void __launch_bounds__(256) npp_head_render_kernel(const __half* __re
   }
 }
 
+// Patch crops of the sampler (models/sampler.py:262-296 via utils/extract_glimpse.py with mode='nearest',
+// padding_mode='zeros'): out[m, c, i, j] = img[rows[m, i], cols[m, j], c], zero where an index falls outside the image.
+// img is the [H, W, C] image as the train scripts hold it; rows / cols are the per-window index tables (contiguous for
+// integer centroids, grid_sample's nearest rounding for fractional ones).  Pure data movement: bit-exact.
+__global__ void __launch_bounds__(256) npp_gather_windows_kernel(const float* __restrict__ img, int H, int W, int C,
+                                                                 const long long* __restrict__ rows,
+                                                                 const long long* __restrict__ cols, int M, int h, int w,
+                                                                 float* __restrict__ out) {
+  const long long total = (long long)M * C * h * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w);
+    const int i = (int)((idx / w) % h);
+    const int c = (int)((idx / ((long long)w * h)) % C);
+    const int m = (int)(idx / ((long long)w * h * C));
+    const long long r = rows[(long long)m * h + i], q = cols[(long long)m * w + j];
+    float v = 0.f;
+    if (r >= 0 && r < H && q >= 0 && q < W) v = img[((size_t)r * W + (size_t)q) * C + c];
+    out[idx] = v;
+  }
+}
+
 // Power-of-two gradient scale so that fp16 deltas sit in the middle of the half range:
 // amax * scale == 2^10 (rounded down to a power of two).  Exact to undo in fp32.
 __device__ __forceinline__ float npp_grad_scale(float amax) {

@@ -52,8 +52,20 @@ def _is_integral(t):
 
 
 def _gather_window(img_nchw, rows, cols):
-    """img [1,C,H,W]; rows [M,h], cols [M,w] int64 index tables -> [M,C,h,w], zeros outside the image."""
+    """img [1,C,H,W]; rows [M,h], cols [M,w] int64 index tables -> [M,C,h,w], zeros outside the image.
+    CUDA images held as [1,H,W,C] fp32 (how the train scripts pass them) are cropped by one kernel
+    (npp_gather_windows); anything else by the equivalent torch indexing."""
     _, C, H, W = img_nchw.shape
+    if img_nchw.is_cuda and img_nchw.dtype == torch.float32 and rows.shape[0] > 0 and \
+            img_nchw.permute(0, 2, 3, 1).is_contiguous():
+        from ._core import native as _nat
+        rows = rows.to(img_nchw.device, torch.int64).contiguous()
+        cols = cols.to(img_nchw.device, torch.int64).contiguous()
+        out = torch.empty(rows.shape[0], C, rows.shape[1], cols.shape[1], device=img_nchw.device)
+        _nat.check(_nat.lib().npp_gather_windows(img_nchw.data_ptr(), H, W, C, rows.data_ptr(), cols.data_ptr(),
+                                                 rows.shape[0], rows.shape[1], cols.shape[1], out.data_ptr(),
+                                                 _nat.current_stream()))
+        return out
     ok = ((rows >= 0) & (rows < H))[:, :, None] & ((cols >= 0) & (cols < W))[:, None, :]
     out = img_nchw[0][:, rows.clamp(0, H - 1)[:, :, None], cols.clamp(0, W - 1)[:, None, :]]   # [C,M,h,w]
     return (out * ok[None].to(out.dtype)).permute(1, 0, 2, 3).contiguous()
