@@ -173,9 +173,10 @@ class GridPatchSampler():
             total = s1[None, None, :] * self.permutation1[..., None] + s2[None, None, :] * self.permutation2[..., None]
             pool = (cent[:, None, None, :] + total[None]).reshape(-1, 2)                       # (sample, i, j) order
             in_bound = (pool[:, 0] > 0) & (pool[:, 0] < self.height - 1) & (pool[:, 1] > 0) & (pool[:, 1] < self.width - 1)
-            pool = pool[in_bound]
-            indicator = self.coord_batch_indicator[:N * total.shape[0] * total.shape[1]][in_bound]
-            distance_all = self.permute_distance[:N * total.shape[0] * total.shape[1]][in_bound]
+            sel = torch.nonzero(in_bound).squeeze(1)        # one host round trip for the three selections below
+            pool = pool[sel]
+            indicator = self.coord_batch_indicator[:N * total.shape[0] * total.shape[1]][sel]
+            distance_all = self.permute_distance[:N * total.shape[0] * total.shape[1]][sel]
             integral = _is_integral(pool)
             if integral:      # windows are contiguous: O(1) unknown-pixel counts from the summed-area table
                 r0 = pool[:, 0].long() - hh
@@ -185,7 +186,7 @@ class GridPatchSampler():
                 rows = _nearest_index(pool[:, 0], 2 * hh, self.height)
                 cols = _nearest_index(pool[:, 1], 2 * wh, self.width)
                 unknown = (_gather_window(self.mask, rows, cols) < 0.5).sum(dim=[1, 2, 3])
-            keep = ~(unknown > (hh * wh * 4 * invalid_ratio))
+            keep = torch.nonzero(~(unknown > (hh * wh * 4 * invalid_ratio))).squeeze(1)
             pool, indicator, distance_all = pool[keep], indicator[keep], distance_all[keep]
 
             sel_cent, weight_topks = [], []
