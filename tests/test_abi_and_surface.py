@@ -66,6 +66,10 @@ def test_reference_signatures():
     assert names(NPP_Net_top1.__init__)[1:] == ["input_ch_periodic", "freq_scales", "freq_offsets", "angle_offsets",
                                                 "D", "W", "freq_nerf", "output_ch", "skips", "activation"]
     assert names(NPP_Net.forward)[1:] == ["x", "x_periodic"]
+    from models.networks import NPP_Net_light
+    assert names(NPP_Net_light.__init__)[1:] == ["input_ch_periodic", "freq_scales", "freq_offsets", "angle_offsets",
+                                                 "D", "W", "input_ch", "output_ch", "skips", "activation"]
+    assert names(NPP_Net_light.forward)[1:] == ["x", "x_periodic"]
     assert names(create_npp_net) == ["args", "selected_angles", "selected_periods", "res", "percep_net", "is_search",
                                      "style_net"]
     assert names(render) == ["select_coords_emb", "select_coords_emb_periodic", "args", "network_query_fn",
@@ -122,3 +126,23 @@ def test_no_cpu_fallback():
                  freq_scales=[1], freq_offsets=[0, -1, 1, 0.5, -0.5], angle_offsets=[0])
     with pytest.raises(npp_b200._native.NppError):
         NPP_Net_top1(22, [1], [0, -1, 1, 0.5, -0.5], [0], D=8, W=512, freq_nerf=21, activation='snake')
+
+
+def test_search_mode_embedders_coords_mode_shapes():
+    """get_embedder(..., is_search=True) (models/embedder.py:76-95): 42 / 20 columns, coordinates passed through in the
+    default 'coords' embed mode (NPP_Net_light encodes inside the kernels)."""
+    import torch
+    _models()
+    from models.embedder import get_embedder
+    torch.manual_seed(0)
+    emb, d = get_embedder(10, 0, (64, 48), is_search=True)
+    per, dp = get_embedder(10, 0, (64, 48), selected_angles=torch.tensor([90.0, 180.0]),
+                           selected_periods=torch.tensor([12.0, 11.0]), freq_scales=[1],
+                           freq_offsets=[0, -1, 1, 0.5, -0.5], angle_offsets=[0], is_search=True)
+    assert (d, dp) == (42, 20) and emb.is_search and not per.include_input
+    coords = torch.tensor([[0.0, 0.0], [5.0, 7.0]])
+    assert torch.equal(emb.embed(coords.clone()), coords) and torch.equal(per.embed(coords), coords)
+    # same default-RNG consumption as the reference: one torch.normal(size=(multires, 1)) per positional embedder
+    torch.manual_seed(0)
+    ref_draw = torch.normal(mean=0.0, std=1.0, size=(10, 1)) * 10
+    assert torch.equal(emb.freq_bands, ref_draw)
