@@ -2,13 +2,13 @@
 
 This is a plain-numpy (fp32) restatement of the reference's algorithm for the path
 ``encoding -> MLP forward -> sigmoid + masked MSE -> backward -> Adam``.  It exists to check
-the CUDA kernels; nothing in the product package imports it (only tests/, bench.py's
-cpu_baseline / --impl reference legs and __graft_entry__.smoke() do).
+the CUDA kernels; nothing in the product package imports it (only tests/, the cpu_baseline /
+--impl reference legs of bench.py and tools/bench_search_fits.py, and __graft_entry__.smoke() do).
 
 Pinning: the reference ships no tests or golden vectors for this path, so
 the oracle is pinned against the reference itself: tests/golden/make_golden.py imports the
 reference modules from /root/reference, runs them on seeded inputs and stores the results in
-tests/golden/*.npz; tests/test_oracle_golden.py checks every function below against them.
+tests/golden/*.npz (make_golden_light.py for the search-stage network and encoders); tests/test_oracle_golden.py checks every function below against them.
 
 Every function cites the reference file:line (relative to the reference root) it restates.
 The backward pass is derived by hand (the reference relies on torch autograd), which makes it an
