@@ -49,6 +49,18 @@ def render(select_coords_emb, select_coords_emb_periodic, args, network_query_fn
     assert False, 'Wrong normalize type'
 
 
+def weights_init_normal(m):
+    """Initialiser the reference applies when activation == 'relu' (models/helpers.py:63-71,139-140): N(0, 0.02) for
+    convolution weights, N(1, 0.02) / 0 for BatchNorm2d.  It matches by class name, so the Linear layers of NPP-Net keep
+    PyTorch's default initialisation -- applying it to the fused networks is a no-op, as it is in the reference."""
+    kind = type(m).__name__
+    if "Conv" in kind:
+        nn.init.normal_(m.weight.data, 0.0, 0.02)
+    elif "BatchNorm2d" in kind:
+        nn.init.normal_(m.weight.data, 1.0, 0.02)
+        nn.init.constant_(m.bias.data, 0.0)
+
+
 def create_npp_net(args, selected_angles, selected_periods, res, percep_net, is_search=False, style_net=None):
     """Same 7-tuple as the reference (models/helpers.py:75-175).  The model is never wrapped in nn.DataParallel:
     this framework runs one process per GPU (data parallelism is an NCCL all-reduce of the gradient arena)."""
@@ -80,6 +92,8 @@ def create_npp_net(args, selected_angles, selected_periods, res, percep_net, is_
         else:
             model = NPP_Net_top1(input_ch_periodic=input_ch_periodics[:1].sum(), **common)
 
+    if args.activation == 'relu':
+        model.apply(weights_init_normal)
     grad_vars = list(model.parameters())
     if adaptive_pix is not None:
         grad_vars += list(adaptive_pix.parameters())

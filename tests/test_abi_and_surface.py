@@ -83,7 +83,8 @@ def test_reference_signatures():
     # names the reference train scripts pick up through their star imports
     import models.helpers as H
     import models.sampler as S
-    for n in ("torch", "np", "nn", "F", "os", "device", "adaptive_pix", "create_npp_net", "render", "img2mse"):
+    for n in ("torch", "np", "nn", "F", "os", "device", "adaptive_pix", "create_npp_net", "render", "img2mse",
+              "weights_init_normal", "batchify", "run_network"):
         assert hasattr(H, n), n
     for n in ("np", "F", "torch", "GridPatchSampler", "extract_glimpse"):
         assert hasattr(S, n), n
@@ -146,3 +147,15 @@ def test_search_mode_embedders_coords_mode_shapes():
     torch.manual_seed(0)
     ref_draw = torch.normal(mean=0.0, std=1.0, size=(10, 1)) * 10
     assert torch.equal(emb.freq_bands, ref_draw)
+
+
+def test_weights_init_normal_touches_conv_and_batchnorm_only():
+    import torch
+    _models()
+    from models.helpers import weights_init_normal
+    torch.manual_seed(0)
+    lin, conv, bn = torch.nn.Linear(4, 4), torch.nn.Conv2d(2, 2, 3), torch.nn.BatchNorm2d(3)
+    before = lin.weight.detach().clone()
+    torch.nn.Sequential(lin, conv, bn).apply(weights_init_normal)
+    assert torch.equal(lin.weight, before)                       # Linear keeps PyTorch's default init
+    assert conv.weight.abs().max() < 0.2 and abs(bn.weight.mean().item() - 1.0) < 0.1 and bn.bias.abs().max() == 0
