@@ -16,6 +16,7 @@
 //    split-K over row ranges with deterministic fp32 partial slabs.
 #pragma once
 #include "ptx_sm100.cuh"
+#include "grad_scale.cuh"
 
 namespace npp {
 
@@ -49,6 +50,9 @@ enum : int {
   EPI_SNAKE = 1,      // z = acc + bias; out0 = z + sin^2 z; out1 = 1 + sin 2z   (activations.py:34-35)
   EPI_DGRAD_MUL = 2,  // out0 = acc * mul  (mul = stored snake derivative); colsum += out0
   EPI_DGRAD = 3,      // out0 = acc; colsum += out0
+  // Last forward layer of a fused train step: snake, then the RGB head, sigmoid + masked MSE and the head backward
+  // without leaving the CTA; out0 = delta of this layer (fp16, scaled), nothing else is written per row.
+  EPI_SNAKE_HEAD = 4,
 };
 
 // One dense layer (forward) or one dgrad GEMM of the chain; lives in GLOBAL memory (array of ops).
@@ -95,7 +99,7 @@ __host__ __device__ constexpr int fwd_perm(int p) { return (p & ~3) | ((p & 1) <
 
 // The scalar part of an op, copied into the kernel parameters (constant bank): the roles read it at every op
 // boundary, and a dependent chain of global loads there (~1500 clocks) is exactly where the pipeline has no slack.
-constexpr int MAX_CHAIN_OPS = 16;
+constexpr int MAX_CHAIN_OPS = 24;   // forward (12) + dgrad (11) of the joint model in one launch
 struct OpScalars {
   int nseg, tiles_n, epi, fwd_in, fwd_out, kb_per_tile;
   int kblocks[2], a_k0[2], b_k0[2], b_row0[2], a_src[2];
@@ -105,6 +109,22 @@ struct OpScalars {
   float* colsum;
   float* out_f32;
   unsigned long long desc_hi;
+};
+
+// Arguments of the EPI_SNAKE_HEAD epilogue (one head per chain).  Reference: rgb_linear (models/networks.py:94),
+// sigmoid (models/helpers.py:55-56), img2mse 'l2' with mask (models/mse_calculator.py:13-27) and their autograd.
+struct HeadArgs {
+  const float* w;         // rgb_linear.weight [3, width] fp32 (master copy)
+  const float* b;         // rgb_linear.bias [3]
+  const float* target;    // [M, 3]
+  const float* mask;      // [M] or nullptr
+  float* logits;          // optional [M, 3]
+  float* head_acc;        // [3 * width + 3]: dW_rgb, db_rgb (unscaled fp32 atomics)
+  float* loss_acc;        // scalar: sum of the squared masked residuals * inv_count
+  const unsigned int* amax_prev;  // max |dL/dlogit| / inv_count of the PREVIOUS step (float bits, 0 = unknown)
+  unsigned int* amax_next;        // same of this step (atomicMax)
+  float inv_count;        // 1 / (3 * n_norm)
+  int width;              // reference in_features of rgb_linear (128 or 256)
 };
 
 // A chain = ops executed in order for every 128-row stripe; op i may read what ops < i wrote for the
@@ -122,6 +142,8 @@ struct ChainParams {
   int zero_n;           //   whose encoding was prefetched: the encode kernel, which normally does this, did not run)
   float* zero_b;
   int relu;             // host side only: selects the npp_gemm_kmajor<CLUSTER, true> instantiation
+  HeadArgs head;        // used by the EPI_SNAKE_HEAD op, if the chain has one
+  int pdl;              // launched with programmatic stream serialization: wait for the previous kernel after the prologue
 };
 
 struct WgUnit {
@@ -512,6 +534,240 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
 }
 
 // ---------------------------------------------------------------------------------
+// EPI_SNAKE_HEAD: epilogue of the LAST dense layer (pos_linears.0, one 256-column tile) of a fused train step.  The
+// accumulator never leaves the CTA as an activation: the snake output feeds the RGB head (models/networks.py:94), the
+// sigmoid (models/helpers.py:55-56) and the masked 'l2' loss (models/mse_calculator.py:13-27) right here, and the
+// backward of all three produces this layer's delta, which is staged exactly like any other op's output (TMA store
+// to the delta buffer + on-chip forwarding into the first dgrad GEMM).  Two passes over the TMEM accumulator:
+//   1. h = snake(z) rounded to fp16 (what the stand-alone head kernel would read back), partial logits over this
+//      warp's 128 columns; the two warps of a lane quadrant swap their partials through their aux boxes;
+//      loss, dL/dlogit, max |dL/dlogit|, db_rgb;
+//   2. h and snake'(z) again, delta = (g . W_rgb) * snake'(z) * scale (fp16), dW_rgb and the layer's bias gradient
+//      as column sums.
+// Neither h_P nor its derivative is written to global memory (the stand-alone path wrote and re-read 2 x 8 MB).
+template <bool RELU>
+__device__ __forceinline__ void epilogue_head_tile(const KmajorParams& p, const EpiArgs ea, const HeadArgs& hd,
+                                                   const GemmSmem& s, uint32_t tmem_acc, int m0, int M, int warp,
+                                                   int lane, uint64_t* tfull, uint32_t acc_phase, uint32_t& seq,
+                                                   uint32_t& deferred_seq) {
+  constexpr int NSUB = BN / EPI_COLS;
+  const int q = warp & 3;
+  const int e = (warp - 2) >> 2;
+  const int lane_base = q * 32;
+  uint8_t* aux = s.epi + EPI_OUT_BYTES + (warp - 2) * EPI_BUF_BYTES;
+  const uint8_t* aux_peer = s.epi + EPI_OUT_BYTES + ((warp - 2) ^ 4) * EPI_BUF_BYTES;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+  const int row0 = m0 + lane_base;
+  const int row = row0 + lane;
+  const bool row_ok = row < M;
+  const bool warp_ok = row0 < M;
+  const int width = hd.width;
+  const uint32_t tlane = tmem_acc + (static_cast<uint32_t>(lane_base) << 16);
+  // inputs of the loss: requested before the accumulator is waited for
+  float tg[3] = {0.f, 0.f, 0.f};
+  float mk = 1.0f;
+  if (row_ok) {
+    tg[0] = __ldg(hd.target + 3 * (size_t)row);
+    tg[1] = __ldg(hd.target + 3 * (size_t)row + 1);
+    tg[2] = __ldg(hd.target + 3 * (size_t)row + 2);
+    if (hd.mask != nullptr) mk = __ldg(hd.mask + row);
+  }
+  const float rb0 = __ldg(hd.b), rb1 = __ldg(hd.b + 1), rb2 = __ldg(hd.b + 2);
+  const float scale = npp_grad_scale(npp_step_amax(hd.amax_prev, hd.inv_count));
+  // This warp's aux box carries its partial logits to the other warp of the quadrant: every bulk store that read the
+  // box (the snake derivative of an earlier layer) and every earlier store from the output staging has finished reading.
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
+  mbar_wait(tfull, acc_phase);
+  tc_fence_after();
+
+  // ---- pass 1: partial logits over columns [128 e, 128 e + 128)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; ++blk) {
+    const int col = e * 128 + blk * 32;
+    if (col >= width) break;   // padded half of a 128-wide layer: zero weights, nothing to add
+    uint32_t raw[32];
+    tmem_ld_32x32(tlane + col, raw);
+    tmem_ld_wait();
+    const float4* w0p = reinterpret_cast<const float4*>(hd.w + col);
+    const float4* w1p = reinterpret_cast<const float4*>(hd.w + width + col);
+    const float4* w2p = reinterpret_cast<const float4*>(hd.w + 2 * width + col);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w0 = __ldg(w0p + (i >> 2)), w1 = __ldg(w1p + (i >> 2)), w2 = __ldg(w2p + (i >> 2));
+      float z[4];
+      z[0] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, ea.bias4.x, blk * 8 + (i >> 2));
+      z[1] = __uint_as_float(raw[i + 1]) + __shfl_sync(0xffffffffu, ea.bias4.y, blk * 8 + (i >> 2));
+      z[2] = __uint_as_float(raw[i + 2]) + __shfl_sync(0xffffffffu, ea.bias4.z, blk * 8 + (i >> 2));
+      z[3] = __uint_as_float(raw[i + 3]) + __shfl_sync(0xffffffffu, ea.bias4.w, blk * 8 + (i >> 2));
+      float h[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (RELU) h[k] = fmaxf(z[k], 0.f);
+        else h[k] = fmaf(-0.5f, __cosf(z[k] + z[k]), z[k] + 0.5f);
+      }
+      const float2 f0 = unpack_h2(pack_h2(h[0], h[1])), f1 = unpack_h2(pack_h2(h[2], h[3]));
+      a0 = fmaf(f0.x, w0.x, fmaf(f0.y, w0.y, fmaf(f1.x, w0.z, fmaf(f1.y, w0.w, a0))));
+      a1 = fmaf(f0.x, w1.x, fmaf(f0.y, w1.y, fmaf(f1.x, w1.z, fmaf(f1.y, w1.w, a1))));
+      a2 = fmaf(f0.x, w2.x, fmaf(f0.y, w2.y, fmaf(f1.x, w2.z, fmaf(f1.y, w2.w, a2))));
+    }
+  }
+  *reinterpret_cast<float4*>(aux + lane * 16) = make_float4(a0, a1, a2, 0.f);
+  named_bar_sync(1 + q, 64);
+  const float4 o = *reinterpret_cast<const float4*>(aux_peer + lane * 16);
+  named_bar_sync(1 + q, 64);   // both boxes have been read before either is reused
+  // (fp32 addition commutes: both warps of the quadrant hold bit-identical logits)
+  const float z0 = (a0 + o.x) + rb0, z1 = (a1 + o.y) + rb1, z2 = (a2 + o.z) + rb2;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  {
+    const float wgt = mk + (1.0f - mk) * 0.3f;
+    const float y0 = 1.0f / (1.0f + expf(-z0)), y1 = 1.0f / (1.0f + expf(-z1)), y2 = 1.0f / (1.0f + expf(-z2));
+    const float d0 = (y0 - tg[0]) * wgt, d1 = (y1 - tg[1]) * wgt, d2 = (y2 - tg[2]) * wgt;
+    float lsum = 0.f;
+    if (row_ok) {
+      g0 = 2.0f * d0 * wgt * hd.inv_count * y0 * (1.0f - y0);
+      g1 = 2.0f * d1 * wgt * hd.inv_count * y1 * (1.0f - y1);
+      g2 = 2.0f * d2 * wgt * hd.inv_count * y2 * (1.0f - y2);
+      lsum = d0 * d0 + d1 * d1 + d2 * d2;
+    }
+    if (e == 0) {   // one warp of the quadrant accounts for the row
+      if (hd.logits != nullptr && row_ok) {
+        hd.logits[3 * (size_t)row] = z0;
+        hd.logits[3 * (size_t)row + 1] = z1;
+        hd.logits[3 * (size_t)row + 2] = z2;
+      }
+      float lmax = fmaxf(fabsf(g0), fmaxf(fabsf(g1), fabsf(g2)));
+      float s0 = g0, s1 = g1, s2 = g2;
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, sft);
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, sft));
+        s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
+      }
+      if (lane == 0 && warp_ok) {
+        atomicAdd(hd.loss_acc, lsum * hd.inv_count);
+        if (lmax > 0.f) atomicMax(hd.amax_next, __float_as_uint(lmax / hd.inv_count));
+        atomicAdd(hd.head_acc + 3 * width, s0);      // db_rgb
+        atomicAdd(hd.head_acc + 3 * width + 1, s1);
+        atomicAdd(hd.head_acc + 3 * width + 2, s2);
+      }
+    }
+  }
+
+  // ---- pass 2: delta of this layer, dW_rgb, bias gradient
+#pragma unroll 1
+  for (int sub = 2 * e; sub < 2 * e + 2; ++sub) {
+    uint8_t* obuf = s.epi + sub * (4 * EPI_BUF_BYTES) + q * EPI_BUF_BYTES;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int col = sub * EPI_COLS + half * 32;
+      const bool col_ok = col < width;
+      uint32_t raw[32];
+      tmem_ld_32x32(tlane + col, raw);
+      tmem_ld_wait();
+      const int src0 = (sub - 2 * e) * 16 + half * 8;
+      const float4* w0p = reinterpret_cast<const float4*>(hd.w + col);
+      const float4* w1p = reinterpret_cast<const float4*>(hd.w + width + col);
+      const float4* w2p = reinterpret_cast<const float4*>(hd.w + 2 * width + col);
+      uint32_t hp[16], dl[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 w0 = col_ok ? __ldg(w0p + (i >> 2)) : zero4;
+        const float4 w1 = col_ok ? __ldg(w1p + (i >> 2)) : zero4;
+        const float4 w2 = col_ok ? __ldg(w2p + (i >> 2)) : zero4;
+        float z[4];
+        z[0] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, ea.bias4.x, src0 + (i >> 2));
+        z[1] = __uint_as_float(raw[i + 1]) + __shfl_sync(0xffffffffu, ea.bias4.y, src0 + (i >> 2));
+        z[2] = __uint_as_float(raw[i + 2]) + __shfl_sync(0xffffffffu, ea.bias4.z, src0 + (i >> 2));
+        z[3] = __uint_as_float(raw[i + 3]) + __shfl_sync(0xffffffffu, ea.bias4.w, src0 + (i >> 2));
+        float h[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (RELU) {
+            h[k] = fmaxf(z[k], 0.f);
+            d[k] = z[k] > 0.f ? 1.f : 0.f;
+          } else {
+            const float w = z[k] + z[k];
+            h[k] = fmaf(-0.5f, __cosf(w), z[k] + 0.5f);
+            d[k] = 1.0f + __sinf(w);
+          }
+        }
+        hp[i >> 1] = pack_h2(h[0], h[1]);
+        hp[(i >> 1) + 1] = pack_h2(h[2], h[3]);
+        // the derivative rounded to fp16, as the stand-alone path stores it between forward and backward
+        const float2 dd0 = unpack_h2(pack_h2(d[0], d[1])), dd1 = unpack_h2(pack_h2(d[2], d[3]));
+        const float t0 = fmaf(g0, w0.x, fmaf(g1, w1.x, g2 * w2.x));
+        const float t1 = fmaf(g0, w0.y, fmaf(g1, w1.y, g2 * w2.y));
+        const float t2 = fmaf(g0, w0.z, fmaf(g1, w1.z, g2 * w2.z));
+        const float t3 = fmaf(g0, w0.w, fmaf(g1, w1.w, g2 * w2.w));
+        dl[i >> 1] = pack_h2(t0 * dd0.x * scale, t1 * dd0.y * scale);
+        dl[(i >> 1) + 1] = pack_h2(t2 * dd1.x * scale, t3 * dd1.y * scale);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = static_cast<uint32_t>(half * 4 + j);
+        *reinterpret_cast<uint4*>(obuf + row_off + ((c ^ sw) << 4)) =
+            make_uint4(dl[4 * j], dl[4 * j + 1], dl[4 * j + 2], dl[4 * j + 3]);
+      }
+      float v[32];
+      if (ea.colsum != nullptr) {   // bias gradient of this layer: column sums of the fp16-rounded deltas
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 r = unpack_h2(dl[i]);
+          v[2 * i] = r.x;
+          v[2 * i + 1] = r.y;
+        }
+        const float cs = warp_colsum32(v, lane);
+        if (warp_ok) atomicAdd(ea.colsum + col + lane, cs);
+      }
+      if (col_ok) {                 // dW_rgb[c, col + j] = sum over rows of g_c * h[row, col + j]
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          const float gc = c == 0 ? g0 : (c == 1 ? g1 : g2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 r = unpack_h2(hp[i]);
+            v[2 * i] = gc * r.x;
+            v[2 * i + 1] = gc * r.y;
+          }
+          const float cs = warp_colsum32(v, lane);
+          if (warp_ok) atomicAdd(hd.head_acc + c * width + col + lane, cs);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (ea.fwd_out) {
+        uint64_t* afull = &s.afull[sub];
+        if (ea.leader) mbar_arrive(afull);
+        else mbar_arrive_remote_relaxed(afull, 0);
+      }
+      if (warp_ok) {
+        tma_store_2d(&p.tmOut0, obuf, sub * EPI_COLS, row0);
+        bulk_commit();
+      }
+      if (deferred_seq != 0) {
+        if (warp_ok) bulk_wait1();
+        publish_progress(&s.prog[warp - 2], deferred_seq);
+      }
+    }
+    deferred_seq = 0;
+  }
+  seq += NSUB;
+  if (lane == 0) {   // the first dgrad op's second tile (if any) reloads this delta from global memory
+    bulk_wait0();
+    publish_progress(&s.prog[warp - 2], seq);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------
 // CLUSTER == 1: every CTA is on its own (UMMA cta_group::1, M = 128).
 // CLUSTER == 2: CTA pairs (thread-block cluster of 2 = one TPC) run cta_group::2 UMMAs with M = 256: CTA r owns
 //   row stripe 2p + r, keeps its own A tile and HALF of every weight tile in its shared memory, and the leader
@@ -526,11 +782,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   const GemmSmem s = carve_smem_t<NST, EPI_STAGE_BYTES, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
+  // Programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) may overlap the tail of the
+  // previous kernel in the stream; nothing below may (a no-op for an ordinary launch).
+  grid_dependency_wait();
   if (blockIdx.x == 0 && cp.zero_n > 0) {
     for (int i = threadIdx.x; i < cp.zero_n; i += blockDim.x) cp.zero_a[i] = 0.f;
     if (threadIdx.x == 0 && cp.zero_b != nullptr) *cp.zero_b = 0.f;
   }
-  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
   // every CTA of a pair runs the same number of stripe iterations (phantom stripes load zeros, store nothing)
   const int stripe_iters = (cp.tiles_m + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
@@ -547,6 +806,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
       const int gi = min(STRIPE_GROUP, stripe_iters - si);
       for (int oi = 0; oi < cp.n_ops; ++oi) {
         const KmajorParams& p = cp.ops[oi];
+        // the next kernel of the stream may start its prologue while this CTA works on its last op
+        if (oi == cp.n_ops - 1 && si + gi >= stripe_iters && lane == 0) grid_launch_dependents();
         if (lane == 0) {
           for (int i = 0; i < cp.sc[oi].nseg; ++i) {
             tma_prefetch_desc(&p.tmA[i]);
@@ -799,6 +1060,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
                 epilogue_tile<EPI_SNAKE, RELU>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase, seq,
                                          last, deferred, dbgp, fwd_phase, mul_ready);
                 break;
+              case EPI_SNAKE_HEAD:
+                epilogue_head_tile<RELU>(p, ea, cp.head, s, tacc, m0, cp.M, warp, lane, &s.tfull[acc], acc_phase, seq,
+                                         deferred);
+                break;
               case EPI_DGRAD_MUL:
                 epilogue_tile<EPI_DGRAD_MUL, false>(p, ea, s, tacc, m0, n0, cp.M, warp, lane, ld_phase, &s.tfull[acc], acc_phase,
                                              seq, last, deferred, dbgp, fwd_phase, mul_ready);
@@ -845,6 +1110,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4>(s, warp);
+  grid_dependency_wait();   // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
   const int kb_total = (p.rows + BK - 1) / BK;
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
   const bool leader = crank == 0;
@@ -887,6 +1153,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
         ps.advance();
       }
     }
+    if (lane == 0) grid_launch_dependents();   // all loads of this CTA are issued: the next kernel may start its prologue
   } else if (warp == 1) {
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(BM * CLUSTER, BN, 1, 1);

@@ -144,6 +144,12 @@ struct NppPlan {
   long long slab_stride = 0;
   float* acc = nullptr;  // [bias accumulators | head accumulators | amax | loss scratch]
   long long acc_floats = 0, headacc_off = 0, amax_off = 0;
+  long long acc_zero_floats = 0;   // [0, acc_zero_floats) are the per-step accumulators; behind them: state that survives a step
+  long long ring_off = 0;          // max|g| ring of the fused step (3 slots) and its loss accumulator (slot 3)
+  long long step_seq = 0;          // fused steps run so far (selects the ring slots)
+  bool acc_clean = true;           // the per-step accumulators are all zero (the fused step's update kernel leaves them so)
+  int pdl = 1;                     // programmatic dependent launch between the kernels of a fused step
+  bool fused_step = true;          // npp_train_step runs forward + head + backward as one chain (NPP_SPLIT_STEP=1: r01 path)
   float* g_buf = nullptr;       // [max_rows,3] grad wrt logits (fused path)
   unsigned int* d_barrier = nullptr;  // {arrivals, generation} of the fused head kernel's grid barrier
   int head_fused_blocks = 0;          // co-resident blocks of npp_head_fused_kernel (0: not usable)
@@ -155,6 +161,8 @@ struct NppPlan {
   KmajorParams* d_fwd_ops = nullptr;    // forward chain (one op per dense layer)
   KmajorParams* d_fwd_ops_alt = nullptr;  // same, reading the second encoding set
   KmajorParams* d_dgrad_ops = nullptr;  // dgrad chain
+  KmajorParams* d_step_ops = nullptr;      // fused train step: forward ops (last one with the head epilogue) + dgrad ops
+  KmajorParams* d_step_ops_alt = nullptr;  // same, reading the second encoding set
   WgUnit* d_units = nullptr;
   int n_units = 0;
   int splits_max = 0;       // slabs allocated
@@ -183,7 +191,7 @@ struct NppPlan {
   std::vector<CUtensorMap> map_a;   // per buffer, box {64,128}: K-major A operand
   std::vector<CUtensorMap> map_mn;  // per buffer, box {64,64}: MN-major wgrad operand
   std::vector<CUtensorMap> map_ep;  // per buffer, box {64,32}: per-warp epilogue store / load
-  std::vector<KmajorParams> fwd_params, fwd_params_alt, dgrad_params;
+  std::vector<KmajorParams> fwd_params, fwd_params_alt, dgrad_params, step_params, step_params_alt;
   WgradParams wg_params, wg_params_alt;
   std::vector<int> wg_src_bufs;  // buffer ids behind WgradParams::maps[nl + k]
   int launches = 0;
@@ -445,7 +453,9 @@ static int alloc_plan_memory(NppPlan* p) {
   // accumulators: [bias acc (bg) | head acc (3*hw+3) | amax | loss]
   p->headacc_off = (bg + 3) / 4 * 4;
   p->amax_off = p->headacc_off + (3 * p->head_width + 3 + 3) / 4 * 4;
-  p->acc_floats = p->amax_off + 4;
+  p->acc_zero_floats = p->amax_off + 4;
+  p->ring_off = p->acc_zero_floats;
+  p->acc_floats = p->ring_off + 4;
   CK(cudaMalloc(&p->acc, p->acc_floats * sizeof(float)));
   CK(cudaMemset(p->acc, 0, p->acc_floats * sizeof(float)));
   CK(cudaMalloc(&p->g_buf, (size_t)R * 3 * sizeof(float)));
@@ -543,6 +553,8 @@ static int alloc_plan_memory(NppPlan* p) {
   CK(cudaEventCreateWithFlags(&p->coop_evt, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&p->pref[i].done, cudaEventDisableTiming));
   CK(cudaMalloc(&p->d_dgrad_ops, (p->dgrads.size() + 1) * sizeof(KmajorParams)));
+  CK(cudaMalloc(&p->d_step_ops, (p->layers.size() + p->dgrads.size()) * sizeof(KmajorParams)));
+  CK(cudaMalloc(&p->d_step_ops_alt, (p->layers.size() + p->dgrads.size()) * sizeof(KmajorParams)));
   CK(cudaMalloc(&p->d_shadow, sh.size() * sizeof(ShadowLayer)));
   CK(cudaMemcpy(p->d_shadow, sh.data(), sh.size() * sizeof(ShadowLayer), cudaMemcpyHostToDevice));
 
@@ -726,9 +738,37 @@ static int prepare(NppPlan* p, long long n) {
   }
   p->fwd_subs = fwd_subs;
   p->dgrad_subs = dg_subs;
+  // Fused train step: ONE chain per stripe = the forward ops, whose last one carries the RGB head + loss + head
+  // backward in its epilogue (EPI_SNAKE_HEAD) and writes the last layer's delta, followed by the dgrad ops.
+  {
+    const int nlf = (int)p->layers.size();
+    const Layer& last = p->layers.back();
+    auto build = [&](const std::vector<KmajorParams>& fwd, std::vector<KmajorParams>& out) {
+      out = fwd;
+      KmajorParams& h = out.back();
+      h.epi = EPI_SNAKE_HEAD;
+      h.out0 = p->bufs[last.buf_delta].ptr;
+      h.ld0 = last.out;
+      h.tmOut0 = p->map_ep[last.buf_delta];
+      h.out1 = nullptr;
+      h.colsum = p->acc + last.bg_off;
+      for (auto k : p->dgrad_params) {
+        for (int sg = 0; sg < k.nseg; ++sg) k.a_src[sg] = k.a_src[sg] < 0 ? nlf - 1 : nlf + k.a_src[sg];
+        k.sub_base += fwd_subs;
+        out.push_back(k);
+      }
+    };
+    build(p->fwd_params, p->step_params);
+    build(p->fwd_params_alt, p->step_params_alt);
+  }
   finish_chain_ops(p->fwd_params, p->cluster);
   finish_chain_ops(p->fwd_params_alt, p->cluster);
   finish_chain_ops(p->dgrad_params, p->cluster);
+  finish_chain_ops(p->step_params, p->cluster);
+  finish_chain_ops(p->step_params_alt, p->cluster);
+  CK(cudaMemcpy(p->d_step_ops, p->step_params.data(), p->step_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_step_ops_alt, p->step_params_alt.data(), p->step_params_alt.size() * sizeof(KmajorParams),
+                cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_fwd_ops, p->fwd_params.data(), p->fwd_params.size() * sizeof(KmajorParams), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_fwd_ops_alt, p->fwd_params_alt.data(), p->fwd_params_alt.size() * sizeof(KmajorParams),
                 cudaMemcpyHostToDevice));
@@ -774,7 +814,7 @@ static int set_smem_attrs() {
 // cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
 static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, int n_ops, int M, int num_sms,
                         cudaStream_t st, int subs_per_stripe, int cluster = 1, float* zero_a = nullptr, int zero_n = 0,
-                        float* zero_b = nullptr, int relu = 0) {
+                        float* zero_b = nullptr, int relu = 0, const HeadArgs* head = nullptr, int pdl = 0) {
   CKI(set_smem_attrs());
   if (n_ops > MAX_CHAIN_OPS) return fail("chain longer than MAX_CHAIN_OPS");
   ChainParams cp;
@@ -799,6 +839,8 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   cp.zero_n = zero_n;
   cp.zero_b = zero_b;
   cp.relu = relu;
+  if (head != nullptr) cp.head = *head;
+  cp.pdl = pdl;
   cp.n_ops = n_ops;
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
@@ -821,13 +863,15 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   // NPP_DEBUG_MODEL_STAMPS=<k>: the k-th chain launch of the process prints the per-tile clock stamps of one CTA
   static int model_stamp_calls = 0;
   const char* ms_env = getenv("NPP_DEBUG_MODEL_STAMPS");
@@ -864,7 +908,7 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   return 0;
 }
 
-static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int cluster) {
+static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int cluster, int pdl = 0) {
   CKI(set_smem_attrs());
   if (cluster == 1) {
     const int grid = w.n_units < num_sms ? w.n_units : num_sms;
@@ -879,13 +923,15 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   cfg.blockDim = dim3(WGRAD_THREADS);
   cfg.dynamicSmemBytes = WGRAD_PAIR_SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   CK(cudaLaunchKernelEx(&cfg, npp_gemm_wgrad<2>, w));
   return 0;
 }
@@ -921,7 +967,7 @@ static int launch_encode(NppPlan* p, const float* coords, long long n, int set, 
     unsigned blocks = (unsigned)std::min<long long>((items + 255) / 256, (long long)p->num_sms * 8);
     npp_encode_search_kernel<<<blocks, 256, 0, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, p->bufs[bp].ptr,
                                                      p->Ap, zero_loss ? p->acc : nullptr,
-                                                     zero_loss ? (int)p->acc_floats : 0, zero_loss,
+                                                     zero_loss ? (int)p->acc_zero_floats : 0, zero_loss,
                                                      p->step_mode ? p->d_step : nullptr);
     CK(cudaGetLastError());
     ++p->launches;
@@ -936,10 +982,40 @@ static int launch_encode(NppPlan* p, const float* coords, long long n, int set, 
   const int ba = set ? p->buf_enca_alt : p->buf_enca;
   __half* enca = ba >= 0 ? p->bufs[ba].ptr : nullptr;
   npp_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, enca, p->Ap, rows,
-                                                     zero_loss ? p->acc : nullptr, zero_loss ? (int)p->acc_floats : 0,
+                                                     zero_loss ? p->acc : nullptr, zero_loss ? (int)p->acc_zero_floats : 0,
                                                      zero_loss);
   CK(cudaGetLastError());
   ++p->launches;
+  return 0;
+}
+
+// Makes the encoding of `coords` available in one of the two encoding sets (p->enc_set on return): picks up a
+// prefetched one (*prefetched = true) or encodes in line.
+static int select_encoding(NppPlan* p, const float* coords, long long n, cudaStream_t st, float* zero_loss,
+                           bool* prefetched) {
+  int hit = -1;
+  for (int i = 0; i < 2; ++i)
+    if (p->pref[i].valid && p->pref[i].coords == coords && p->pref[i].n == n) hit = i;
+  if (hit >= 0) {
+    // npp_encode_prefetch already wrote this batch's encoding into set `hit` (on the side stream, while earlier
+    // work was running): wait for it, switch sets, and let the chain kernel clear the step accumulators
+    CK(cudaStreamWaitEvent(st, p->pref[hit].done, 0));
+    p->pref[hit].valid = false;
+    p->enc_set = hit;
+    *prefetched = true;
+    ++p->launches;   // the encode launch belongs to this step
+    return 0;
+  }
+  // encode in line, into a set nobody has prefetched into (or, failing that, over a prefetch that is now stale)
+  int set = p->enc_set;
+  if (p->pref[set].valid && !p->pref[1 - set].valid) set = 1 - set;
+  if (p->pref[set].valid) {
+    CK(cudaStreamWaitEvent(st, p->pref[set].done, 0));
+    p->pref[set].valid = false;
+  }
+  p->enc_set = set;
+  ProfScope ps(p, st, PROF_ENCODE, 1);
+  CKI(launch_encode(p, coords, n, set, st, zero_loss));
   return 0;
 }
 
@@ -961,36 +1037,14 @@ static int run_forward(NppPlan* p, const float* coords, long long n, float* logi
     CK(cudaGetLastError());
     ++p->launches;
   } else {
-    int hit = -1;
-    for (int i = 0; i < 2; ++i)
-      if (p->pref[i].valid && p->pref[i].coords == coords && p->pref[i].n == n) hit = i;
-    if (hit >= 0) {
-      // npp_encode_prefetch already wrote this batch's encoding into set `hit` (on the side stream, while earlier
-      // work was running): wait for it, switch sets, and let the chain kernel clear the step accumulators
-      CK(cudaStreamWaitEvent(st, p->pref[hit].done, 0));
-      p->pref[hit].valid = false;
-      p->enc_set = hit;
-      prefetched = true;
-      ++p->launches;   // the encode launch belongs to this step
-    } else {
-      // encode in line, into a set nobody has prefetched into (or, failing that, over a prefetch that is now stale)
-      int set = p->enc_set;
-      if (p->pref[set].valid && !p->pref[1 - set].valid) set = 1 - set;
-      if (p->pref[set].valid) {
-        CK(cudaStreamWaitEvent(st, p->pref[set].done, 0));
-        p->pref[set].valid = false;
-      }
-      p->enc_set = set;
-      ProfScope ps(p, st, PROF_ENCODE, 1);
-      CKI(launch_encode(p, coords, n, set, st, zero_loss));
-    }
+    CKI(select_encoding(p, coords, n, st, zero_loss, &prefetched));
   }
   {
     ProfScope ps(p, st, PROF_GEMM_FWD, 1);
     const bool alt = p->enc_set != 0;
     CKI(launch_chain(alt ? p->d_fwd_ops_alt : p->d_fwd_ops, alt ? p->fwd_params_alt.data() : p->fwd_params.data(),
                      (int)p->layers.size(), (int)n, p->num_sms, st, p->fwd_subs, p->cluster,
-                     prefetched && zero_loss ? p->acc : nullptr, prefetched && zero_loss ? (int)p->acc_floats : 0,
+                     prefetched && zero_loss ? p->acc : nullptr, prefetched && zero_loss ? (int)p->acc_zero_floats : 0,
                      prefetched ? zero_loss : nullptr, p->cfg.activation));
     ++p->launches;
   }
@@ -1012,6 +1066,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
   CKI(prepare(p, n));
   CKI(set_smem_attrs());
+  p->acc_clean = false;
   const Layer& last = p->layers.back();
   unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
   if (!head_done) {
@@ -1053,7 +1108,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
 }
 
 static int zero_acc(NppPlan* p, cudaStream_t st) {
-  CK(cudaMemsetAsync(p->acc, 0, p->acc_floats * sizeof(float), st));
+  CK(cudaMemsetAsync(p->acc, 0, p->acc_zero_floats * sizeof(float), st));
   return 0;
 }
 
@@ -1122,6 +1177,8 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   p->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("NPP_CLUSTER")) p->cluster = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("NPP_WG_CLUSTER")) p->wg_cluster = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("NPP_PDL")) p->pdl = atoi(e) != 0;
+  if (const char* e = getenv("NPP_SPLIT_STEP")) p->fused_step = atoi(e) == 0;
   memset(&p->enc, 0, sizeof(p->enc));
   p->enc.topk = cfg->topk;
   p->enc.n_aug = cfg->n_aug;
@@ -1183,6 +1240,8 @@ int npp_plan_destroy(NppPlan* p) {
   if (p->coop_evt) cudaEventDestroy(p->coop_evt);
   for (int i = 0; i < 2; ++i) if (p->pref[i].done) cudaEventDestroy(p->pref[i].done);
   cudaFree(p->d_dgrad_ops);
+  cudaFree(p->d_step_ops);
+  cudaFree(p->d_step_ops_alt);
   cudaFree(p->d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1407,12 +1466,128 @@ int npp_adam_step(NppPlan* p, float lr, float beta1, float beta2, float eps, int
   return run_shadow(p, (cudaStream_t)stream);
 }
 
+// The update kernel of a train step: split-K slabs -> gradient -> Adam -> fp32 master + fp16 shadows.
+static int launch_update(NppPlan* p, const AdamScalars& ad, const unsigned int* amax_bits, const StepReset& rs, int pdl,
+                         cudaStream_t st) {
+  const unsigned blocks = (unsigned)p->update_table.tile_begin[p->update_table.n_layers] + 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const float* partial = p->partial;
+  float* bias_acc = p->acc;
+  float* head_acc = p->acc + p->headacc_off;
+  float* grads = p->keep_grads ? p->grads : nullptr;
+  const AdamScalars* ad_table = p->step_mode ? p->d_ad_table : nullptr;
+  const int* d_step = p->d_step;
+#define NPP_UPDATE_CASE(S_)                                                                                            \
+  case S_:                                                                                                             \
+    CK(cudaLaunchKernelEx(&cfg, npp_fused_update_kernel<S_>, p->update_table, partial, p->slab_stride, bias_acc,       \
+                          head_acc, p->rgb_w_off, p->rgb_b_off, p->head_width, amax_bits, p->params, grads, p->m,      \
+                          p->v, ad, ad_table, d_step, rs));                                                            \
+    break;
+  switch (p->wg_params.n_splits) {
+    NPP_UPDATE_CASE(1) NPP_UPDATE_CASE(2) NPP_UPDATE_CASE(3) NPP_UPDATE_CASE(4) NPP_UPDATE_CASE(5) NPP_UPDATE_CASE(6)
+    NPP_UPDATE_CASE(7) NPP_UPDATE_CASE(8) NPP_UPDATE_CASE(9) NPP_UPDATE_CASE(10) NPP_UPDATE_CASE(11)
+    NPP_UPDATE_CASE(12)
+    default: return fail("unsupported split-K factor in the fused update");
+  }
+#undef NPP_UPDATE_CASE
+  ++p->launches;
+  return 0;
+}
+
+static AdamScalars adam_scalars(float lr, float beta1, float beta2, float eps, long long step) {
+  AdamScalars ad;
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  ad.beta1 = beta1;
+  ad.beta2 = beta2;
+  ad.step_size = (float)((double)lr / bc1);
+  ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  ad.eps = eps;
+  return ad;
+}
+
+// Fused train step, three launches: [forward chain -> RGB head + loss + head backward -> dgrad chain] as ONE persistent
+// kernel (every 128-row stripe runs all of it without a grid-wide dependency, because the fp16 delta scale comes from the
+// previous step's max|g|: npp_step_amax), the grouped weight-gradient GEMM, and the update kernel.  Consecutive
+// launches are programmatic dependents: a kernel's prologue overlaps its predecessor's tail.
+static int run_fused_step(NppPlan* p, const float* coords, const float* target, const float* mask, long long n,
+                          long long n_norm, const AdamScalars& ad, float* loss, cudaStream_t st) {
+  if (!p->params) return fail("npp_plan_bind has not been called");
+  if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
+  CKI(prepare(p, n));
+  CKI(set_smem_attrs());
+  if (!p->acc_clean) {   // a call of the unfused path left its sums behind
+    CK(cudaMemsetAsync(p->acc, 0, p->acc_zero_floats * sizeof(float), st));
+    p->acc_clean = true;
+  }
+  bool prefetched = false;
+  CKI(select_encoding(p, coords, n, st, nullptr, &prefetched));
+  const Layer& last = p->layers.back();
+  if (last.out != BN) return fail("fused step: the last dense layer must be one 256-column tile");
+  unsigned int* ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
+  const int cur = (int)(p->step_seq % 3), prev = (int)((p->step_seq + 2) % 3), clr = (int)((p->step_seq + 1) % 3);
+  float* loss_acc = p->acc + p->ring_off + 3;
+  HeadArgs hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.w = p->params + p->rgb_w_off;
+  hd.b = p->params + p->rgb_b_off;
+  hd.target = target;
+  hd.mask = mask;
+  hd.logits = nullptr;
+  hd.head_acc = p->acc + p->headacc_off;
+  hd.loss_acc = loss_acc;
+  hd.amax_prev = ring + prev;
+  hd.amax_next = ring + cur;
+  hd.inv_count = 1.0f / (3.0f * (float)n_norm);
+  hd.width = p->head_width;
+  const bool alt = p->enc_set != 0;
+  {
+    ProfScope ps(p, st, PROF_GEMM_FWD, 1);
+    const std::vector<KmajorParams>& ops = alt ? p->step_params_alt : p->step_params;
+    CKI(launch_chain(alt ? p->d_step_ops_alt : p->d_step_ops, ops.data(), (int)ops.size(), (int)n, p->num_sms, st,
+                     p->fwd_subs + p->dgrad_subs, p->cluster, nullptr, 0, nullptr, p->cfg.activation, &hd, p->pdl));
+    ++p->launches;
+  }
+  {
+    ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
+    CKI(launch_wgrad(alt ? p->wg_params_alt : p->wg_params, p->num_sms, st, p->wg_cluster, p->pdl));
+    ++p->launches;
+  }
+  CKI(mark_busy(p, st));
+  {
+    ProfScope ps(p, st, PROF_ADAM, 1);
+    StepReset rs;
+    rs.on = 1;
+    rs.inv_count = hd.inv_count;
+    rs.loss_acc = loss_acc;
+    rs.loss_out = loss;
+    rs.amax_clear = ring + clr;
+    CKI(launch_update(p, ad, ring + prev, rs, p->pdl, st));
+  }
+  ++p->step_seq;
+  return 0;
+}
+
 int npp_train_step(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n, int64_t n_norm,
                    float lr, float beta1, float beta2, float eps, int64_t step, float* loss, void* stream) {
   if (!p || !coords || !target || !loss) return fail("npp_train_step: null argument");
   if (n_norm <= 0) return fail("n_norm must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
+  if (p->fused_step && !p->step_mode) {
+    if (step < 1) return fail("Adam step must be >= 1");
+    return run_fused_step(p, coords, target, mask, n, n_norm, adam_scalars(lr, beta1, beta2, eps, step), loss, st);
+  }
+  p->acc_clean = false;
   // the encode kernel clears the accumulators and the loss scalar of this step
   CKI(run_forward(p, coords, n, p->logits_buf, st, /*with_head=*/false, nullptr, loss));
   const float inv_count = 1.0f / (3.0f * (float)n_norm);
@@ -1483,31 +1658,10 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
     if (step < 1) return fail("Adam step must be >= 1");
     ProfScope ps(p, st, PROF_ADAM, 1);
-    AdamScalars ad;
-    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-    ad.beta1 = beta1;
-    ad.beta2 = beta2;
-    ad.step_size = (float)((double)lr / bc1);
-    ad.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
-    ad.eps = eps;
-    const unsigned blocks = (unsigned)p->update_table.tile_begin[p->update_table.n_layers] + 1;
-#define NPP_UPDATE_CASE(S_)                                                                                          \
-  case S_:                                                                                                           \
-    npp_fused_update_kernel<S_><<<blocks, 256, 0, st>>>(                                                             \
-        p->update_table, p->partial, p->slab_stride, p->acc, p->acc + p->headacc_off, p->rgb_w_off, p->rgb_b_off,    \
-        p->head_width, reinterpret_cast<unsigned int*>(p->acc + p->amax_off), p->params,                             \
-        p->keep_grads ? p->grads : nullptr, p->m, p->v, ad, p->step_mode ? p->d_ad_table : nullptr, p->d_step);      \
-    break;
-    switch (p->wg_params.n_splits) {
-      NPP_UPDATE_CASE(1) NPP_UPDATE_CASE(2) NPP_UPDATE_CASE(3) NPP_UPDATE_CASE(4) NPP_UPDATE_CASE(5) NPP_UPDATE_CASE(6)
-      NPP_UPDATE_CASE(7) NPP_UPDATE_CASE(8) NPP_UPDATE_CASE(9) NPP_UPDATE_CASE(10) NPP_UPDATE_CASE(11)
-      NPP_UPDATE_CASE(12)
-      default: return fail("unsupported split-K factor in the fused update");
-    }
-#undef NPP_UPDATE_CASE
-    CK(cudaGetLastError());
-    ++p->launches;
+    StepReset rs;
+    memset(&rs, 0, sizeof(rs));
+    CKI(launch_update(p, adam_scalars(lr, beta1, beta2, eps, step), reinterpret_cast<unsigned int*>(p->acc + p->amax_off), rs,
+                      0, st));
   }
   return 0;
 }

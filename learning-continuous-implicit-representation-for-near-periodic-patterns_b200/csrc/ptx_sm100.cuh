@@ -164,6 +164,17 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // orders async-proxy accesses (TMA loads/stores) of ANY state space against generic-proxy accesses
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ------------------------------------------------------- programmatic dependent launch
+// griddepcontrol.wait: blocks until every kernel this launch depends on has completed and its writes are visible
+// (no-op when the kernel was launched without the programmatic-stream-serialization attribute).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// the dependent kernel of this launch may start its prologue (it still waits for this grid in grid_dependency_wait)
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// named barrier for a subset of the CTA's warps
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

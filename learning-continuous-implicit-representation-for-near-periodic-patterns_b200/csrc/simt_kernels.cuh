@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include "grad_scale.cuh"
+#include "ptx_sm100.cuh"
 
 namespace npp {
 
@@ -429,17 +431,6 @@ __global__ void __launch_bounds__(256) npp_gather_windows_kernel(const float* __
     if (r >= 0 && r < H && q >= 0 && q < W) v = img[((size_t)r * W + (size_t)q) * C + c];
     out[idx] = v;
   }
-}
-
-// Power-of-two gradient scale so that fp16 deltas sit in the middle of the half range:
-// amax * scale == 2^10 (rounded down to a power of two).  Exact to undo in fp32.
-__device__ __forceinline__ float npp_grad_scale(float amax) {
-  if (!(amax > 0.0f) || !isfinite(amax)) return 1.0f;
-  int e;
-  frexpf(amax, &e);  // amax = m * 2^e, m in [0.5, 1)
-  int k = 10 - e;
-  k = max(-60, min(60, k));
-  return ldexpf(1.0f, k);
 }
 
 // sigmoid + masked MSE (models/helpers.py:55-56, models/mse_calculator.py:13-27 'l2' branch)
@@ -1151,6 +1142,15 @@ struct UpdateLayer {
 struct AdamScalars {
   float beta1, beta2, step_size, inv_sqrt_bc2, eps;
 };
+// Fused step (forward + head + backward in one launch, see EPI_SNAKE_HEAD): the update kernel is the last reader of
+// the step's accumulators, so it clears them for the next step, hands the loss out, and rotates the max|g| ring.
+struct StepReset {
+  int on;                    // 0: legacy behaviour (nothing below is touched, amax_bits holds this step's maximum)
+  float inv_count;
+  float* loss_acc;
+  float* loss_out;
+  unsigned int* amax_clear;
+};
 __device__ __forceinline__ float npp_adam1(float p, float g, float& m, float& v, const AdamScalars a) {
   m = m + (g - m) * (1.0f - a.beta1);
   v = v * a.beta2 + (1.0f - a.beta2) * g * g;
@@ -1173,26 +1173,34 @@ struct UpdateTable {
 template <int S>
 __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_constant__ UpdateTable tab,
                                                                const float* __restrict__ partial, long long slab_stride,
-                                                               const float* __restrict__ bias_acc,
-                                                               const float* __restrict__ head_acc, long long rgb_w_off,
+                                                               float* bias_acc, float* head_acc, long long rgb_w_off,
                                                                long long rgb_b_off, int head_width,
                                                                const unsigned int* __restrict__ amax_bits,
                                                                float* __restrict__ params, float* __restrict__ grads,
                                                                float* __restrict__ m, float* __restrict__ v,
                                                                AdamScalars ad_arg,
                                                                const AdamScalars* __restrict__ ad_table,
-                                                               const int* __restrict__ step) {
+                                                               const int* __restrict__ step, StepReset rs) {
   __shared__ float tile[32][129];
+  grid_launch_dependents();   // programmatic dependent launch: the next kernel's prologue may overlap this kernel
+  grid_dependency_wait();
   // re-launched step graph: the scalars of Adam step *step come from a table filled by npp_fit_run
   const AdamScalars ad = ad_table != nullptr ? ad_table[*step] : ad_arg;
   const int total_tiles = tab.tile_begin[tab.n_layers];
   if ((int)blockIdx.x >= total_tiles) {  // rgb_linear: unscaled fp32 accumulators written by the head backward
     const int total = 3 * head_width + 3;
+    float* hacc = head_acc;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const long long idx = i < 3 * head_width ? rgb_w_off + i : rgb_b_off + (i - 3 * head_width);
       const float g = head_acc[i];
+      if (rs.on) hacc[i] = 0.f;   // the consumer clears the step accumulators (nobody else reads this entry)
       if (grads) grads[idx] = g;
       params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
+    }
+    if (rs.on && threadIdx.x == 0) {
+      if (rs.loss_out != nullptr) *rs.loss_out = *rs.loss_acc;
+      *rs.loss_acc = 0.f;
+      *rs.amax_clear = 0u;        // ring slot the step after the next one accumulates into
     }
     return;
   }
@@ -1200,7 +1208,8 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
   while ((int)blockIdx.x >= tab.tile_begin[li + 1]) ++li;
   const UpdateLayer& L = tab.L[li];
   const int t = (int)blockIdx.x - tab.tile_begin[li];
-  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
+  // fused step: the deltas were scaled with the PREVIOUS step's maximum (npp_step_amax), else with this step's
+  const float inv = 1.0f / npp_grad_scale(rs.on ? npp_step_amax(amax_bits, rs.inv_count) : __uint_as_float(*amax_bits));
   const int tiles_c = (L.kpad + 127) >> 7;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 column groups x 8 rows per pass
   const bool two_seg = L.in_ref > L.split_col;
@@ -1339,9 +1348,11 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
     }
   }
   if (t == 0) {
+    float* bacc = bias_acc;
     for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
       const long long idx = L.b_off + o;
       const float g = bias_acc[L.bg_off + o] * inv;
+      if (rs.on) bacc[L.bg_off + o] = 0.f;
       if (grads) grads[idx] = g;
       params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
     }

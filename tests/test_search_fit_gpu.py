@@ -187,7 +187,7 @@ def test_light_fused_train_steps_follow_the_oracle():
         plan.train_step(cd, td, None, lr, loss, step=step)
         l_ref, _ = O.train_step_light(p, m, v, step, pos, per, target, lr)
         assert abs(loss.item() - l_ref) < 1e-3 * l_ref, (step, loss.item(), l_ref)
-    assert plan.launch_count() == 7      # encode, forward chain, head loss, head backward, dgrad chain, wgrad, update
+    assert plan.launch_count() == 4      # encode, fused chain (forward + head + loss + backward), wgrad, update
     got = plan.state()
     for k in p:
         a = got[k].cpu().numpy()
@@ -267,7 +267,7 @@ def test_fit_run_equals_stepwise_train_steps():
         a.train_step(coords[i], target[i], None, O.lr_schedule(i + 1, lrate=5e-4, lrate_decay=0.02), loss)
         step_losses.append(loss.item())
     run_losses = b.fit_run(coords, target, lrate=5e-4, lrate_decay=0.02)     # decays 10x every 2 steps: LR rule visible
-    assert b.launch_count() == 7 * iters and b.adam_steps == iters
+    assert b.launch_count() == 4 * iters and b.adam_steps == iters
     np.testing.assert_allclose(run_losses.cpu().numpy(), step_losses, rtol=1e-4)
     sa, sb = a.state(), b.state()
     for k in sa:
@@ -324,7 +324,7 @@ def test_fit_run_graph_modes_equal_plain_launches(monkeypatch, mode):
     b, *_ = make(n, seed=21)
     monkeypatch.setenv("NPP_FIT_GRAPH", "0")
     direct = a.fit_run(coords, target).cpu().numpy()
-    assert a.launch_count() == 7 * iters
+    assert a.launch_count() == 4 * iters
     monkeypatch.setenv("NPP_FIT_GRAPH", mode)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
