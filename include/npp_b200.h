@@ -160,6 +160,28 @@ int npp_train_step(NppPlan* plan, const float* coords, const float* target, cons
                    int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
                    void* stream);
 
+/* The same step in three phases, for data parallelism inside one image (reference: nn.DataParallel,
+ * models/helpers.py:133-137; here one process per GPU, rows split over the ranks).  The gradient arena
+ * exists between the phases so that the caller can sum it over the ranks:
+ *   npp_step_forward_backward  encode + forward + RGB head + masked l2 (normalised by the GLOBAL count n_norm) + head
+ *                              backward + dgrad chain: one persistent kernel; this rank's share of the loss stays on
+ *                              the device until npp_step_finish
+ *   npp_step_wgrad             weight + bias gradients of the dense layers [layer_begin, layer_end) (execution order,
+ *                              npp_plan_layer_count of them; rgb_linear rides with the last one) into the gradient
+ *                              arena, floats [offset, offset + count) of npp_plan_layer_grad_range.  One grouped GEMM
+ *                              launch + one reduction launch per call: call it for a few layer groups and all-reduce
+ *                              each group's range while the next group's GEMMs run
+ *   npp_step_finish            torch.optim.Adam over the arena (models/helpers.py:164), shadow refresh, loss -> *loss
+ * n / n_norm must be the values given to npp_step_forward_backward. */
+int npp_step_forward_backward(NppPlan* plan, const float* coords, const float* target, const float* mask, int64_t n,
+                              int64_t n_norm, void* stream);
+int npp_plan_layer_count(const NppPlan* plan);
+int npp_plan_layer_grad_range(const NppPlan* plan, int32_t layer_begin, int32_t layer_end, int64_t* offset,
+                              int64_t* count);
+int npp_step_wgrad(NppPlan* plan, int32_t layer_begin, int32_t layer_end, int64_t n, int64_t n_norm, void* stream);
+int npp_step_finish(NppPlan* plan, int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                    float* loss, void* stream);
+
 /* A run of `iters` train steps without returning to the caller in between: the loop of
  * NPP_proposal/search.py:110-146 (and of NPP_completion/train.py:150-263 when every batch is known up front).
  * Step i (0-based) reads coords_all[i] ([iters, n, 2]), target_all[i] ([iters, n, 3]) and, if given, mask_all[i]

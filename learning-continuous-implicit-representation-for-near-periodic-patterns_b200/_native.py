@@ -71,6 +71,11 @@ SIGNATURES = {
     "npp_robust_adaptive_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
     "npp_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int64, _P, _P]),
+    "npp_step_forward_backward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "npp_plan_layer_count": (C.c_int, [_P]),
+    "npp_plan_layer_grad_range": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "npp_step_wgrad": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P]),
+    "npp_step_finish": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P, _P]),
     "npp_fit_run": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_float, C.c_int64, _P, _P]),
     "npp_set_keep_grads": (C.c_int, [_P, C.c_int]),
@@ -116,8 +121,11 @@ def lib() -> C.CDLL:
             raise NppError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(needs nvcc).  This package has no CPU / PyTorch fallback path.")
-        handle = C.CDLL(str(LIB_PATH))
+        # NPP_B200_LIB: another build of the same library (kernel A/B experiments); the default is the in-tree build
+        handle = C.CDLL(os.environ.get("NPP_B200_LIB") or str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("NPP_B200_LIB") and not hasattr(handle, name):
+                continue                # an older experimental build: entry points added since are simply absent
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args

@@ -154,6 +154,8 @@ struct WgUnit {
   int out_off;         // float offset of (m0, col0) inside one partial slab
   int ld;              // row pitch (floats) of this layer inside the slab
   int ncols_left;      // valid columns from col0 to the padded layer width
+  int bias_off;        // >= 0: this unit also sums its delta columns over its rows (bias gradient of out-features
+                       //   [a_m0, a_m0 + 256)) into WgradParams::bias_acc + bias_off; -1: another unit of the layer does
 };
 
 constexpr int WG_MAX_MAPS = 28;
@@ -168,6 +170,7 @@ struct alignas(64) WgradParams {
   long long slab_stride;
   unsigned long long desc_hi;  // 0 = default MN-major SW128 (LBO 8192, SBO 1024)
   int k_adv;                   // 0 = default 2048
+  float* bias_acc;             // bias-gradient accumulators (scaled like the deltas), nullptr: nobody wants them
 };
 
 template <int NSTAGES>
@@ -220,12 +223,12 @@ __device__ __forceinline__ GemmSmem carve_smem_t(uint8_t* raw) {
   return s;
 }
 
-template <int NSTAGES, int CLUSTER = 1, int NEPI = 4, int FULL_COUNT = 1>
+template <int NSTAGES, int CLUSTER = 1, int NEPI = 4, int FULL_COUNT = 1, int EMPTY_COUNT = 1, int AFULL_COUNT = 0>
 __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(&s.full[i], FULL_COUNT);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.empty[i], EMPTY_COUNT);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tfull[i], 1);
@@ -233,7 +236,8 @@ __device__ __forceinline__ uint32_t gemm_prologue_t(const GemmSmem& s, int warp)
     }
     for (int i = 0; i < 8; ++i) mbar_init(&s.epi_bar[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&s.fempty[i], 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&s.afull[i], (NEPI / 2) * CLUSTER);  // 4 quadrant warps of every CTA
+    for (int i = 0; i < 8; ++i)   // chain kernel: 4 quadrant warps of every CTA
+      mbar_init(&s.afull[i], AFULL_COUNT ? AFULL_COUNT : (NEPI / 2) * CLUSTER);
     for (int i = 0; i < 8; ++i) s.prog[i] = 0;
     fence_mbar_init();
   }
@@ -344,7 +348,7 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
   const int row = row0 + lane;
   const bool row_ok = row < M;
   const bool warp_ok = row0 < M;
-  float* colsum = ea.colsum;
+  (void)ea.colsum;   // bias gradients are summed by the weight-gradient kernel (WgUnit::bias_off)
   float* out_f32 = ea.out_f32;
   if (EPI == EPI_DGRAD_MUL) {
     // Multiplier of this warp's first sub-tile.  Normally the previous tile already asked for it (right after it had
@@ -482,18 +486,6 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
         if (EPI == EPI_SNAKE)
           *reinterpret_cast<uint4*>(aux + row_off + ((c ^ sw) << 4)) =
               make_uint4(dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
-      }
-      if ((EPI == EPI_DGRAD_MUL || EPI == EPI_DGRAD) && colsum != nullptr) {
-        // bias gradient of the layer that produced this delta: column sums of the
-        // fp16-rounded values, so it matches what the wgrad GEMM consumes.
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float2 r = unpack_h2(hd[i]);
-          v[2 * i] = row_ok ? r.x : 0.f;
-          v[2 * i + 1] = row_ok ? r.y : 0.f;
-        }
-        const float cs = warp_colsum32(v, lane);
-        if (warp_ok) atomicAdd(colsum + hcol + lane, cs);
       }
     }
     fence_proxy_async_smem();
@@ -1097,7 +1089,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 //   [m0 + 128 r, +128) (its own delta columns as A) and loads only half of the activation tile (B columns
 //   [n0 + 128 r, +128)), so a pair moves 64 KB per K block for twice the MMA work (the single-CTA kernel is L2
 //   bandwidth bound: 1.5 GB of operand reads per step at 16 k rows).
-constexpr int WG_PAIR_STAGES = 5;
+#ifndef NPP_WG_PAIR_STAGES
+#define NPP_WG_PAIR_STAGES 5
+#endif
+constexpr int WG_PAIR_STAGES = NPP_WG_PAIR_STAGES;
 constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 512 + 1024;
 
 template <int CLUSTER>
@@ -1109,7 +1104,14 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
   const GemmSmem s = carve_smem_t<NST, 0, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4>(s, warp);
+  static_assert(NST <= 8, "the per-stage `alocal` barriers reuse the eight afull slots");
+  // Bias gradients (see the epilogue warps below) need to know when THIS CTA's delta tile of a stage has landed.  In
+  // pair mode every TMA load used to complete on the leader's full barrier, which the peer CTA cannot wait on; now the
+  // peer's delta tile completes on a peer-local barrier (`alocal`, the afull slots), and the peer's otherwise idle warp
+  // 1 forwards that completion to the leader's full barrier (second pending arrival there).  A stage is free again when
+  // its UMMAs have completed (one commit) and the four epilogue warps of the CTA have arrived.
+  uint64_t* const alocal = s.afull;
+  const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4, CLUSTER, 1 + 4, 1>(s, warp);
   grid_dependency_wait();   // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
   const int kb_total = (p.rows + BK - 1) / BK;
   const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0u;
@@ -1139,11 +1141,17 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], am0 + j * 64, kb * BK);
 #pragma unroll
             for (int j = 0; j < B_COLS / 64; ++j) tma_load_2d(sb + j * 8192, mb, &s.full[ps.stage], bn0 + j * 64, kb * BK);
-          } else {
-            if (leader) mbar_expect_tx(&s.full[ps.stage], CLUSTER * (A_STAGE_BYTES + B_BYTES));
+          } else if (leader) {
+            mbar_expect_tx(&s.full[ps.stage], A_STAGE_BYTES + CLUSTER * B_BYTES);   // own delta tile + both activation halves
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d_pair(sa + j * 8192, ma, &s.full[ps.stage], am0 + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &s.full[ps.stage], am0 + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < B_COLS / 64; ++j)
+              tma_load_2d_pair(sb + j * 8192, mb, &s.full[ps.stage], bn0 + j * 64, kb * BK);
+          } else {
+            mbar_expect_tx(&alocal[ps.stage], A_STAGE_BYTES);                        // the peer's delta tile: local barrier
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &alocal[ps.stage], am0 + j * 64, kb * BK);
 #pragma unroll
             for (int j = 0; j < B_COLS / 64; ++j)
               tma_load_2d_pair(sb + j * 8192, mb, &s.full[ps.stage], bn0 + j * 64, kb * BK);
@@ -1200,16 +1208,78 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+    } else {
+      // peer CTA: tell the leader's full barrier that this CTA's delta tile of the stage has landed.  Relaxed arrive: the
+      // tile was written by the async proxy and is read by the tensor core, no generic-proxy data is published.
+      PipeStateT<NST> ps;
+      for (int u = unit0; u < p.n_units; u += ustride) {
+        const WgUnit un = p.units[u];
+        if (un.split >= p.n_splits) continue;
+        const int kb0 = un.split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&alocal[ps.stage], ps.phase);
+          if (lane == 0) mbar_arrive_remote_relaxed(&s.full[ps.stage], 0);
+          __syncwarp();
+          ps.advance();
+        }
+      }
     }
   } else {
     const int lane_base = (warp & 3) * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
+    PipeStateT<NST> ps;
+    // this CTA's delta tile of a stage has landed: the full barrier in the leader (and without pairs), alocal in the peer
+    uint64_t* const mine = (CLUSTER == 1 || leader) ? s.full : alocal;
+    // Bias gradients: db[o] = sum over rows of delta[row, o] (fp16-rounded, scaled: exactly the values the tensor core
+    // consumes).  The delta tile of every K block passes through this CTA's shared memory anyway (A operand, 64 rows x
+    // 128 out-features, MN-major: row r = 128 bytes per 64-feature atom, 16-byte chunks XOR-swizzled with r & 7), so the
+    // epilogue warps, idle during the mainloop, add it up: thread t owns chunk column t & 15 (8 features) of the rows
+    // r = t >> 4 (mod 8).  This used to be a 32 x 32 shuffle transpose-reduce per epilogue block of the dgrad chain
+    // (a quarter of that epilogue's instructions, on the kernel's critical resource).
+    const int et = (warp - 2) * 32 + lane;          // 0..127
+    const int cc = et & 15, rg = et >> 4;
+    const uint32_t rd_off = (uint32_t)(cc >> 3) * 8192u + (uint32_t)rg * 128u + (uint32_t)(((cc & 7) ^ rg) << 4);
     for (int u = unit0; u < p.n_units; u += ustride) {
       const WgUnit un = p.units[u];
       if (un.split >= p.n_splits) continue;
       float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off +
                    (size_t)((int)crank * BM + lane_base + lane) * un.ld;
+      {
+        const int kb0 = un.split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+        const bool want = un.bias_off >= 0 && p.bias_acc != nullptr;
+        float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kb = kb0; kb < kb1; ++kb) {
+          // Units without a bias sum arrive as soon as the stage's previous round is over (never on the critical path);
+          // the others once they have read the tile, which lands long before the stage's UMMAs complete.
+          if (want) mbar_wait(&mine[ps.stage], ps.phase);
+          else mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+          if (want) {
+            const uint8_t* sa = s.a + ps.stage * A_STAGE_BYTES + rd_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(sa + i * 1024);
+              const float2 f0 = unpack_h2(q4.x), f1 = unpack_h2(q4.y), f2 = unpack_h2(q4.z), f3 = unpack_h2(q4.w);
+              bs[0] += f0.x; bs[1] += f0.y; bs[2] += f1.x; bs[3] += f1.y;
+              bs[4] += f2.x; bs[5] += f2.y; bs[6] += f3.x; bs[7] += f3.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.empty[ps.stage]);
+          ps.advance();
+        }
+        if (want) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bs[i] += __shfl_xor_sync(0xffffffffu, bs[i], 16);   // rows rg and rg + 1 of this warp
+          if (lane < 16) {
+            float* dst = p.bias_acc + un.bias_off + (int)crank * BM + cc * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dst + i, bs[i]);
+          }
+        }
+      }
       mbar_wait(&s.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1

@@ -165,6 +165,15 @@ struct NppPlan {
   KmajorParams* d_step_ops_alt = nullptr;  // same, reading the second encoding set
   WgUnit* d_units = nullptr;
   int n_units = 0;
+  std::vector<WgUnit> tile_units;        // one entry per (layer, m-tile, n-tile) with split 0: template of every unit table
+  std::vector<int> tile_begin;           // first entry of layer i inside tile_units (size layers + 1)
+  struct GroupTable {                    // unit table of one layer range for npp_step_wgrad (built on first use)
+    int lb, le, splits;
+    WgUnit* d_units;
+    int n_units;
+  };
+  std::vector<GroupTable> groups;
+  int slabs_alloc = 0;                   // split-K slabs allocated (>= splits_max: layer-range launches split further)
   int splits_max = 0;       // slabs allocated
   int splits_fill = 1;      // splits that give every CTA pair a unit (or the caller's explicit choice)
   bool splits_auto = false;
@@ -448,7 +457,8 @@ static int alloc_plan_memory(NppPlan* p) {
   if (p->splits_auto) S = std::max(S, (int)((p->cfg.max_rows + WG_ROWS_PER_SPLIT - 1) / WG_ROWS_PER_SPLIT));
   if (S > NPP_MAX_SPLITS) S = NPP_MAX_SPLITS;
   p->splits_max = S;
-  CK(cudaMalloc(&p->partial, (size_t)S * p->slab_stride * sizeof(float)));
+  p->slabs_alloc = std::max(S, 4);   // npp_step_wgrad launches a few layers at a time and splits their rows to fill the GPU
+  CK(cudaMalloc(&p->partial, (size_t)p->slabs_alloc * p->slab_stride * sizeof(float)));
 
   // accumulators: [bias acc (bg) | head acc (3*hw+3) | amax | loss]
   p->headacc_off = (bg + 3) / 4 * 4;
@@ -570,6 +580,7 @@ static int alloc_plan_memory(NppPlan* p) {
   };
   std::vector<WgUnit> units;
   const int nl = (int)p->layers.size();
+  p->tile_begin.assign(1, 0);
   for (int li = 0; li < nl; ++li) {
     const Layer& L = p->layers[li];
     for (int s = 0; s < S; ++s)
@@ -589,8 +600,11 @@ static int alloc_plan_memory(NppPlan* p) {
           u.out_off = (int)(L.pg_off + (long long)m0 * L.kpad + n0);
           u.ld = L.kpad;
           u.ncols_left = sg->pad_off + sg->pad_w - n0;
+          u.bias_off = n0 == 0 ? (int)(L.bg_off + m0) : -1;   // one unit per (layer, split, m-tile) sums the delta columns
           units.push_back(u);
+          if (s == 0) p->tile_units.push_back(u);
         }
+    p->tile_begin.push_back((int)p->tile_units.size());
   }
   if (nl + (int)src_bufs.size() > WG_MAX_MAPS) return fail("wgrad: too many tensor maps");
   if (p->slab_stride > 0x7fffffffLL) return fail("wgrad: slab too large for 32-bit offsets");
@@ -732,7 +746,7 @@ static int prepare(NppPlan* p, long long n) {
       k.ldm = P.out;
       k.tmMul = p->map_ep[P.buf_d];
     }
-    k.colsum = p->acc + P.bg_off;
+    k.colsum = nullptr;   // bias gradients are summed by the weight-gradient kernel (WgUnit::bias_off)
     k.epi = P.act ? EPI_DGRAD_MUL : EPI_DGRAD;
     p->dgrad_params.push_back(k);
   }
@@ -751,7 +765,7 @@ static int prepare(NppPlan* p, long long n) {
       h.ld0 = last.out;
       h.tmOut0 = p->map_ep[last.buf_delta];
       h.out1 = nullptr;
-      h.colsum = p->acc + last.bg_off;
+      h.colsum = nullptr;
       for (auto k : p->dgrad_params) {
         for (int sg = 0; sg < k.nseg; ++sg) k.a_src[sg] = k.a_src[sg] < 0 ? nlf - 1 : nlf + k.a_src[sg];
         k.sub_base += fwd_subs;
@@ -789,6 +803,7 @@ static int prepare(NppPlan* p, long long n) {
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
   w.partial = p->partial;
   w.slab_stride = p->slab_stride;
+  w.bias_acc = getenv("NPP_WG_NOBIAS") ? nullptr : p->acc;   // (timing experiments only: the bias gradients are then missing)
   p->wg_params_alt = w;
   for (size_t i = 0; i < p->wg_src_bufs.size(); ++i) p->wg_params_alt.maps[nl + i] = p->map_mn[alt_buf(p->wg_src_bufs[i])];
   p->prepared_n = n;
@@ -1073,7 +1088,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
   ProfScope ps(p, st, PROF_HEAD_LOSS, 1);
   npp_head_bwd_kernel<<<(unsigned)((n + HEAD_BWD_ROWS - 1) / HEAD_BWD_ROWS), 256, 0, st>>>(
       g, p->bufs[last.buf_h].ptr, p->bufs[last.buf_d].ptr, last.out, p->head_width, (int)n, p->params + p->rgb_w_off,
-      amax, p->bufs[last.buf_delta].ptr, last.out, p->acc + p->headacc_off, p->acc + last.bg_off);
+      amax, p->bufs[last.buf_delta].ptr, last.out, p->acc + p->headacc_off, nullptr);
   CK(cudaGetLastError());
   ++p->launches;
   }
@@ -1093,7 +1108,7 @@ static int run_backward(NppPlan* p, long long n, const float* g, cudaStream_t st
     ProfScope ps(p, st, PROF_FINALIZE, 3);
     dim3 grid(128, (unsigned)p->layers.size());
     npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin, p->partial, p->wg_params.n_splits, p->slab_stride, p->acc,
-                                                   amax, p->grads);
+                                                   amax, p->grads, 0.f);
     CK(cudaGetLastError());
     const int hn = 3 * p->head_width + 3;
     // rgb_linear weight [3, W/2] and bias [3] are contiguous in the head accumulator and (up to the
@@ -1243,6 +1258,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_step_ops);
   cudaFree(p->d_step_ops_alt);
   cudaFree(p->d_units);
+  for (auto& g : p->groups) cudaFree(g.d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;
@@ -1519,10 +1535,26 @@ static AdamScalars adam_scalars(float lr, float beta1, float beta2, float eps, l
 // kernel (every 128-row stripe runs all of it without a grid-wide dependency, because the fp16 delta scale comes from the
 // previous step's max|g|: npp_step_amax), the grouped weight-gradient GEMM, and the update kernel.  Consecutive
 // launches are programmatic dependents: a kernel's prologue overlaps its predecessor's tail.
-static int run_fused_step(NppPlan* p, const float* coords, const float* target, const float* mask, long long n,
-                          long long n_norm, const AdamScalars& ad, float* loss, cudaStream_t st) {
+struct StepSlots {
+  unsigned int *prev, *cur, *clr;
+  float* loss_acc;
+  float inv_count;
+};
+static StepSlots step_slots(NppPlan* p, long long n_norm) {
+  unsigned int* ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
+  StepSlots s;
+  s.cur = ring + (int)(p->step_seq % 3);
+  s.prev = ring + (int)((p->step_seq + 2) % 3);
+  s.clr = ring + (int)((p->step_seq + 1) % 3);
+  s.loss_acc = p->acc + p->ring_off + 3;
+  s.inv_count = 1.0f / (3.0f * (float)n_norm);
+  return s;
+}
+
+// First launch of a fused step: forward chain + RGB head + loss + head backward + dgrad chain (one persistent kernel).
+static int launch_step_chain(NppPlan* p, const float* coords, const float* target, const float* mask, long long n,
+                             const StepSlots& sl, cudaStream_t st) {
   if (!p->params) return fail("npp_plan_bind has not been called");
-  if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
   CKI(prepare(p, n));
   CKI(set_smem_attrs());
   if (!p->acc_clean) {   // a call of the unfused path left its sums behind
@@ -1533,9 +1565,6 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
   CKI(select_encoding(p, coords, n, st, nullptr, &prefetched));
   const Layer& last = p->layers.back();
   if (last.out != BN) return fail("fused step: the last dense layer must be one 256-column tile");
-  unsigned int* ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
-  const int cur = (int)(p->step_seq % 3), prev = (int)((p->step_seq + 2) % 3), clr = (int)((p->step_seq + 1) % 3);
-  float* loss_acc = p->acc + p->ring_off + 3;
   HeadArgs hd;
   memset(&hd, 0, sizeof(hd));
   hd.w = p->params + p->rgb_w_off;
@@ -1544,19 +1573,26 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
   hd.mask = mask;
   hd.logits = nullptr;
   hd.head_acc = p->acc + p->headacc_off;
-  hd.loss_acc = loss_acc;
-  hd.amax_prev = ring + prev;
-  hd.amax_next = ring + cur;
-  hd.inv_count = 1.0f / (3.0f * (float)n_norm);
+  hd.loss_acc = sl.loss_acc;
+  hd.amax_prev = sl.prev;
+  hd.amax_next = sl.cur;
+  hd.inv_count = sl.inv_count;
   hd.width = p->head_width;
   const bool alt = p->enc_set != 0;
-  {
-    ProfScope ps(p, st, PROF_GEMM_FWD, 1);
-    const std::vector<KmajorParams>& ops = alt ? p->step_params_alt : p->step_params;
-    CKI(launch_chain(alt ? p->d_step_ops_alt : p->d_step_ops, ops.data(), (int)ops.size(), (int)n, p->num_sms, st,
-                     p->fwd_subs + p->dgrad_subs, p->cluster, nullptr, 0, nullptr, p->cfg.activation, &hd, p->pdl));
-    ++p->launches;
-  }
+  ProfScope ps(p, st, PROF_GEMM_FWD, 1);
+  const std::vector<KmajorParams>& ops = alt ? p->step_params_alt : p->step_params;
+  CKI(launch_chain(alt ? p->d_step_ops_alt : p->d_step_ops, ops.data(), (int)ops.size(), (int)n, p->num_sms, st,
+                   p->fwd_subs + p->dgrad_subs, p->cluster, nullptr, 0, nullptr, p->cfg.activation, &hd, p->pdl));
+  ++p->launches;
+  return 0;
+}
+
+static int run_fused_step(NppPlan* p, const float* coords, const float* target, const float* mask, long long n,
+                          long long n_norm, const AdamScalars& ad, float* loss, cudaStream_t st) {
+  if (!p->m || !p->v) return fail("npp_train_step needs exp_avg and exp_avg_sq bound");
+  const StepSlots sl = step_slots(p, n_norm);
+  CKI(launch_step_chain(p, coords, target, mask, n, sl, st));
+  const bool alt = p->enc_set != 0;
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
     CKI(launch_wgrad(alt ? p->wg_params_alt : p->wg_params, p->num_sms, st, p->wg_cluster, p->pdl));
@@ -1567,11 +1603,11 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
     ProfScope ps(p, st, PROF_ADAM, 1);
     StepReset rs;
     rs.on = 1;
-    rs.inv_count = hd.inv_count;
-    rs.loss_acc = loss_acc;
+    rs.inv_count = sl.inv_count;
+    rs.loss_acc = sl.loss_acc;
     rs.loss_out = loss;
-    rs.amax_clear = ring + clr;
-    CKI(launch_update(p, ad, ring + prev, rs, p->pdl, st));
+    rs.amax_clear = sl.clr;
+    CKI(launch_update(p, ad, sl.prev, rs, p->pdl, st));
   }
   ++p->step_seq;
   return 0;
@@ -1619,7 +1655,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     unsigned int* amax = reinterpret_cast<unsigned int*>(p->acc + p->amax_off);
     __half* delta = p->bufs[last.buf_delta].ptr;
     float* head_acc = p->acc + p->headacc_off;
-    float* bias_acc = p->acc + last.bg_off;
+    float* bias_acc = nullptr;   // the weight-gradient kernel sums the bias gradients (WgUnit::bias_off)
     unsigned int* bar = p->d_barrier;
     void* args[] = {&hp, &dp, &ld, &width, &ni, &w, &b, &target, &mask, &ic, &logits, &g, &loss, &amax,
                     &delta, &ldd, &head_acc, &bias_acc, &bar};
@@ -1663,6 +1699,107 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
     CKI(launch_update(p, adam_scalars(lr, beta1, beta2, eps, step), reinterpret_cast<unsigned int*>(p->acc + p->amax_off), rs,
                       0, st));
   }
+  return 0;
+}
+
+// ---- the fused step in three phases (data parallelism inside one image: the gradient arena must exist between the
+//      backward pass and Adam, and the all-reduce of one layer group should overlap the weight-gradient GEMMs of the next)
+int npp_step_forward_backward(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n,
+                              int64_t n_norm, void* stream) {
+  if (!p || !coords || !target) return fail("npp_step_forward_backward: null argument");
+  if (n_norm <= 0) return fail("n_norm must be positive");
+  if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
+  p->launches = 0;
+  const StepSlots sl = step_slots(p, n_norm);
+  CKI(launch_step_chain(p, coords, target, mask, n, sl, (cudaStream_t)stream));
+  return mark_busy(p, (cudaStream_t)stream);
+}
+
+int npp_plan_layer_count(const NppPlan* p) { return p ? (int)p->layers.size() : 0; }
+
+int npp_plan_layer_grad_range(const NppPlan* p, int32_t layer_begin, int32_t layer_end, int64_t* offset, int64_t* count) {
+  if (!p || !offset || !count) return fail("npp_plan_layer_grad_range: null argument");
+  const int nl = (int)p->layers.size();
+  if (layer_begin < 0 || layer_end > nl || layer_begin >= layer_end) return fail("layer range out of bounds");
+  *offset = p->layers[layer_begin].w_off;
+  // weights and biases are laid out layer by layer, rgb_linear right behind the last dense layer
+  const long long end = layer_end == nl ? p->arena_trained : p->layers[layer_end].w_off;
+  *count = end - *offset;
+  return 0;
+}
+
+int npp_step_wgrad(NppPlan* p, int32_t layer_begin, int32_t layer_end, int64_t n, int64_t n_norm, void* stream) {
+  if (!p) return fail("null plan");
+  const int nl = (int)p->layers.size();
+  if (layer_begin < 0 || layer_end > nl || layer_begin >= layer_end) return fail("npp_step_wgrad: layer range out of bounds");
+  if (p->prepared_n != n) return fail("npp_step_wgrad: call npp_step_forward_backward with the same row count first");
+  cudaStream_t st = (cudaStream_t)stream;
+  // split factor of this launch: enough row splits to give every CTA pair a unit, at least one per 32768 rows
+  const int tiles = p->tile_begin[layer_end] - p->tile_begin[layer_begin];
+  const int slots = p->num_sms / p->wg_cluster;
+  int S = std::max(1, (slots + tiles / 2) / tiles);
+  S = std::max(S, (int)((n + WG_ROWS_PER_SPLIT - 1) / WG_ROWS_PER_SPLIT));
+  S = std::min(S, std::min(p->slabs_alloc, (int)NPP_MAX_SPLITS));
+  const int kb_total = (int)((n + BK - 1) / BK);
+  if (S > kb_total) S = kb_total;
+  NppPlan::GroupTable* gt = nullptr;
+  for (auto& g : p->groups)
+    if (g.lb == layer_begin && g.le == layer_end && g.splits == S) gt = &g;
+  if (gt == nullptr) {
+    std::vector<WgUnit> units;
+    for (int sidx = 0; sidx < S; ++sidx)
+      for (int t = p->tile_begin[layer_begin]; t < p->tile_begin[layer_end]; ++t) {
+        WgUnit u = p->tile_units[t];
+        u.split = sidx;
+        units.push_back(u);
+      }
+    NppPlan::GroupTable g;
+    g.lb = layer_begin; g.le = layer_end; g.splits = S; g.n_units = (int)units.size(); g.d_units = nullptr;
+    CK(cudaMalloc(&g.d_units, units.size() * sizeof(WgUnit)));
+    CK(cudaMemcpy(g.d_units, units.data(), units.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
+    p->groups.push_back(g);
+    gt = &p->groups.back();
+  }
+  WgradParams w = p->enc_set ? p->wg_params_alt : p->wg_params;
+  w.units = gt->d_units;
+  w.n_units = gt->n_units;
+  w.kb_per_split = (kb_total + S - 1) / S;
+  w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
+  {
+    ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
+    CKI(launch_wgrad(w, p->num_sms, st, p->wg_cluster, 0));
+    ++p->launches;
+  }
+  {
+    ProfScope ps(p, st, PROF_FINALIZE, 1);
+    const StepSlots sl = step_slots(p, n_norm);
+    dim3 grid(128, (unsigned)(layer_end - layer_begin));
+    npp_grad_finalize_kernel<<<grid, 256, 0, st>>>(p->d_fin + layer_begin, p->partial, w.n_splits, p->slab_stride, p->acc,
+                                                   sl.prev, p->grads, sl.inv_count);
+    CK(cudaGetLastError());
+    ++p->launches;
+    if (layer_end == nl) {   // rgb_linear: unscaled fp32 sums written by the head epilogue
+      npp_copy_kernel<<<2, 256, 0, st>>>(p->acc + p->headacc_off, p->grads + p->rgb_w_off, 3 * p->head_width);
+      npp_copy_kernel<<<1, 32, 0, st>>>(p->acc + p->headacc_off + 3 * p->head_width, p->grads + p->rgb_b_off, 3);
+      CK(cudaGetLastError());
+      p->launches += 2;
+    }
+  }
+  return mark_busy(p, st);
+}
+
+int npp_step_finish(NppPlan* p, int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
+                    void* stream) {
+  if (!p) return fail("null plan");
+  if (n_norm <= 0) return fail("n_norm must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  CKI(run_adam(p, lr, beta1, beta2, eps, step, st));
+  CKI(run_shadow(p, st));
+  const StepSlots sl = step_slots(p, n_norm);
+  npp_step_finish_kernel<<<8, 256, 0, st>>>(p->acc, (int)p->acc_zero_floats, sl.loss_acc, loss, sl.clr);
+  CK(cudaGetLastError());
+  ++p->launches;
+  ++p->step_seq;
   return 0;
 }
 
@@ -2006,6 +2143,7 @@ int npp_debug_wgrad(const void* a, const void* b, float* c, int rows, int m, int
         u.out_off = m0 * n + n0;
         u.ld = n;
         u.ncols_left = n - n0;
+        u.bias_off = -1;
         units.push_back(u);
       }
   WgUnit* d_units = nullptr;

@@ -709,7 +709,7 @@ __device__ __forceinline__ void npp_head_bwd_part(const float* g, const __half* 
         if (idx >= 1024) atomicAdd(head_acc + 3 * width + (idx - 1024), t);
         else if (col < width) {
           if (a < 3) atomicAdd(head_acc + a * width + col, t);
-          else atomicAdd(bias_acc + col, t);
+          else if (bias_acc != nullptr) atomicAdd(bias_acc + col, t);
         }
       }
       __syncthreads();
@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(256, 2) npp_head_fused_reg_kernel(
     for (int q = 0; q < 8; ++q) t += red[q][idx];
     const int acc_i = idx >> 8, col = idx & (W - 1);
     if (acc_i < 3) atomicAdd(head_acc + acc_i * W + col, t);
-    else atomicAdd(bias_acc + col, t);
+    else if (bias_acc != nullptr) atomicAdd(bias_acc + col, t);
   }
   if (threadIdx.x < 3) atomicAdd(head_acc + 3 * W + threadIdx.x, gs[threadIdx.x]);
 }
@@ -1112,9 +1112,11 @@ __global__ void __launch_bounds__(256) npp_grad_finalize_kernel(const FinalizeLa
                                                                 const float* __restrict__ partial, int n_splits,
                                                                 long long slab_stride, const float* __restrict__ bias_acc,
                                                                 const unsigned int* __restrict__ amax_bits,
-                                                                float* __restrict__ grads) {
+                                                                float* __restrict__ grads, float step_inv_count) {
   const FinalizeLayer L = layers[blockIdx.y];
-  const float inv = 1.0f / npp_grad_scale(__uint_as_float(*amax_bits));
+  // step_inv_count > 0: the deltas carry the fused step's scale (npp_step_amax of the previous step's maximum)
+  const float inv = 1.0f / npp_grad_scale(step_inv_count > 0.f ? npp_step_amax(amax_bits, step_inv_count)
+                                                                : __uint_as_float(*amax_bits));
   for (int o = blockIdx.x; o < L.out; o += gridDim.x) {
     const float* prow = partial + L.pg_off + (long long)o * L.kpad;
     float* grow = grads + L.w_off + (long long)o * L.in_ref;
@@ -1356,6 +1358,16 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
       if (grads) grads[idx] = g;
       params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
     }
+  }
+}
+
+// End of a three-phase (data-parallel) step: hand the loss out, clear the step accumulators, rotate the max|g| ring.
+__global__ void npp_step_finish_kernel(float* acc, int acc_n, float* loss_acc, float* loss_out, unsigned int* amax_clear) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < acc_n; i += gridDim.x * blockDim.x) acc[i] = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (loss_out != nullptr) *loss_out = *loss_acc;
+    *loss_acc = 0.f;
+    *amax_clear = 0u;
   }
 }
 

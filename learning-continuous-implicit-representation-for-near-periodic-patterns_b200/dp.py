@@ -27,18 +27,37 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
 
 
 class DataParallelStep:
-    """One train step of a row-sharded batch on a Plan: forward, masked MSE normalised by the global row count,
-    backward, gradient all-reduce, identical Adam on every rank.  Returns this rank's share of the loss (the sum
-    over ranks is the global loss)."""
+    """One train step of a row-sharded batch on a Plan: the fused forward + head + backward chain on this rank's rows
+    (loss normalised by the global row count), then the weight gradients in a few layer groups, each group's slice of
+    the flat fp32 gradient arena all-reduced (NCCL, asynchronously on its own stream) while the next group's GEMMs
+    run, then identical Adam on every rank.  Returns this rank's share of the loss (the sum over ranks is the global
+    loss) as a device scalar."""
 
-    def __init__(self, plan):
+    def __init__(self, plan, n_buckets: int = 3):
         self.plan = plan
+        nl = plan.layer_count()
+        n_buckets = max(1, min(int(n_buckets), nl))
+        # last layers first (any order is correct: the whole backward chain has run before the first group starts)
+        edges = [round(nl * k / n_buckets) for k in range(n_buckets + 1)]
+        self.groups = [(edges[k], edges[k + 1]) for k in range(n_buckets - 1, -1, -1)]
+        self.buckets = [plan.grad_range(lb, le) for lb, le in self.groups]
+        self.loss = torch.zeros((), device=plan.device)
+        self.launches = 0
+        self.last_loss = self.loss
 
     def __call__(self, coords, target, mask, lr, n_global, step=None):
         plan = self.plan
-        logits = plan.forward(coords)
-        loss, g, _ = plan.mse(logits, target, mask, n_norm=n_global)
-        plan.backward(coords.shape[0], g)
-        allreduce_sum_(plan.grads[: plan.trained_floats])
-        plan.adam_step(lr, step=step)
-        return loss
+        n = coords.shape[0]
+        plan.step_forward_backward(coords, target, mask, n_norm=n_global)
+        pending = []
+        multi = world() > 1
+        for (lb, le), bucket in zip(self.groups, self.buckets):
+            plan.step_wgrad(lb, le, n, n_global)
+            if multi:
+                pending.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))
+        for w in pending:
+            w.wait()                      # the compute stream waits for the collective, the host does not
+        plan.step_finish(n_global, lr, self.loss, step=step)
+        self.launches = plan.launch_count()
+        self.last_loss = self.loss
+        return self.loss

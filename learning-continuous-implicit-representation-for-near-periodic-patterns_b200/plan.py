@@ -180,19 +180,26 @@ class Plan:
             v.copy_(src.to(self.device, torch.float32).reshape(v.shape))
         self.sync_weights()
 
-    def reset_parameters(self, seed: Optional[int] = None):
+    def reset_parameters(self, seed: Optional[int] = None, on_device: bool = False):
         """torch.nn.Linear default init for every tensor: U(-1/sqrt(in), 1/sqrt(in)) for weight and bias
         (the reference keeps PyTorch's default because weights_init_normal only touches Conv/BatchNorm,
-        models/helpers.py:65-71,140-141)."""
-        gen = torch.Generator(device="cpu")
+        models/helpers.py:65-71,140-141).  on_device: draw on the GPU (a fresh fit without a host round trip; another
+        random stream than the CPU generator) and clear the Adam state."""
+        gen = torch.Generator(device=self.device if on_device else "cpu")
         if seed is not None:
             gen.manual_seed(seed)
         views = self.param_views()
+        by_name = dict((t.name, t) for t in self.slots)
         for s in self.slots:
-            fan_in = s.shape[1] if len(s.shape) == 2 else dict((t.name, t) for t in self.slots)[
-                s.name.replace(".bias", ".weight")].shape[1]
+            fan_in = s.shape[1] if len(s.shape) == 2 else by_name[s.name.replace(".bias", ".weight")].shape[1]
             bound = 1.0 / math.sqrt(fan_in)
-            views[s.name].copy_((torch.rand(s.shape, generator=gen) * 2 - 1) * bound)
+            if on_device:
+                views[s.name].copy_((torch.rand(s.shape, generator=gen, device=self.device) * 2 - 1) * bound)
+            else:
+                views[s.name].copy_((torch.rand(s.shape, generator=gen) * 2 - 1) * bound)
+        if on_device and self.exp_avg is not None:
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
         self.sync_weights()
 
     def state(self) -> Dict[str, torch.Tensor]:
@@ -284,6 +291,32 @@ class Plan:
         nat.check(self.lib.npp_train_step(self.handle, coords.data_ptr(), target.data_ptr(), nat.ptr(mask), n,
                                           n if n_norm is None else int(n_norm), lr, betas[0], betas[1], eps, step,
                                           loss_out.data_ptr(), nat.current_stream()))
+
+    # ---- the step in three phases (data parallelism: the gradient arena is summed over the ranks in between)
+    def step_forward_backward(self, coords, target, mask, n_norm: int):
+        nat.check(self.lib.npp_step_forward_backward(self.handle, coords.data_ptr(), target.data_ptr(), nat.ptr(mask),
+                                                     coords.shape[0], int(n_norm), nat.current_stream()))
+
+    def layer_count(self) -> int:
+        return self.lib.npp_plan_layer_count(self.handle)
+
+    def grad_range(self, layer_begin: int, layer_end: int) -> torch.Tensor:
+        """View of the gradient arena holding weights + biases of the dense layers [layer_begin, layer_end) in
+        execution order (rgb_linear rides with the last layer)."""
+        off, cnt = C.c_int64(), C.c_int64()
+        nat.check(self.lib.npp_plan_layer_grad_range(self.handle, layer_begin, layer_end, C.byref(off), C.byref(cnt)))
+        return self.grads[off.value: off.value + cnt.value]
+
+    def step_wgrad(self, layer_begin: int, layer_end: int, n: int, n_norm: int):
+        nat.check(self.lib.npp_step_wgrad(self.handle, layer_begin, layer_end, int(n), int(n_norm), nat.current_stream()))
+
+    def step_finish(self, n_norm: int, lr: float, loss_out: torch.Tensor, betas=(0.9, 0.999), eps: float = 1e-8,
+                    step: Optional[int] = None):
+        if step is None:
+            self.adam_steps += 1
+            step = self.adam_steps
+        nat.check(self.lib.npp_step_finish(self.handle, int(n_norm), lr, betas[0], betas[1], eps, step,
+                                           loss_out.data_ptr(), nat.current_stream()))
 
     def fit_run(self, coords_all: torch.Tensor, target_all: torch.Tensor, mask_all: Optional[torch.Tensor] = None, *,
                 lrate: float = 5e-4, lrate_decay: float = 500, decay_rate: float = 0.1, betas=(0.9, 0.999),
