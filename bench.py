@@ -387,7 +387,10 @@ def main():
     # only gets the SMs the step's kernels leave idle (the chain kernels occupy 128 of the 148).
     torch.cuda.set_stream(torch.cuda.Stream(device=local_rank, priority=-1))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that falls out of step must fail within minutes, not after NCCL's 10-minute default
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -420,7 +423,7 @@ def main():
         step = fit.step
     plan = fit.plan
     my_rows = fit.rows
-    total_ms, t0, t1, done = timed_loop(step, args.steps, args.warmup, barrier)
+    total_ms, t0, t1, done = timed_loop(step, args.steps, args.warmup, barrier, settle_s=0.0 if dp else 0.5)
     launches_per_step = plan.launch_count() if not dp else dps.launches
     clocks = sampler.stop(t0, t1) if sampler else None
     total_ms = max_over_ranks(total_ms)
@@ -613,7 +616,8 @@ def bench_dp_cfg4(rank, world, dev, barrier, max_over_ranks, steps=30):
     def step(i):
         b = i % f.nb
         dps(f.coords[b], f.target[b], f.mask[b], f.lr, rows)
-    ms, _, _, _ = timed_loop(step, steps, 5, barrier, rewarm=10, settle_s=0.2)
+    # every rank must run the SAME number of steps (each one holds collectives): no time-based warm-up here
+    ms, _, _, _ = timed_loop(step, steps, 5, barrier, rewarm=10, settle_s=0.0)
     ms = max_over_ranks(ms)
     return {"value": rows * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
             "rows_per_step": rows, "rows_per_step_per_gpu": rows // world, "scaling": "strong",
