@@ -1136,7 +1136,7 @@ static int run_adam(NppPlan* p, float lr, float beta1, float beta2, float eps, l
   const float inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
   ProfScope ps(p, st, PROF_ADAM, 1);
   npp_adam_kernel<<<p->num_sms * 4, 256, 0, st>>>(p->params, p->grads, p->m, p->v, p->arena_trained, beta1, beta2,
-                                                  step_size, inv_sqrt_bc2, eps);
+                                                  step_size, inv_sqrt_bc2, eps, 1);
   CK(cudaGetLastError());
   ++p->launches;
   return 0;
@@ -1411,9 +1411,11 @@ int npp_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
   long long blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 592) blocks = 592;
+  // views into larger tensors (storage offsets) need not be 16-byte aligned: those take the scalar loop
+  const int vec4 = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
   npp_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, beta1,
                                                                     beta2, (float)((double)lr / bc1),
-                                                                    (float)(1.0 / std::sqrt(bc2)), eps);
+                                                                    (float)(1.0 / std::sqrt(bc2)), eps, vec4);
   CK(cudaGetLastError());
   return 0;
 }

@@ -1381,8 +1381,8 @@ __global__ void npp_copy_kernel(const float* __restrict__ src, float* __restrict
 __global__ void __launch_bounds__(256) npp_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, long long n,
                                                        float beta1, float beta2, float step_size, float inv_sqrt_bc2,
-                                                       float eps) {
-  const long long n4 = n >> 2;
+                                                       float eps, int vec4) {
+  const long long n4 = vec4 ? n >> 2 : 0;   // vec4 == 0: some pointer is not 16-byte aligned, everything takes the scalar loop
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];

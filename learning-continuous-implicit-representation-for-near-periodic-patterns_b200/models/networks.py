@@ -40,7 +40,14 @@ class _NppFunction(torch.autograd.Function):
         if ctx.generation != net._generation:
             raise RuntimeError("NPP_Net: the activations of this forward were overwritten by a later forward; "
                                "call backward() before running the network again")
+        # plan.backward OVERWRITES the gradient arena.  If the arena views are still installed as .grad (a previous
+        # backward without zero_grad() in between: micro-batch accumulation, or a foreign training loop), keep what
+        # they hold and add it back, like autograd's AccumulateGrad would.
+        pending = any(p.grad is g and g is not None for p, g in zip(net._params, net._grad_view_list))
+        keep = net._plan.grads[: net._plan.trained_floats].clone() if pending else None
         net._plan.backward(ctx.n, grad_logits)
+        if keep is not None:
+            net._plan.grads[: net._plan.trained_floats].add_(keep)
         net._publish_grads()
         return None, None, None
 
@@ -71,7 +78,12 @@ class _FusedNet(nn.Module):
                              "and the other networks with the regular ones")
         self._spec = spec
         # `i in skips` is tested for i < D (forward) and i < D-1 (constructor): a skip index beyond the trunk is inert
-        # (the search default D=4 with skips=[4], options/arg_config.py:114)
+        # (the search default D=4 with skips=[4], options/arg_config.py:114).  skips[0] == D-1 is the one value the
+        # reference cannot run: forward concatenates after the last trunk layer and feature_linear1 then fails on the
+        # shape (networks.py:70-73) -- refuse it instead of training a different network.
+        if skips[0] == D - 1:
+            raise ValueError(f"skips=[{skips[0]}] with D={D}: the reference forward concatenates the input after the last "
+                             "trunk layer and fails in feature_linear1; use a skip index < D-1, or >= D for none")
         self._skip_layer = skips[0] if skips[0] < D - 1 else -1
         self._model_kind = _planmod.MODEL_LIGHT if light else None
         self._activation = 'snake' if activation == 'snake' else 'relu'     # networks.py:51-54: anything else is relu

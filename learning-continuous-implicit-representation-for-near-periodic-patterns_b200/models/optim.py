@@ -25,9 +25,19 @@ class NppAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if len(self.param_groups) != 1:
+            raise RuntimeError("NppAdam updates the whole parameter arena with one set of hyper-parameters: "
+                               "exactly one param_group is supported (the reference builds one, helpers.py:164)")
         group = self.param_groups[0]
         if self.net is not None and any(p.grad is not None for p in self._own):
             plan = self.net._plan
+            # the fused kernel runs over the whole trained arena: a frozen tensor or one without a gradient would be
+            # updated from stale arena contents where torch.optim.Adam skips it
+            bad = [n for n, p, g in zip(self.net._param_names, self.net._params, self.net._grad_view_list)
+                   if g is not None and (p.grad is None or not p.requires_grad)]
+            if bad:
+                raise RuntimeError("NppAdam cannot skip individual NPP-Net tensors (no gradient / requires_grad=False): "
+                                   + ", ".join(bad[:4]) + (" ..." if len(bad) > 4 else ""))
             for p, g in zip(self.net._params, self.net._grad_view_list):
                 if g is None or p.grad is None or p.grad is g:
                     continue

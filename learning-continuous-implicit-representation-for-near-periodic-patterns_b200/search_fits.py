@@ -6,8 +6,9 @@ the 148 SMs busy and is bound by the latency of its dependent kernels, so the ca
 fits on the GPU at the same time: one plan, one CUDA stream and one host thread per candidate (the C ABI releases the
 GIL for the whole `npp_fit_run` call, so the threads enqueue kernels in parallel).  There is no data-path collective.
 
-Scoring the fitted candidates (LPIPS + contextual loss on the held-out region, search.py:150-196) stays with the
-caller; `Plan.forward` / `NPP_Net_light.forward` under ``torch.no_grad()`` renders the pixels it needs.
+Only the ``--loss_type l2`` variant of that loop is covered (see `run_fits`); the default adaptive robust loss carries
+trained latents across candidates and stays with the drop-in modules.  Scoring the fitted candidates (LPIPS +
+contextual loss on the held-out region, search.py:150-196) stays with the caller; `Plan.forward` / `NPP_Net_light.forward` under ``torch.no_grad()`` renders the pixels it needs.
 """
 from __future__ import annotations
 
@@ -56,9 +57,20 @@ def gather_batches(image: torch.Tensor, train_coords: torch.Tensor, indices: tor
 
 def run_fits(plans: Sequence[Plan], coords_all: torch.Tensor, target_all: torch.Tensor, *, lrate: float = 5e-4,
              lrate_decay: float = 500, streams: Optional[Sequence[torch.cuda.Stream]] = None,
-             threads: bool = True) -> torch.Tensor:
+             threads: bool = True, loss_type: str = "l2") -> torch.Tensor:
     """Fit every plan on the same batches (or on its own, if coords_all / target_all are lists), concurrently.
-    Returns the losses [len(plans), iters]; the call returns once the current stream waits for every fit."""
+    Returns the losses [len(plans), iters]; the call returns once the current stream waits for every fit.
+
+    Equivalent to the reference loop only for ``--loss_type l2``: npp_fit_run trains with sigmoid + masked MSE
+    (img2mse(pred, gt, 'l2', ...), NPP_proposal/search.py:133).  The scripts' DEFAULT is 'robust_loss_adaptive'
+    (options/arg_config.py:34), whose latent alpha / scale are trained along with the network and carried from one
+    candidate to the next (the module-level adaptive_pix): that objective can rank candidates differently, so asking for
+    it here raises instead of silently fitting another loss.  Run the default loss through the drop-in modules
+    (models.helpers.create_npp_net + img2mse), which evaluate it with the fused adaptive-loss kernel."""
+    if loss_type != "l2":
+        raise NotImplementedError(
+            f"run_fits fits with loss_type='l2' only (got {loss_type!r}); the adaptive robust loss of the reference's "
+            "default configuration goes through models.helpers.create_npp_net + models.mse_calculator.img2mse")
     k = len(plans)
     per_plan = isinstance(coords_all, (list, tuple))
     iters = int((coords_all[0] if per_plan else coords_all).shape[0])

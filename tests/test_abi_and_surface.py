@@ -159,3 +159,23 @@ def test_weights_init_normal_touches_conv_and_batchnorm_only():
     torch.nn.Sequential(lin, conv, bn).apply(weights_init_normal)
     assert torch.equal(lin.weight, before)                       # Linear keeps PyTorch's default init
     assert conv.weight.abs().max() < 0.2 and abs(bn.weight.mean().item() - 1.0) < 0.1 and bn.bias.abs().max() == 0
+
+
+def test_alias_package_shares_module_objects():
+    """`import npp_b200.x` and the hyphenated package's `x` are ONE module (one library handle, one set of classes:
+    isinstance checks across the two import paths hold)."""
+    import importlib
+    import npp_b200  # noqa: F401
+    real = "learning-continuous-implicit-representation-for-near-periodic-patterns_b200"
+    for sub in ("_native", "plan", "robust_loss", "dp", "search_fits"):
+        a = importlib.import_module("npp_b200." + sub)
+        b = importlib.import_module(real + "." + sub)
+        assert a is b, sub
+
+
+def test_run_fits_refuses_the_adaptive_loss():
+    """The concurrent-fit path trains with 'l2' only; the reference's default --loss_type must not be silently replaced."""
+    import pytest
+    from npp_b200 import search_fits
+    with pytest.raises(NotImplementedError):
+        search_fits.run_fits([], None, None, loss_type="robust_loss_adaptive")

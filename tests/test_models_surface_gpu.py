@@ -281,3 +281,62 @@ def test_relu_activation_on_the_dropin_surface(monkeypatch):
         optimizer.step()
         losses.append(loss.item())
     assert losses[-1] < 0.8 * losses[0], losses[::6]
+
+
+def test_backward_accumulates_without_zero_grad():
+    """Two forward/backward passes without zero_grad() in between (micro-batch accumulation, foreign training loops):
+    .grad must hold the SUM, as autograd's AccumulateGrad gives for the reference modules -- the kernels overwrite
+    the gradient arena, so the drop-in layer has to add the earlier contents back."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.helpers import create_npp_net, render
+    from models.mse_calculator import img2mse
+    torch.manual_seed(0)
+    res = (64, 80)
+    args = _args(3)
+    angles = torch.Tensor([[83.0, 172.5], [90.0, 180.0], [41.3, 127.9]])
+    periods = torch.Tensor([[17.2, 14.9], [8.6, 7.45], [34.4, 29.8]])
+    kw, _, _, _, optimizer, embedder, per = create_npp_net(args, angles, periods, res, None)
+    model = kw['network_fn']
+    coords = [torch.stack([torch.randint(0, res[0], (700,)), torch.randint(0, res[1], (700,))], 1).float().cuda()
+              for _ in range(2)]
+    targets = [torch.rand(700, 3, device="cuda") for _ in range(2)]
+
+    def one(k):
+        x = torch.cat([embedder.embed(e.embed(coords[k].clone())) for e in per], 1)
+        loss = img2mse(render(None, x, args, **kw), targets[k], 'l2', None, None)
+        loss.backward()
+
+    names = [n for n, p in model.named_parameters() if not n.startswith("alpha_linear")]
+    singles = []
+    for k in range(2):
+        optimizer.zero_grad()
+        one(k)
+        singles.append({n: p.grad.clone() for n, p in model.named_parameters() if n in names})
+    optimizer.zero_grad()
+    one(0)
+    one(1)                      # no zero_grad in between
+    for n, p in model.named_parameters():
+        if n not in names:
+            continue
+        want = singles[0][n] + singles[1][n]
+        err = (p.grad - want).norm() / (want.norm() + 1e-30)
+        assert err < 1e-4, (n, err.item())     # identical kernels, only atomics order differs
+
+
+def test_unrunnable_skip_index_is_refused():
+    """skips[0] == D-1 concatenates after the last trunk layer in the reference forward, which then fails in
+    feature_linear1 (networks.py:70-73); the drop-in refuses it instead of training another network."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from models.embedder import get_embedder
+    from models.networks import NPP_Net_top1
+    res = (32, 32)
+    emb, freq_nerf = get_embedder(10, 0, res)
+    e, ch = get_embedder(10, 0, res, selected_angles=torch.Tensor([83.0, 172.5]), selected_periods=torch.Tensor([9.0, 7.0]),
+                         freq_scales=[1], freq_offsets=[0, -1, 1, 0.5, -0.5], angle_offsets=[0])
+    with pytest.raises(ValueError):
+        NPP_Net_top1(D=4, W=256, freq_nerf=freq_nerf, input_ch_periodic=ch, freq_scales=[1],
+                     freq_offsets=[0, -1, 1, 0.5, -0.5], angle_offsets=[0], output_ch=3, skips=[3], activation='snake')
+    NPP_Net_top1(D=4, W=256, freq_nerf=freq_nerf, input_ch_periodic=ch, freq_scales=[1],
+                 freq_offsets=[0, -1, 1, 0.5, -0.5], angle_offsets=[0], output_ch=3, skips=[4], activation='snake')
