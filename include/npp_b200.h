@@ -199,6 +199,17 @@ int npp_fit_run(NppPlan* plan, const float* coords_all, const float* target_all,
 int npp_gather_windows(const float* img, int32_t img_h, int32_t img_w, int32_t channels, const int64_t* rows,
                        const int64_t* cols, int64_t m, int32_t h, int32_t w, float* out, void* stream);
 
+/* Candidate filter of GridPatchSampler.sample_patch_real (models/sampler.py:127-216) for an integer lattice: for each
+ * of the n_samples fake centroids (centroids [n_samples, 2] int64, (row, col)) and each (i, j) in [-10, 10)^2, the
+ * centroid c = cent + i * shift1 + j * shift2 (shifts4 = {s1_row, s1_col, s2_row, s2_col}, HOST int64) is kept iff it
+ * lies strictly inside the image and its (2 half_h) x (2 half_w) window holds at most max_unknown unknown pixels
+ * (sampler.py:156-190; pixels outside the image count as unknown).  sat: device int64 [img_h + 1, img_w + 1],
+ * summed-area table of (mask < 0.5) with a zero first row / column.  keep: device uint8 [n_samples, 400], candidate
+ * q = (i + 10) * 20 + (j + 10) in the order of the reference's meshgrid.  No plan needed. */
+int npp_sampler_candidates(const int64_t* sat, int32_t img_h, int32_t img_w, const int64_t* centroids, int32_t n_samples,
+                           const int64_t* shifts4, int32_t half_h, int32_t half_w, float max_unknown, uint8_t* keep,
+                           void* stream);
+
 /* Optional input pipelining for npp_train_step (the data-loader analogue of NPP_completion/train.py:164-181, where
  * the reference gathers the next batch's rows of the encoding table): encodes `coords` of a FUTURE step into the
  * plan's second encoding buffer on an internal stream.  It waits for everything already enqueued on `stream`

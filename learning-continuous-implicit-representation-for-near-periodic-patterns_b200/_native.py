@@ -67,6 +67,8 @@ SIGNATURES = {
     "npp_encode_prefetch": (C.c_int, [_P, _P, C.c_int64, _P]),
     "npp_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "npp_gather_windows": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "npp_sampler_candidates": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int64), C.c_int32,
+                                         C.c_int32, C.c_float, _P, _P]),
     "npp_l2_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "npp_robust_adaptive_fwd_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
     "npp_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,

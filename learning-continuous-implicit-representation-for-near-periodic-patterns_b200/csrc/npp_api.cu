@@ -1437,6 +1437,22 @@ int npp_gather_windows(const float* img, int32_t img_h, int32_t img_w, int32_t c
   return 0;
 }
 
+int npp_sampler_candidates(const int64_t* sat, int32_t img_h, int32_t img_w, const int64_t* centroids, int32_t n_samples,
+                           const int64_t* shifts4, int32_t half_h, int32_t half_w, float max_unknown, uint8_t* keep,
+                           void* stream) {
+  if (!sat || !centroids || !shifts4 || !keep) return fail("npp_sampler_candidates: null argument");
+  if (img_h <= 0 || img_w <= 0 || half_h <= 0 || half_w <= 0) return fail("npp_sampler_candidates: sizes must be positive");
+  if (n_samples <= 0) return 0;
+  if (n_samples > (1 << 20)) return fail("npp_sampler_candidates: too many samples");
+  static_assert(sizeof(long long) == sizeof(int64_t), "index tables are int64");
+  const int total = n_samples * 400;
+  npp_sampler_candidates_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(sat), img_h, img_w, reinterpret_cast<const long long*>(centroids), n_samples,
+      shifts4[0], shifts4[1], shifts4[2], shifts4[3], half_h, half_w, max_unknown, keep);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int npp_l2_fwd_bwd(const float* x, const float* y, const float* mask, int64_t n, float* loss, float* grad_x,
                    void* stream) {
   if (!x || !y || !loss || !grad_x) return fail("npp_l2_fwd_bwd: null argument");

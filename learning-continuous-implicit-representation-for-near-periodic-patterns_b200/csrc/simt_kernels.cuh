@@ -433,6 +433,32 @@ __global__ void __launch_bounds__(256) npp_gather_windows_kernel(const float* __
   }
 }
 
+// Candidate real-patch centroids of GridPatchSampler.sample_patch_real (models/sampler.py:127-216, integer lattice):
+// for fake centroid n and (i, j) in [-10, 10)^2 (q = (i + 10) * 20 + (j + 10), the order of the reference's
+// meshgrid / reshape), c = cent[n] + i * s1 + j * s2 in (row, col).  keep[n * 400 + q] = 1 iff the centroid lies
+// strictly inside the image (sampler.py:156-159) and its window [row - hh, row + hh) x [col - wh, col + wh) holds at
+// most `thresh` unknown pixels (mask < 0.5; outside the image counts as unknown: zero padding), counted in O(1) from
+// the summed-area table sat [H + 1, W + 1] (the reference crops every candidate window, sampler.py:171-190).
+__global__ void __launch_bounds__(256) npp_sampler_candidates_kernel(const long long* __restrict__ sat, int H, int W,
+                                                                     const long long* __restrict__ cent, int n_samples,
+                                                                     long long s1r, long long s1c, long long s2r,
+                                                                     long long s2c, int hh, int wh, float thresh,
+                                                                     unsigned char* __restrict__ keep) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_samples * 400) return;
+  const int n = idx / 400, q = idx - n * 400;
+  const long long i = q / 20 - 10, j = q % 20 - 10;
+  const long long r = cent[2 * n] + i * s1r + j * s2r, c = cent[2 * n + 1] + i * s1c + j * s2c;
+  const bool in_bound = r > 0 && r < H - 1 && c > 0 && c < W - 1;
+  const long long h = 2 * hh, w = 2 * wh, r0 = r - hh, c0 = c - wh;
+  const long long ra = min(max(r0, 0LL), (long long)H), rb = min(max(r0 + h, 0LL), (long long)H);
+  const long long ca = min(max(c0, 0LL), (long long)W), cb = min(max(c0 + w, 0LL), (long long)W);
+  const long long pitch = W + 1;
+  const long long inside = sat[rb * pitch + cb] - sat[ra * pitch + cb] - sat[rb * pitch + ca] + sat[ra * pitch + ca];
+  const long long unknown = inside + (h * w - (rb - ra) * (cb - ca));
+  keep[idx] = (in_bound && !((float)unknown > thresh)) ? 1 : 0;
+}
+
 // sigmoid + masked MSE (models/helpers.py:55-56, models/mse_calculator.py:13-27 'l2' branch)
 //   y_hat = sigmoid(logit); d = (y_hat - y) * (m + 0.3 (1 - m)); loss = mean(d^2) over n_norm*3
 // also emits g = dLoss/dlogit and the running max |g| (as uint bits) for the fp16 delta scale.

@@ -14,6 +14,7 @@ What changed: the reference tiles the full image once per candidate (up to N_sam
 sampler.py:171-178) and materialises every stride-ps/10 unfold patch (sampler.py:66-84).  Here the unknown-pixel
 count of any window comes from a summed-area table in O(1) and only the patches that are returned are cropped.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -21,12 +22,41 @@ import torch
 import torch.nn.functional as F  # noqa: F401  (re-exported like the reference module)
 
 
-def _choice(n, k):
+_device_gen = {}
+
+
+def _mode():
+    return os.environ.get("NPP_B200_SAMPLER", "parity")
+
+
+def _uniform(device):
+    """The patch-source draw of sample_patches (np.random.uniform(0, 1), sampler.py:324)."""
+    if _mode() == "device" and device.type == "cuda":
+        return float(torch.rand(1, device=device, generator=_generator(device)).item())
+    return np.random.uniform(0, 1)
+
+
+def _generator(device):
+    g = _device_gen.get(device)
+    if g is None:
+        g = _device_gen[device] = torch.Generator(device=device)       # Philox, seeded from torch's global seed
+        g.manual_seed(torch.initial_seed())
+    return g
+
+
+def _choice(n, k, device=None):
     """np.random.choice(n, size=[k], replace=False) of the reference (sampler.py:229,260).  numpy's legacy RandomState
     shuffles all n entries to draw k of them (1.9 ms for a 512 x 512 pool, more than the rest of sample_patches); the
     default keeps that call so the host RNG stream stays the reference's.  NPP_B200_SAMPLER=fast draws k distinct
-    indices by rejection instead: same distribution (uniform without replacement), O(k), a different RNG stream."""
-    if os.environ.get("NPP_B200_SAMPLER", "parity") != "fast" or 4 * k > n:
+    indices by rejection instead: same distribution (uniform without replacement), O(k), a different RNG stream;
+    NPP_B200_SAMPLER=device does the same with the CUDA (Philox) generator, no host RNG at all."""
+    if _mode() == "device" and device is not None and device.type == "cuda" and 4 * k <= n:
+        g = _generator(device)
+        idx = torch.randint(0, n, (k,), device=device, generator=g)
+        while len(torch.unique(idx)) < k:
+            idx = torch.randint(0, n, (k,), device=device, generator=g)
+        return idx.cpu().numpy()
+    if _mode() not in ("fast", "device") or 4 * k > n:
         return np.random.choice(n, size=[k], replace=False)
     idx = np.random.randint(0, n, size=k)
     while len(np.unique(idx)) < k:
@@ -120,6 +150,9 @@ class GridPatchSampler():
         # only the top-1 periodicity is used for sampling; first coordinate along the vertical direction
         selected_shifts = selected_shifts[0]
         self.selected_shifts = [torch.tensor([s[1], s[0]]) for s in selected_shifts]
+        self._shifts_integral = all(_is_integral(s) for s in self.selected_shifts)
+        r = np.arange(-10, 10)
+        self._dist400 = (np.abs(r)[:, None] + np.abs(r)[None, :]).reshape(-1).astype(np.int64)   # |i| + |j|, (i, j) order
         self.no_reg_sampling = no_reg_sampling
         self.coord_patches = None
         self.reset_patchsize(img, mask, patch_size, N_samples)
@@ -162,10 +195,75 @@ class GridPatchSampler():
 
         self.pool_train = _get_valid_centroid(pool_train)
         self.pool_val = _get_valid_centroid(pool_val)
+        # CUDA fast path: integer pools (the scripts build them with np.nonzero) are mirrored on the host once, so that a
+        # draw's centroids, window index tables and lattice candidates need no device round trip per call
+        self._pool_host = {}
+        if self.device.type == "cuda":
+            for name, pool in (("train", self.pool_train), ("val", self.pool_val)):
+                if pool.shape[0] and _is_integral(pool):
+                    self._pool_host[name] = pool.cpu().numpy().astype(np.int64)
+        self._last_cent_host = None
 
     # ------------------------------------------------------------------------------------------
+    def _sample_real_fused(self, cent, topk, invalid_ratio):
+        """CUDA path of the periodicity-guided strategy for an integer lattice: ONE kernel evaluates all N x 400 candidate
+        centroids (bounds + unknown-pixel ratio from the summed-area table), the tiny ranking runs on the host with the
+        reference's own torch.topk call on a CPU tensor -- many candidates tie on |i| + |j| and torch.topk's tie order is
+        implementation defined, so this reproduces the reference's CPU results (the goldens) on any device -- and two
+        gather kernels cut the selected windows.  Replaces ~40 small CUDA launches and several host round trips."""
+        from ._core import native as _nat
+        hh, wh = self.patch_size_h_half, self.patch_size_w_half
+        N = self.N_samples
+        cent_h = cent if isinstance(cent, np.ndarray) else cent.cpu().numpy().astype(np.int64)   # [N, 2]
+        cent_d = torch.as_tensor(cent_h, device=self.device)
+        s1, s2 = (np.asarray(x.cpu().numpy(), np.int64) for x in self.selected_shifts)
+        shifts4 = (C.c_int64 * 4)(int(s1[0]), int(s1[1]), int(s2[0]), int(s2[1]))
+        keep = torch.empty(N * 400, dtype=torch.uint8, device=self.device)
+        thresh = float(np.float32(hh * wh * 4 * invalid_ratio))        # torch compares an int64 tensor with a float in fp32
+        _nat.check(_nat.lib().npp_sampler_candidates(self._mask_counter.sat.data_ptr(), self.height, self.width,
+                                                     cent_d.data_ptr(), N, shifts4, hh, wh, thresh, keep.data_ptr(),
+                                                     _nat.current_stream()))
+        keep_h = keep.cpu().numpy().reshape(N, 400).astype(bool)       # the one synchronising copy
+        dist_all = self._dist400
+        sel_cent, weight_topks = [], []
+        self.last_topk_distance = []
+        topk_min = topk
+        for i in range(N):
+            q = np.nonzero(keep_h[i])[0]
+            distance = torch.from_numpy(dist_all[q].copy())
+            distance[distance == 0] = 10000                            # the patch itself is never its own reference
+            if min(len(distance) - 1, topk) < topk_min:
+                topk_min = min(len(distance) - 1, topk)
+                if topk_min <= 0:
+                    return None, None, None, 0
+            distance_topk, inds_topk = torch.topk(distance, k=topk_min, largest=False)
+            self.last_topk_distance.append(distance_topk.clone())
+            distance_topk = 1 / distance_topk
+            weight_topks.append(distance_topk / torch.sum(distance_topk))
+            qs = q[inds_topk.numpy()]
+            ii, jj = qs // 20 - 10, qs % 20 - 10
+            sel_cent.append(cent_h[i][None, :] + ii[:, None] * s1[None, :] + jj[:, None] * s2[None, :])
+        if topk_min < topk:
+            weight_topks = [w[:topk_min] for w in weight_topks]
+            sel_cent = [c[:topk_min] for c in sel_cent]
+        weight_topks = torch.cat(weight_topks).to(self.device)
+        cents = np.concatenate(sel_cent)                                # [N * topk_min, 2]
+        rows = torch.as_tensor((cents[:, 0] - hh)[:, None] + np.arange(2 * hh)[None, :], device=self.device)
+        cols = torch.as_tensor((cents[:, 1] - wh)[:, None] + np.arange(2 * wh)[None, :], device=self.device)
+        img_p = _gather_window(self.img, rows, cols).reshape(N, topk_min, 3, 2 * hh, 2 * wh)
+        mask_p = _gather_window(self.mask, rows, cols).reshape(N, topk_min, 1, 2 * hh, 2 * wh)
+        return img_p.permute(0, 1, 3, 4, 2), mask_p.permute(0, 1, 3, 4, 2), weight_topks, topk_min
+
     def sample_patch_real(self, fake_coords=None, topk=5, invalid_ratio=0.3):
         hh, wh = self.patch_size_h_half, self.patch_size_w_half
+        if fake_coords is not None and not self.no_reg_sampling and self.device.type == "cuda" and \
+                self.img.dtype == torch.float32 and self._shifts_integral and fake_coords.shape[0] == self.N_samples and \
+                os.environ.get("NPP_B200_SAMPLER_FUSED", "1") != "0":
+            if self._last_cent_host is not None:        # the centroids sample_patch_fake just drew (host mirror)
+                return self._sample_real_fused(self._last_cent_host, topk, invalid_ratio)
+            cent = fake_coords[:, hh, wh, :]
+            if _is_integral(cent):
+                return self._sample_real_fused(cent, topk, invalid_ratio)
         if fake_coords is not None and not self.no_reg_sampling:
             N = fake_coords.shape[0]
             cent = fake_coords[:, hh, wh, :].to(self.device)                                  # [N,2] (row, col)
@@ -223,7 +321,7 @@ class GridPatchSampler():
             select_mask_patches = _gather_window(self.mask, rows, cols).reshape(self.N_samples, topk_min, 1, 2 * hh, 2 * wh)
         else:
             ps = self._patch_size
-            select_inds = _choice(self._unfold_r0.shape[0], self.N_samples * topk)
+            select_inds = _choice(self._unfold_r0.shape[0], self.N_samples * topk, self.device)
             sel = torch.as_tensor(select_inds, device=self.device)
             r0s, c0s = self._unfold_r0[sel], self._unfold_c0[sel]
             select_img_patches = _crop(self._unfold_img, r0s, c0s, ps, ps).reshape(self.N_samples, topk, 3, ps, ps)
@@ -237,7 +335,20 @@ class GridPatchSampler():
     def sample_patch_fake(self, mode):
         pool = self.pool_train if mode == 'train' else self.pool_val
         hh, wh = self.patch_size_h_half, self.patch_size_w_half
-        select_inds = _choice(pool.shape[0], self.N_samples)
+        select_inds = _choice(pool.shape[0], self.N_samples, pool.device)
+        pool_h = self._pool_host.get(mode)
+        self._last_cent_host = None
+        if pool_h is not None and self.img.dtype == torch.float32:
+            # integer centroids: the glimpse rows / columns are c - size/2 + [0, size) (equal to the fp32 arithmetic of
+            # _nearest_index for every integer c, tests/test_sampler_parity.py), built on the host and cropped by one
+            # kernel per tensor
+            cent_h = pool_h[np.asarray(select_inds)]
+            rows = torch.as_tensor((cent_h[:, 0] - hh)[:, None] + np.arange(2 * hh)[None, :], device=self.device)
+            cols = torch.as_tensor((cent_h[:, 1] - wh)[:, None] + np.arange(2 * wh)[None, :], device=self.device)
+            select_patch_grids = torch.stack([rows[:, :, None].expand(-1, -1, 2 * wh),
+                                              cols[:, None, :].expand(-1, 2 * hh, -1)], dim=-1)
+            self._last_cent_host = cent_h
+            return _gather_window(self.img, rows, cols), _gather_window(self.mask, rows, cols), select_patch_grids
         select_centroid = pool[torch.as_tensor(select_inds, device=pool.device)]
         cent = select_centroid.long()                       # int(left_h) of the reference truncates the same way
         r0, c0 = cent[:, 0] - hh, cent[:, 1] - wh
@@ -252,7 +363,7 @@ class GridPatchSampler():
         return select_patch, select_patch_mask, select_patch_grids
 
     def sample_patches(self, topk, invalid_ratio):
-        prob = np.random.uniform(0, 1)
+        prob = _uniform(self.device)
         if prob < 0.5:
             patch_source = 'val'
             fake, fake_mask, coords = self.sample_patch_fake('val')
