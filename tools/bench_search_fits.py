@@ -143,7 +143,7 @@ def main():
         "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_search": e2e_ms,
                 "h2d_bytes_per_step": int(pin_c.numel() * 4 + pin_t.numel() * 4), "d2h_bytes_per_step": int(K * 4),
                 "note": "includes drawing the pixel indices and gathering coordinates / targets on the host"},
-        "gpu_launches": int(args.steps * K * iters * 7),
+        "gpu_launches": int(args.steps * sum(pl.launch_count() for pl in fits)),
         "final_losses": [round(float(v), 5) for v in final.tolist()],
         "roofline": {"bound": "tensor", "kernel": "npp_gemm_kmajor (forward + dgrad chains of NPP_Net_light)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
