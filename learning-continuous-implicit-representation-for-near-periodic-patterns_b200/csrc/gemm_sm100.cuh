@@ -283,6 +283,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// same, clamped to +-65504 instead of overflowing to infinity (scaled deltas: one clipped step beats NaN weights)
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
@@ -457,7 +463,8 @@ __device__ __forceinline__ void epilogue_tile(const KmajorParams& p, const EpiAr
           }
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hd[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < 16; ++i)
+          hd[i] = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_MUL) ? pack_h2_sat(v[2 * i], v[2 * i + 1]) : pack_h2(v[2 * i], v[2 * i + 1]);
       }
       if (half == 0) {
         // Every sub-tile is one bulk group (out0 from staging block `sub`, snake: plus the derivative from the aux
@@ -697,8 +704,8 @@ __device__ __forceinline__ void epilogue_head_tile(const KmajorParams& p, const 
         const float t1 = fmaf(g0, w0.y, fmaf(g1, w1.y, g2 * w2.y));
         const float t2 = fmaf(g0, w0.z, fmaf(g1, w1.z, g2 * w2.z));
         const float t3 = fmaf(g0, w0.w, fmaf(g1, w1.w, g2 * w2.w));
-        dl[i >> 1] = pack_h2(t0 * dd0.x * scale, t1 * dd0.y * scale);
-        dl[(i >> 1) + 1] = pack_h2(t2 * dd1.x * scale, t3 * dd1.y * scale);
+        dl[i >> 1] = pack_h2_sat(t0 * dd0.x * scale, t1 * dd0.y * scale);
+        dl[(i >> 1) + 1] = pack_h2_sat(t2 * dd1.x * scale, t3 * dd1.y * scale);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -21,9 +21,14 @@ __device__ __forceinline__ float npp_grad_scale(float amax) {
 // leaves the fp16 rounding of every delta unchanged, so the result is the one the same-step maximum would give
 // unless the maximum moves by more than the 2^6 of headroom between two steps.  Unknown history (first step):
 // the bound |dL/dlogit| <= inv_count / 2 (|d| <= 1, weight <= 1, yh (1 - yh) <= 1/4).
+// A sudden jump of the maximum between two steps (a converged fit meeting an outlier batch) must not overflow fp16: the
+// relative maximum is floored at 2^-6, so that even the largest possible gradient (0.5 relative) lands at 2^15 < 65504 at
+// the head; a floor that high costs nothing (deltas of a converged fit then peak near 2^4 instead of 2^10, still ten
+// binades above fp16's normal minimum).  Deeper layers, where deltas may grow, pack with saturation (pack_h2_sat).
 __device__ __forceinline__ float npp_step_amax(const unsigned int* amax_prev, float inv_count) {
   float a = amax_prev != nullptr ? __uint_as_float(__ldcg(amax_prev)) : 0.f;
   if (!(a > 0.f) || !isfinite(a)) a = 0.5f;
+  a = fmaxf(a, 0.015625f);
   return a * inv_count;
 }
 

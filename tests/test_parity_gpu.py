@@ -724,3 +724,35 @@ def test_adam_trajectory_is_not_vacuous():
         assert rel(ours_m, m[k]) < 2e-3, (k, rel(ours_m, m[k]))
         mean_dw = float(np.abs(got[k].cpu().numpy() - p[k]).mean())
         assert mean_dw < 0.05 * lr, (k, mean_dw)
+
+
+def test_fused_step_survives_a_jump_of_the_gradient_maximum():
+    """The fused step scales its fp16 deltas with the PREVIOUS step's max|dL/dlogit|.  A converged fit (tiny residuals)
+    followed by an outlier batch (residuals of order one) is the worst case: the maximum jumps by three orders of
+    magnitude between two steps.  Nothing may overflow, and the gradients of the jump step must still match the oracle."""
+    topk, n = 3, 2048
+    plan, params, coords, tabs, freqs, rng = make(topk, n)
+    enc = O.encode(coords, tabs, freqs, RES)
+    logits_ref, c = O.forward(params, enc, topk_model=True)
+    pred = O.sigmoid(logits_ref)
+    cd = torch.from_numpy(coords).cuda()
+    md = torch.ones(n, 1, device="cuda")
+    easy = torch.from_numpy((pred + 1e-4 * rng.standard_normal(pred.shape)).astype(np.float32)).cuda()
+    loss = torch.zeros((), device="cuda")
+    for step in range(1, 4):                 # residuals ~1e-4: the ring now holds a tiny maximum
+        plan.train_step(cd, easy, md, 0.0, loss, step=step)          # lr = 0: the weights stay put
+        assert loss.item() < 1e-6
+    hard = rng.random((n, 3), dtype=np.float32)
+    hd = torch.from_numpy(hard).cuda()
+    plan.step_forward_backward(cd, hd, md, n)                       # the jump step
+    plan.step_wgrad(0, plan.layer_count(), n, n)
+    torch.cuda.synchronize()
+    g = O.mse_l2_grad_logits(logits_ref, hard, np.ones((n, 1), np.float32))
+    grads_ref, _ = O.backward(params, c, g, topk_model=True)
+    gv = plan.grad_views()
+    for k, ref in grads_ref.items():
+        got = gv[k].cpu().numpy()
+        assert np.isfinite(got).all(), k
+        assert rel(got, ref) < 2e-3, (k, rel(got, ref))
+    plan.step_finish(n, 0.0, loss, step=4)
+    assert abs(loss.item() - float(O.mse_l2(pred, hard, np.ones((n, 1), np.float32)))) < 1e-3 * loss.item()
