@@ -628,7 +628,12 @@ def bench_dp_cfg4(rank, world, dev, barrier, max_over_ranks, steps=30):
     # every rank must run the SAME number of steps (each one holds collectives): no time-based warm-up here
     ms, _, _, _ = timed_loop(step, steps, 5, barrier, rewarm=10, settle_s=0.0)
     ms = max_over_ranks(ms)
-    return {"value": rows * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
+    exposed = None
+    if world > 1:       # the same steps without the collectives (the ranks' weights drift apart: timing only, done last)
+        dps.skip_allreduce = True
+        ms0, _, _, _ = timed_loop(step, steps, 3, barrier, rewarm=10, settle_s=0.0)
+        exposed = (ms - max_over_ranks(ms0)) / steps
+    return {"allreduce_exposed_ms_per_step": exposed, "value": rows * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
             "n_gpus": world, "rows_per_step": rows, "rows_per_step_per_gpu": rows // world, "scaling": "strong",
             "collective": "ncclAllReduce(sum) of the fp32 gradients in layer-group buckets on a side stream, overlapped "
                           "with the remaining weight-gradient GEMM groups; identical Adam on every rank",

@@ -1575,8 +1575,9 @@ static int launch_step_chain(NppPlan* p, const float* coords, const float* targe
   if (!p->params) return fail("npp_plan_bind has not been called");
   CKI(prepare(p, n));
   CKI(set_smem_attrs());
-  if (!p->acc_clean) {   // a call of the unfused path left its sums behind
+  if (!p->acc_clean) {   // a call of the unfused path, or an abandoned three-phase step, left its sums behind
     CK(cudaMemsetAsync(p->acc, 0, p->acc_zero_floats * sizeof(float), st));
+    CK(cudaMemsetAsync(p->acc + p->ring_off + 3, 0, sizeof(float), st));   // the loss accumulator lives behind the ring
     p->acc_clean = true;
   }
   bool prefetched = false;
@@ -1730,6 +1731,9 @@ int npp_step_forward_backward(NppPlan* p, const float* coords, const float* targ
   p->launches = 0;
   const StepSlots sl = step_slots(p, n_norm);
   CKI(launch_step_chain(p, coords, target, mask, n, sl, (cudaStream_t)stream));
+  // until npp_step_finish has run, the step accumulators hold this step's sums: a caller that abandons the step here
+  // must not have them added to the next one (launch_step_chain clears them when it finds them dirty)
+  p->acc_clean = false;
   return mark_busy(p, (cudaStream_t)stream);
 }
 
@@ -1818,6 +1822,7 @@ int npp_step_finish(NppPlan* p, int64_t n_norm, float lr, float beta1, float bet
   CK(cudaGetLastError());
   ++p->launches;
   ++p->step_seq;
+  p->acc_clean = true;
   return 0;
 }
 

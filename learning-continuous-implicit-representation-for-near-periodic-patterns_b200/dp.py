@@ -44,13 +44,14 @@ class DataParallelStep:
         self.loss = torch.zeros((), device=plan.device)
         self.launches = 0
         self.last_loss = self.loss
+        self.skip_allreduce = False       # timing experiments only: how much of a step is exposed communication
 
     def __call__(self, coords, target, mask, lr, n_global, step=None):
         plan = self.plan
         n = coords.shape[0]
         plan.step_forward_backward(coords, target, mask, n_norm=n_global)
         pending = []
-        multi = world() > 1
+        multi = world() > 1 and not self.skip_allreduce
         for (lb, le), bucket in zip(self.groups, self.buckets):
             plan.step_wgrad(lb, le, n, n_global)
             if multi:

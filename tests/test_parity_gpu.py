@@ -756,3 +756,27 @@ def test_fused_step_survives_a_jump_of_the_gradient_maximum():
         assert rel(got, ref) < 2e-3, (k, rel(got, ref))
     plan.step_finish(n, 0.0, loss, step=4)
     assert abs(loss.item() - float(O.mse_l2(pred, hard, np.ones((n, 1), np.float32)))) < 1e-3 * loss.item()
+
+
+@pytest.mark.parametrize("topk,n", [(3, 1), (1, 129), (3, 300)])
+def test_fused_step_ragged_row_counts(topk, n):
+    """Row counts that fill neither a 32-row TMEM quadrant nor a 128-row stripe: the fused step's loss and the direction
+    of its first Adam update against the oracle, and an abandoned three-phase step must not leak into the next step."""
+    plan, params, coords, tabs, freqs, rng = make(topk, n)
+    enc = O.encode(coords, tabs, freqs, RES)
+    target = rng.random((n, 3), dtype=np.float32)
+    mask = (rng.random((n, 1)) > 0.3).astype(np.float32)
+    mask[0] = 1.0
+    cd, td, md = (torch.from_numpy(a).cuda() for a in (coords, target, mask))
+    plan.step_forward_backward(cd, td, md, n)          # abandoned on purpose (no wgrad, no finish)
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in p.items()}
+    loss = torch.zeros((), device="cuda")
+    plan.train_step(cd, td, md, 5e-4, loss, step=1)
+    ref_loss, _ = O.train_step(p, m, v, 1, enc, target, mask, 5e-4, topk_model=topk > 1)
+    assert abs(loss.item() - ref_loss) < 1e-3 * ref_loss, (loss.item(), ref_loss)
+    slots = {s.name: s for s in plan.slots}
+    for k in plan.grad_views():
+        ours_m = plan.view(plan.exp_avg, slots[k]).cpu().numpy()
+        assert rel(ours_m, m[k]) < 3e-3, (k, rel(ours_m, m[k]))     # exp_avg = 0.1 * gradient of exactly ONE step
