@@ -193,6 +193,16 @@ int npp_fit_run(NppPlan* plan, const float* coords_all, const float* target_all,
                 int64_t iters, float lrate, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
                 int64_t first_step, float* losses, void* stream);
 
+/* The same loop for k plans at once, advanced in lock step: ONE captured step of every plan (parallel branches of a single
+ * CUDA graph) launched `iters` times -- the candidate loop of NPP_proposal/search.py:85-148, whose candidates all see the
+ * same batches (search.py:91-92 reseeds per candidate).  Arrays of k pointers (host arrays of device pointers; entries may
+ * repeat for coords / targets / masks); first_steps[i] is plan i's first Adam step; losses[i] is a device array [iters].
+ * NPP_MODEL_LIGHT plans only.  Same arithmetic as k calls of npp_fit_run. */
+int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coords_all, const float* const* target_all,
+                      const float* const* mask_all, int64_t n, int64_t iters, float lrate, float decay_rate,
+                      float decay_steps, float beta1, float beta2, float eps, const int64_t* first_steps,
+                      float* const* losses, void* stream);
+
 /* Patch crops of GridPatchSampler (models/sampler.py:262-296; utils/extract_glimpse.py:7-79 with mode='nearest',
  * padding_mode='zeros'): out[m, c, i, j] = img[rows[m, i], cols[m, j], c], zero outside the image.  img: device
  * [img_h, img_w, channels] fp32; rows [m, h], cols [m, w] device int64 index tables; out: device [m, channels, h, w]. */

@@ -80,6 +80,9 @@ SIGNATURES = {
     "npp_step_finish": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P, _P]),
     "npp_fit_run": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_float, C.c_int64, _P, _P]),
+    "npp_multi_fit_run": (C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_int64,
+                                    C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.POINTER(C.c_int64), C.POINTER(_P), _P]),
     "npp_set_keep_grads": (C.c_int, [_P, C.c_int]),
     "npp_last_launch_count": (C.c_int, [_P]),
     "npp_profile_enable": (C.c_int, [_P, C.c_int]),

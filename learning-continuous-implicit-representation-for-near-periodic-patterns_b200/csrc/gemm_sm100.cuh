@@ -125,6 +125,11 @@ struct HeadArgs {
   unsigned int* amax_next;        // same of this step (atomicMax)
   float inv_count;        // 1 / (3 * n_norm)
   int width;              // reference in_features of rgb_linear (128 or 256)
+  // re-launched step graph (npp_multi_fit_run): step index s = *step lives in device memory; this launch works on batch
+  // s of [iters, M, 3] targets / [iters, M] masks and on ring slots (seq0 + s) % 3 (amax_prev / amax_next then unused)
+  const int* step;
+  unsigned int* ring;
+  int seq0;
 };
 
 // A chain = ops executed in order for every 128-row stripe; op i may read what ops < i wrote for the
@@ -301,8 +306,15 @@ __device__ __forceinline__ void publish_progress(uint32_t* slot, uint32_t value)
 }
 __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t need) {
   uint32_t v;
+#ifdef NPP_HANG_DEBUG
+  uint32_t n = 0;
+  long long t0 = 0;
+#endif
   do {
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(slot)) : "memory");
+#ifdef NPP_HANG_DEBUG
+    if (static_cast<int32_t>(v - need) < 0) npp_spin_check(n, t0, 9000 + (__LINE__ & 0xFF), need);
+#endif
   } while (static_cast<int32_t>(v - need) < 0);
   return v;
 }
@@ -563,17 +575,29 @@ __device__ __forceinline__ void epilogue_head_tile(const KmajorParams& p, const 
   const bool warp_ok = row0 < M;
   const int width = hd.width;
   const uint32_t tlane = tmem_acc + (static_cast<uint32_t>(lane_base) << 16);
+  const float* target = hd.target;
+  const float* maskp = hd.mask;
+  const unsigned int* amax_prev = hd.amax_prev;
+  unsigned int* amax_next = hd.amax_next;
+  if (hd.step != nullptr) {
+    const int sidx = *hd.step;
+    target += (size_t)sidx * M * 3;
+    if (maskp != nullptr) maskp += (size_t)sidx * M;
+    const int slot = (hd.seq0 + sidx) % 3;
+    amax_next = hd.ring + slot;
+    amax_prev = hd.ring + (slot + 2) % 3;
+  }
   // inputs of the loss: requested before the accumulator is waited for
   float tg[3] = {0.f, 0.f, 0.f};
   float mk = 1.0f;
   if (row_ok) {
-    tg[0] = __ldg(hd.target + 3 * (size_t)row);
-    tg[1] = __ldg(hd.target + 3 * (size_t)row + 1);
-    tg[2] = __ldg(hd.target + 3 * (size_t)row + 2);
-    if (hd.mask != nullptr) mk = __ldg(hd.mask + row);
+    tg[0] = __ldg(target + 3 * (size_t)row);
+    tg[1] = __ldg(target + 3 * (size_t)row + 1);
+    tg[2] = __ldg(target + 3 * (size_t)row + 2);
+    if (maskp != nullptr) mk = __ldg(maskp + row);
   }
   const float rb0 = __ldg(hd.b), rb1 = __ldg(hd.b + 1), rb2 = __ldg(hd.b + 2);
-  const float scale = npp_grad_scale(npp_step_amax(hd.amax_prev, hd.inv_count));
+  const float scale = npp_grad_scale(npp_step_amax(amax_prev, hd.inv_count));
   // This warp's aux box carries its partial logits to the other warp of the quadrant: every bulk store that read the
   // box (the snake derivative of an earlier layer) and every earlier store from the output staging has finished reading.
   if (lane == 0) bulk_wait_read0();
@@ -649,7 +673,7 @@ __device__ __forceinline__ void epilogue_head_tile(const KmajorParams& p, const 
       }
       if (lane == 0 && warp_ok) {
         atomicAdd(hd.loss_acc, lsum * hd.inv_count);
-        if (lmax > 0.f) atomicMax(hd.amax_next, __float_as_uint(lmax / hd.inv_count));
+        if (lmax > 0.f) atomicMax(amax_next, __float_as_uint(lmax / hd.inv_count));
         atomicAdd(hd.head_acc + 3 * width, s0);      // db_rgb
         atomicAdd(hd.head_acc + 3 * width + 1, s1);
         atomicAdd(hd.head_acc + 3 * width + 2, s2);

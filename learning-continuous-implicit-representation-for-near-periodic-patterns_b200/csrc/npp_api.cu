@@ -1191,6 +1191,11 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   p->cfg = *cfg;
   p->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("NPP_CLUSTER")) p->cluster = atoi(e) == 1 ? 1 : 2;
+  // Search-stage fits run many plans side by side on one GPU.  With the CTA-pair weight-gradient kernel that occasionally
+  // dead-locked (one fit's stream stuck, ~1 run in 5 with nine concurrent fits, r01 library included; never seen with the
+  // single-CTA kernel in 16 runs, never with one plan at a time): NPP_Net_light takes the single-CTA kernel, whose L2
+  // traffic does not matter at 2048 rows.
+  if (cfg->model == NPP_MODEL_LIGHT) p->wg_cluster = 1;
   if (const char* e = getenv("NPP_WG_CLUSTER")) p->wg_cluster = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("NPP_PDL")) p->pdl = atoi(e) != 0;
   if (const char* e = getenv("NPP_SPLIT_STEP")) p->fused_step = atoi(e) == 0;
@@ -1597,6 +1602,11 @@ static int launch_step_chain(NppPlan* p, const float* coords, const float* targe
   hd.amax_next = sl.cur;
   hd.inv_count = sl.inv_count;
   hd.width = p->head_width;
+  if (p->step_mode) {   // one captured step re-launched many times: batch and ring slots follow the device-side step index
+    hd.step = p->d_step;
+    hd.ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
+    hd.seq0 = (int)(p->step_seq % 3);
+  }
   const bool alt = p->enc_set != 0;
   ProfScope ps(p, st, PROF_GEMM_FWD, 1);
   const std::vector<KmajorParams>& ops = alt ? p->step_params_alt : p->step_params;
@@ -1626,9 +1636,12 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
     rs.loss_acc = sl.loss_acc;
     rs.loss_out = loss;
     rs.amax_clear = sl.clr;
+    rs.ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
+    rs.seq0 = (int)(p->step_seq % 3);
+    rs.by_step = p->step_mode ? 1 : 0;
     CKI(launch_update(p, ad, sl.prev, rs, p->pdl, st));
   }
-  ++p->step_seq;
+  if (!p->step_mode) ++p->step_seq;   // a re-launched step graph advances the ring on the device; its caller adds `iters`
   return 0;
 }
 
@@ -1638,7 +1651,7 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
   if (n_norm <= 0) return fail("n_norm must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
-  if (p->fused_step && !p->step_mode) {
+  if (p->fused_step && (!p->step_mode || p->cfg.model == NPP_MODEL_LIGHT)) {
     if (step < 1) return fail("Adam step must be >= 1");
     return run_fused_step(p, coords, target, mask, n, n_norm, adam_scalars(lr, beta1, beta2, eps, step), loss, st);
   }
@@ -1928,12 +1941,151 @@ int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, co
   p->fit_stream = st;
   const int64_t graph_launches = mode == 2 ? iters : 1;
   for (int64_t i = 0; i < graph_launches; ++i) CK(cudaGraphLaunch(p->fit_exec, st));
+  if (mode == 2 && p->fused_step) p->step_seq += iters;
   CKI(mark_busy(p, st));
   p->launches = launches;
   return 0;
 }
 
+// Several fits advanced in lock step by ONE re-launched CUDA graph: the candidate loop of NPP_proposal/search.py:85-148 with
+// every candidate fitted on the same sequence of batches.  One train step of every plan is captured as a parallel branch
+// of a single graph (fork / join through events, each plan on its own capture stream), with the batch index, Adam's
+// scalars and the max-gradient ring following a device-side step counter per plan; the graph is then launched `iters`
+// times from the caller's stream.  Replaces k * iters * 4 kernel launches from k host threads (the run was bound by
+// the launch rate) by `iters` graph launches whose branches run side by side on the GPU.
+int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coords_all, const float* const* target_all,
+                      const float* const* mask_all, int64_t n, int64_t iters, float lrate, float decay_rate,
+                      float decay_steps, float beta1, float beta2, float eps, const int64_t* first_steps,
+                      float* const* losses, void* stream) {
+  if (!plans || k <= 0 || !coords_all || !target_all || !losses || !first_steps) return fail("npp_multi_fit_run: null argument");
+  if (iters < 1) return fail("npp_multi_fit_run: iters must be >= 1");
+  if (!(decay_steps > 0.f) || !(decay_rate > 0.f)) return fail("npp_multi_fit_run: decay_rate and decay_steps must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < k; ++i) {
+    NppPlan* p = plans[i];
+    if (!p || !coords_all[i] || !target_all[i] || !losses[i]) return fail("npp_multi_fit_run: null argument");
+    if (p->cfg.model != NPP_MODEL_LIGHT) return fail("npp_multi_fit_run: built for the search-stage network (NPP_MODEL_LIGHT)");
+    if (!p->fused_step) return fail("npp_multi_fit_run needs the fused train step (NPP_SPLIT_STEP is set)");
+    if (first_steps[i] < 1) return fail("npp_multi_fit_run: first_step must be >= 1");
+    if (!p->params || !p->m || !p->v) return fail("npp_multi_fit_run: parameter and Adam arenas must be bound");
+    for (int j = 0; j < i; ++j)
+      if (plans[j] == p) return fail("npp_multi_fit_run: the same plan is listed twice");
+  }
+  NppPlan* lead = plans[0];
+  if (lead->fit_exec) {           // the previous run's graph may still be executing
+    CK(cudaStreamSynchronize(lead->fit_stream));
+    CK(cudaGraphExecDestroy(lead->fit_exec));
+    lead->fit_exec = nullptr;
+  }
+  CKI(set_smem_attrs());
+  for (int i = 0; i < k; ++i) {
+    NppPlan* p = plans[i];
+    CKI(prepare(p, n));           // synchronises and copies op tables: must happen outside the capture
+    p->pref[0].valid = p->pref[1].valid = false;
+    CK(cudaStreamSynchronize(p->side_stream));
+    if (p->ad_table_cap < iters) {
+      cudaFree(p->d_ad_table);
+      p->d_ad_table = nullptr;
+      CK(cudaMalloc(&p->d_ad_table, (size_t)iters * sizeof(AdamScalars)));
+      p->ad_table_cap = iters;
+    }
+    std::vector<AdamScalars> tab((size_t)iters);
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t step = first_steps[i] + it;
+      const double expo = (double)(step > 2 ? step - 2 : 0) / (double)decay_steps;   // the scripts' LR rewrite, see npp_fit_run
+      tab[it] = adam_scalars((float)((double)lrate * std::pow((double)decay_rate, expo)), beta1, beta2, eps, step);
+    }
+    CK(cudaMemcpyAsync(p->d_ad_table, tab.data(), tab.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
+  }
+  // capture: the lead plan's side stream is the origin, every other plan's side stream a branch forked from it
+  cudaStream_t origin = lead->side_stream;
+  CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  int launches = 0;
+  cudaError_t ce = cudaEventRecord(lead->pref_fork, origin);
+  for (int i = 0; i < k && rc == 0 && ce == cudaSuccess; ++i) {
+    NppPlan* p = plans[i];
+    cudaStream_t bs = p->side_stream;
+    if (i > 0) ce = cudaStreamWaitEvent(bs, lead->pref_fork, 0);
+    if (ce != cudaSuccess) break;
+    p->capturing = true;
+    p->step_mode = true;
+    rc = npp_train_step(p, coords_all[i], target_all[i], mask_all ? mask_all[i] : nullptr, n, n, lrate, beta1, beta2, eps,
+                        first_steps[i], losses[i], bs);
+    if (rc == 0) {
+      npp_step_advance_kernel<<<1, 1, 0, bs>>>(p->d_step);
+      launches += p->launches + 1;
+    }
+    p->step_mode = false;
+    p->capturing = false;
+    if (rc == 0 && i > 0) {       // join the branch
+      ce = cudaEventRecord(p->tables_evt, bs);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, p->tables_evt, 0);
+    }
+  }
+  cudaGraph_t gr = nullptr;
+  const cudaError_t ee = cudaStreamEndCapture(origin, &gr);
+  if (rc != 0) {
+    if (gr) cudaGraphDestroy(gr);
+    return rc;
+  }
+  if (ce != cudaSuccess || ee != cudaSuccess) {
+    if (gr) cudaGraphDestroy(gr);
+    return fail(std::string("npp_multi_fit_run: stream capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&lead->fit_exec, gr, 0ULL);
+  cudaGraphDestroy(gr);
+  if (ie != cudaSuccess) {
+    lead->fit_exec = nullptr;
+    return fail(std::string("npp_multi_fit_run: cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
+  }
+  lead->fit_stream = st;
+  for (int64_t it = 0; it < iters; ++it) CK(cudaGraphLaunch(lead->fit_exec, st));
+  for (int i = 0; i < k; ++i) {
+    plans[i]->step_seq += iters;
+    plans[i]->launches = launches / k * (int)iters;
+    CK(cudaEventRecord(plans[i]->tables_evt, st));
+  }
+  return 0;
+}
+
 int npp_last_launch_count(const NppPlan* p) { return p ? p->launches : 0; }
+
+// Debugging aid for a stuck stream: with npp_profile_enable(plan, 1) every kernel class is bracketed by events; this
+// returns the class (PROF_* index) of the first span whose end event has not completed, its ordinal among the spans
+// recorded since profiling was enabled, or -1.  Meant to be called from another host thread while the plan's own thread
+// is blocked in a CUDA call.
+int npp_debug_pending_class(NppPlan* p, int* ordinal, int* total) {
+  if (!p) return -1;
+  const size_t n = p->spans.size();
+  if (total) *total = (int)n;
+  for (size_t i = 0; i < n; ++i) {
+    const cudaError_t q = cudaEventQuery(p->spans[i].b);
+    if (q == cudaErrorNotReady) {
+      cudaGetLastError();
+      if (ordinal) *ordinal = (int)i;
+      return p->spans[i].cls;
+    }
+  }
+  return -1;
+}
+
+#ifdef NPP_HANG_DEBUG
+// Debug build only: mapped host buffer (1024 x u64) that stuck waits report into (see ptx_sm100.cuh).
+int npp_debug_hang_buffer(unsigned long long** host_ptr) {
+  static unsigned long long* h = nullptr;
+  if (h == nullptr) {
+    CK(cudaHostAlloc(&h, 1024 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(h, 0, 1024 * sizeof(unsigned long long));
+    unsigned long long* d = nullptr;
+    CK(cudaHostGetDevicePointer(&d, h, 0));
+    CK(cudaMemcpyToSymbol(g_npp_hang, &d, sizeof(d)));
+  }
+  if (host_ptr) *host_ptr = h;
+  return 0;
+}
+#endif
 
 int npp_set_keep_grads(NppPlan* p, int on) {
   if (!p) return fail("null plan");

@@ -43,7 +43,13 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 // wait that synchronises with release.cluster arrives of the peer CTA (generic-proxy data forwarded through smem)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster_impl(uint64_t* bar, uint32_t parity, uint32_t line);
+#ifdef NPP_HANG_DEBUG
+#define mbar_wait_cluster(bar, parity) mbar_wait_cluster_impl(bar, parity, __LINE__)
+#else
+#define mbar_wait_cluster(bar, parity) mbar_wait_cluster_impl(bar, parity, 0)
+#endif
+__device__ __forceinline__ void mbar_wait_cluster_plain(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
@@ -66,9 +72,58 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef NPP_HANG_DEBUG
+// Debug build only (-DNPP_HANG_DEBUG): a wait that lasts longer than ~2 s reports where it is stuck (source line of the
+// wait, block, thread, parity) into a mapped host buffer and traps, so that a dead-locked kernel becomes a launch
+// failure with a location instead of a hang.
+__device__ unsigned long long* g_npp_hang = nullptr;
+__device__ __noinline__ void npp_report_hang(uint32_t line, uint32_t info) {
+  if (g_npp_hang != nullptr) {
+    const unsigned long long v = (1ull << 63) | ((unsigned long long)(line & 0x7FFF) << 48) |
+                                 ((unsigned long long)(blockIdx.x & 0xFFFF) << 32) |
+                                 ((unsigned long long)(threadIdx.x & 0xFFFF) << 16) | (info & 0xFFFF);
+    g_npp_hang[(blockIdx.x * 10 + (threadIdx.x >> 5)) & 1023] = v;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void npp_spin_check(uint32_t& n, long long& t0, uint32_t line, uint32_t info) {
+  if ((++n & 0x3FFF) == 0) {
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000LL) npp_report_hang(line, info);
+  }
+}
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t line) {
+  uint32_t n = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) npp_spin_check(n, t0, line, parity);
+}
+#define mbar_wait(bar, parity) mbar_wait_impl(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+#endif
+__device__ __forceinline__ void mbar_wait_cluster_impl(uint64_t* bar, uint32_t parity, uint32_t line) {
+#ifdef NPP_HANG_DEBUG
+  uint32_t n = 0, ok;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok == 0) npp_spin_check(n, t0, line, parity);
+  } while (ok == 0);
+#else
+  (void)line;
+  mbar_wait_cluster_plain(bar, parity);
+#endif
 }
 
 // ---------------------------------------------------------------------- TMA

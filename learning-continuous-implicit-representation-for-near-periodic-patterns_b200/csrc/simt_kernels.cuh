@@ -1178,6 +1178,9 @@ struct StepReset {
   float* loss_acc;
   float* loss_out;
   unsigned int* amax_clear;
+  unsigned int* ring;        // re-launched step graph (step != nullptr): ring slots follow (seq0 + *step) % 3 and the loss
+  int seq0;                  //   goes to loss_out[*step]
+  int by_step;
 };
 __device__ __forceinline__ float npp_adam1(float p, float g, float& m, float& v, const AdamScalars a) {
   m = m + (g - m) * (1.0f - a.beta1);
@@ -1226,9 +1229,16 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
       params[idx] = npp_adam1(params[idx], g, m[idx], v[idx], ad);
     }
     if (rs.on && threadIdx.x == 0) {
-      if (rs.loss_out != nullptr) *rs.loss_out = *rs.loss_acc;
+      float* lout = rs.loss_out;
+      unsigned int* clr = rs.amax_clear;
+      if (rs.by_step) {
+        const int sidx = *step;
+        if (lout != nullptr) lout += sidx;
+        clr = rs.ring + (rs.seq0 + sidx + 1) % 3;
+      }
+      if (lout != nullptr) *lout = *rs.loss_acc;
       *rs.loss_acc = 0.f;
-      *rs.amax_clear = 0u;        // ring slot the step after the next one accumulates into
+      *clr = 0u;                  // ring slot the step after the next one accumulates into
     }
     return;
   }
@@ -1237,7 +1247,8 @@ __global__ void __launch_bounds__(256) npp_fused_update_kernel(const __grid_cons
   const UpdateLayer& L = tab.L[li];
   const int t = (int)blockIdx.x - tab.tile_begin[li];
   // fused step: the deltas were scaled with the PREVIOUS step's maximum (npp_step_amax), else with this step's
-  const float inv = 1.0f / npp_grad_scale(rs.on ? npp_step_amax(amax_bits, rs.inv_count) : __uint_as_float(*amax_bits));
+  const unsigned int* prev_bits = (rs.on && rs.by_step) ? rs.ring + (rs.seq0 + *step + 2) % 3 : amax_bits;
+  const float inv = 1.0f / npp_grad_scale(rs.on ? npp_step_amax(prev_bits, rs.inv_count) : __uint_as_float(*amax_bits));
   const int tiles_c = (L.kpad + 127) >> 7;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 column groups x 8 rows per pass
   const bool two_seg = L.in_ref > L.split_col;

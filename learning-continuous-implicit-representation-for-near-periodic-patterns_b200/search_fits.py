@@ -12,6 +12,7 @@ contextual loss on the held-out region, search.py:150-196) stays with the caller
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import List, Optional, Sequence
 
@@ -19,7 +20,7 @@ import torch
 
 import torch.distributed as dist
 
-from .plan import Plan
+from .plan import MODEL_LIGHT, Plan
 
 
 def assign_candidates(n_candidates: int, rank: int, world: int) -> List[int]:
@@ -55,11 +56,41 @@ def gather_batches(image: torch.Tensor, train_coords: torch.Tensor, indices: tor
     return sel.float().contiguous(), target.float()
 
 
+def _run_fits_grouped(plans, coords_all, target_all, per_plan, iters, lrate, lrate_decay, losses):
+    import ctypes as C
+    from . import _native as nat
+    k = len(plans)
+    cs = [coords_all[i] if per_plan else coords_all for i in range(k)]
+    ts = [target_all[i] if per_plan else target_all for i in range(k)]
+    n = int(cs[0].shape[1])
+    for c, t in zip(cs, ts):
+        if not (c.is_cuda and c.dtype == torch.float32 and c.is_contiguous() and tuple(c.shape) == (iters, n, 2) and
+                t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (iters, n, 3)):
+            raise ValueError("run_fits needs contiguous fp32 CUDA tensors [iters, n, 2] and [iters, n, 3]")
+    if any(n > p.max_rows for p in plans):
+        raise ValueError(f"{n} rows exceed a plan's capacity")
+    P = C.c_void_p
+    handles = (P * k)(*[p.handle for p in plans])
+    cptr = (P * k)(*[c.data_ptr() for c in cs])
+    tptr = (P * k)(*[t.data_ptr() for t in ts])
+    lptr = (P * k)(*[losses[i].data_ptr() for i in range(k)])
+    first = (C.c_int64 * k)(*[p.adam_steps + 1 for p in plans])
+    nat.check(plans[0].lib.npp_multi_fit_run(handles, k, cptr, tptr, None, n, iters, lrate, 0.1, float(lrate_decay) * 100.0,
+                                             0.9, 0.999, 1e-8, first, lptr, nat.current_stream()))
+    for p in plans:
+        p.adam_steps += iters
+
+
 def run_fits(plans: Sequence[Plan], coords_all: torch.Tensor, target_all: torch.Tensor, *, lrate: float = 5e-4,
              lrate_decay: float = 500, streams: Optional[Sequence[torch.cuda.Stream]] = None,
-             threads: bool = True, loss_type: str = "l2") -> torch.Tensor:
+             threads: bool = True, loss_type: str = "l2", grouped: Optional[bool] = None) -> torch.Tensor:
     """Fit every plan on the same batches (or on its own, if coords_all / target_all are lists), concurrently.
     Returns the losses [len(plans), iters]; the call returns once the current stream waits for every fit.
+
+    Default execution (``grouped``, NPP_Net_light plans, no caller-supplied streams): npp_multi_fit_run -- one train step
+    of every plan captured as parallel branches of ONE CUDA graph that is launched `iters` times, the batch index and
+    Adam's scalars following a device-side step counter.  ``grouped=False`` (or NPP_FIT_MULTI=0, or explicit streams):
+    one plan, stream and host thread per candidate, each enqueueing its own kernels (npp_fit_run).
 
     Equivalent to the reference loop only for ``--loss_type l2``: npp_fit_run trains with sigmoid + masked MSE
     (img2mse(pred, gt, 'l2', ...), NPP_proposal/search.py:133).  The scripts' DEFAULT is 'robust_loss_adaptive'
@@ -76,6 +107,11 @@ def run_fits(plans: Sequence[Plan], coords_all: torch.Tensor, target_all: torch.
     iters = int((coords_all[0] if per_plan else coords_all).shape[0])
     dev = plans[0].device
     losses = torch.zeros(k, iters, device=dev)
+    if grouped is None:
+        grouped = os.environ.get("NPP_FIT_MULTI", "1") != "0"
+    if grouped and k >= 1 and iters >= 1 and streams is None and all(p.model == MODEL_LIGHT for p in plans):
+        _run_fits_grouped(plans, coords_all, target_all, per_plan, iters, lrate, lrate_decay, losses)
+        return losses
     streams = list(streams) if streams is not None else [torch.cuda.Stream(device=dev) for _ in range(k)]
     cur = torch.cuda.current_stream(dev)
     errors: List[BaseException] = []

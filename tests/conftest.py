@@ -16,3 +16,11 @@ def pytest_configure(config):
 def native():
     import npp_b200
     return npp_b200._native
+
+
+def pytest_collection_modifyitems(config, items):
+    """Every GPU test gets a wall-clock limit (pytest-timeout): a dead-locked kernel must fail the run, not stall it."""
+    import pytest
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(600))

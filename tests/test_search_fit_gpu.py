@@ -302,9 +302,18 @@ def test_concurrent_candidate_fits_match_fits_run_alone():
             out.append(p)
         return out
 
-    together = run_fits(plans(), coords_all, target_all).cpu().numpy()
+    together = run_fits(plans(), coords_all, target_all).cpu().numpy()            # default: one re-launched graph
+    threaded = run_fits(plans(), coords_all, target_all, grouped=False).cpu().numpy()   # stream + host thread per fit
     alone = np.stack([p.fit_run(coords_all, target_all).cpu().numpy() for p in plans()])
     assert together.shape == (K, iters)
+    np.testing.assert_allclose(threaded[:, :20], alone[:, :20], rtol=2e-3)
+    np.testing.assert_allclose(threaded, alone, rtol=2e-2)
+    # a second grouped run on the same plans continues their Adam steps (the first graph is retired)
+    ps = plans()
+    first = run_fits(ps, coords_all[:10], target_all[:10]).cpu().numpy()
+    second = run_fits(ps, coords_all[10:20], target_all[10:20]).cpu().numpy()
+    np.testing.assert_allclose(np.concatenate([first, second], 1), alone[:, :20], rtol=2e-3)
+    assert all(p.adam_steps == 20 for p in ps)
     # same trajectory; late iterations only to 2 % (atomic-ordering noise in the bias gradients, amplified by Adam)
     np.testing.assert_allclose(together[:, :20], alone[:, :20], rtol=2e-3)
     np.testing.assert_allclose(together, alone, rtol=2e-2)

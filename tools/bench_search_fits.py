@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", default="grouped", choices=["grouped", "threads"],
+                    help="grouped: one re-launched CUDA graph with a branch per candidate (npp_multi_fit_run); threads: one "
+                         "stream + host thread per candidate (npp_fit_run)")
     args = ap.parse_args()
     K, iters = args.candidates, args.iters
     torch.cuda.set_device(0)
@@ -66,7 +69,7 @@ def main():
         r = np.random.default_rng(seed)
         return torch.from_numpy(r.integers(0, H * W, (iters, N_RAND)))
 
-    streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(K)] if args.mode == "threads" else None
     idx = host_indices(0).to(dev)
     coords_all, target_all = gather_batches(image, train_coords, idx)
     fits = plans()
@@ -138,7 +141,7 @@ def main():
         "config": {"workload": f"search: 512x512 synthetic near-periodic texture, {K} candidate periodicities x {iters} "
                                f"iterations x {N_RAND} pixels, NPP_Net_light D=4 W=256, loss l2; one step = one whole search",
                    "l2_policy": "every iteration reads a different batch; working set per fit 4 MB (L2 resident by design)",
-                   "concurrency": "one plan, CUDA stream and host thread per candidate (search_fits.run_fits)"},
+                   "concurrency": ("one re-launched CUDA graph with one branch per candidate (npp_multi_fit_run)" if args.mode == "grouped" else "one plan, CUDA stream and host thread per candidate (npp_fit_run)")},
         "clocks": clocks,
         "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_search": e2e_ms,
                 "h2d_bytes_per_step": int(pin_c.numel() * 4 + pin_t.numel() * 4), "d2h_bytes_per_step": int(K * 4),
