@@ -805,6 +805,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
   const GemmSmem s = carve_smem_t<NST, EPI_STAGE_BYTES, A_STAGE_BYTES, B_BYTES>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef NPP_PDL_WAIT_FIRST
+  grid_dependency_wait();   // experiment: an early-launched CTA holds no TMEM / barrier while it waits
+#endif
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
   // Programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) may overlap the tail of the
   // previous kernel in the stream; nothing below may (a no-op for an ordinary launch).
@@ -1142,6 +1145,9 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
   // 1 forwards that completion to the leader's full barrier (second pending arrival there).  A stage is free again when
   // its UMMAs have completed (one commit) and the four epilogue warps of the CTA have arrived.
   uint64_t* const alocal = s.afull;
+#ifdef NPP_PDL_WAIT_FIRST
+  grid_dependency_wait();
+#endif
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4, CLUSTER, 1 + 4, 1>(s, warp);
   grid_dependency_wait();   // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
   const int kb_total = (p.rows + BK - 1) / BK;

@@ -149,6 +149,7 @@ struct NppPlan {
   long long step_seq = 0;          // fused steps run so far (selects the ring slots)
   bool acc_clean = true;           // the per-step accumulators are all zero (the fused step's update kernel leaves them so)
   int pdl = 1;                     // programmatic dependent launch between the kernels of a fused step
+  int pdl_edges = 7;               // which launches carry the attribute: 1 chain (after update), 2 wgrad (after chain), 4 update (after wgrad)
   bool fused_step = true;          // npp_train_step runs forward + head + backward as one chain (NPP_SPLIT_STEP=1: r01 path)
   float* g_buf = nullptr;       // [max_rows,3] grad wrt logits (fused path)
   unsigned int* d_barrier = nullptr;  // {arrivals, generation} of the fused head kernel's grid barrier
@@ -187,6 +188,8 @@ struct NppPlan {
   bool step_mode = false;               // launches take their batch / scalars through d_step
   cudaEvent_t tables_evt = nullptr;     // recorded after the last kernels that read the device op tables
   cudaEvent_t coop_evt = nullptr;       // recorded after this plan's last cooperative head launch (see coop_head_allowed)
+  cudaEvent_t step_evt = nullptr;       // recorded after this plan's last training launch (see PairStepScope)
+  bool step_pending = false;            // step_evt has been recorded and not yet been seen complete (g_pair_mu held)
   bool capturing = false;               // npp_fit_run is recording into side_stream
   cudaGraphExec_t fit_exec = nullptr;   // the last npp_fit_run, captured as one graph (kept until the next run / destroy)
   cudaStream_t fit_stream = nullptr;    // stream it was launched on
@@ -951,6 +954,53 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   return 0;
 }
 
+// Training launches of two plans that use the CTA-pair weight-gradient kernel never overlap on the GPU.
+// Measured on B200 (tests/diag_concurrent_big.py, profiles/r02/concurrent_plans.txt): three 8192-row NPP_Net fits
+// stepping on three streams from three host threads dead-locked on the device in 6 of 7 runs (eight 2048-row fits: 1 of
+// 6; nine NPP_Net_light fits: 7 of 38), never with the single-CTA instantiation of the weight-gradient kernel (0 of 32)
+// and never with one plan at a time.  No wait of either kernel could be caught spinning (a -DNPP_HANG_DEBUG build whose
+// waits read the clock on every attempt does not hang), the cause is not known.  Until it is, every training entry
+// point of a pair plan holds this mutex while it enqueues, makes its stream wait for the last training launch of every
+// other pair plan, and records its own event: full-size fits of different plans are serialised on the device (one of
+// them fills the GPU anyway), NPP_Net_light plans use the single-CTA kernel and keep running side by side.
+// NPP_PAIR_OVERLAP=1 switches the serialisation off (the stress script uses it to reproduce the dead-lock).
+static std::mutex g_pair_mu;
+static std::vector<NppPlan*> g_pair_plans;   // live plans with wg_cluster == 2
+class PairStepScope {
+ public:
+  PairStepScope(NppPlan* p, cudaStream_t st) : p_(p), st_(st) {
+    static const bool overlap_ok = getenv("NPP_PAIR_OVERLAP") != nullptr && atoi(getenv("NPP_PAIR_OVERLAP")) != 0;
+    on_ = p->wg_cluster == 2 && !p->capturing && p->step_evt != nullptr && !overlap_ok;
+    if (on_) g_pair_mu.lock();
+  }
+  ~PairStepScope() {
+    if (on_) g_pair_mu.unlock();
+  }
+  int begin() {   // this plan's stream waits for the training launches other pair plans have in flight
+    if (!on_) return 0;
+    for (NppPlan* q : g_pair_plans) {
+      if (q == p_ || !q->step_pending) continue;
+      if (cudaEventQuery(q->step_evt) == cudaSuccess) {
+        q->step_pending = false;
+      } else {
+        cudaGetLastError();   // cudaErrorNotReady is not sticky, but keep the error state clean
+        CK(cudaStreamWaitEvent(st_, q->step_evt, 0));
+      }
+    }
+    return 0;
+  }
+  int end() {
+    if (!on_) return 0;
+    CK(cudaEventRecord(p_->step_evt, st_));
+    p_->step_pending = true;
+    return 0;
+  }
+ private:
+  NppPlan* p_;
+  cudaStream_t st_;
+  bool on_ = false;
+};
+
 // The fused head is a cooperative launch with a grid barrier.  Two such grids in flight at the same time (two plans
 // stepping on two streams) can each hold part of the SMs and wait for the rest -- observed as a hang with nine
 // concurrent fits.  One cooperative head may be in flight per process: a plan that finds another plan's head still
@@ -1198,6 +1248,7 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   if (cfg->model == NPP_MODEL_LIGHT) p->wg_cluster = 1;
   if (const char* e = getenv("NPP_WG_CLUSTER")) p->wg_cluster = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("NPP_PDL")) p->pdl = atoi(e) != 0;
+  if (const char* e = getenv("NPP_PDL_EDGES")) p->pdl_edges = atoi(e);
   if (const char* e = getenv("NPP_SPLIT_STEP")) p->fused_step = atoi(e) == 0;
   memset(&p->enc, 0, sizeof(p->enc));
   p->enc.topk = cfg->topk;
@@ -1222,12 +1273,33 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
     npp_plan_destroy(p);
     return r;
   }
+  if (p->wg_cluster == 2) {   // see PairStepScope
+    if (cudaEventCreateWithFlags(&p->step_evt, cudaEventDisableTiming) != cudaSuccess) {
+      npp_plan_destroy(p);
+      return fail("cudaEventCreate failed");
+    }
+    std::lock_guard<std::mutex> g(g_pair_mu);
+    g_pair_plans.push_back(p);
+  }
   *out = p;
   return 0;
 }
 
 int npp_plan_destroy(NppPlan* p) {
   if (!p) return 0;
+  {
+    std::lock_guard<std::mutex> g(g_pair_mu);
+    for (size_t i = 0; i < g_pair_plans.size(); ++i)
+      if (g_pair_plans[i] == p) {
+        g_pair_plans.erase(g_pair_plans.begin() + i);
+        break;
+      }
+    if (p->step_evt) {
+      cudaEventSynchronize(p->step_evt);   // another plan's stream may still be waiting for it
+      cudaEventDestroy(p->step_evt);
+      p->step_evt = nullptr;
+    }
+  }
   {
     std::lock_guard<std::mutex> g(g_coop_mu);
     if (g_coop_plan == p) {
@@ -1387,11 +1459,14 @@ int npp_backward(NppPlan* p, int64_t n, const float* g, void* stream) {
   if (!p || !g) return fail("npp_backward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
+  PairStepScope scope(p, st);
+  CKI(scope.begin());
   CKI(zero_acc(p, st));
   npp_amax_kernel<<<64, 256, 0, st>>>(g, (int)(n * 3), reinterpret_cast<unsigned int*>(p->acc + p->amax_off));
   CK(cudaGetLastError());
   ++p->launches;
-  return run_backward(p, n, g, st);
+  CKI(run_backward(p, n, g, st));
+  return scope.end();
 }
 
 int npp_mse_fwd_bwd(NppPlan* p, const float* logits, const float* target, const float* mask, int64_t n, int64_t n_norm,
@@ -1611,7 +1686,7 @@ static int launch_step_chain(NppPlan* p, const float* coords, const float* targe
   ProfScope ps(p, st, PROF_GEMM_FWD, 1);
   const std::vector<KmajorParams>& ops = alt ? p->step_params_alt : p->step_params;
   CKI(launch_chain(alt ? p->d_step_ops_alt : p->d_step_ops, ops.data(), (int)ops.size(), (int)n, p->num_sms, st,
-                   p->fwd_subs + p->dgrad_subs, p->cluster, nullptr, 0, nullptr, p->cfg.activation, &hd, p->pdl));
+                   p->fwd_subs + p->dgrad_subs, p->cluster, nullptr, 0, nullptr, p->cfg.activation, &hd, p->pdl && (p->pdl_edges & 1)));
   ++p->launches;
   return 0;
 }
@@ -1624,7 +1699,7 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
   const bool alt = p->enc_set != 0;
   {
     ProfScope ps(p, st, PROF_GEMM_WGRAD, 1);
-    CKI(launch_wgrad(alt ? p->wg_params_alt : p->wg_params, p->num_sms, st, p->wg_cluster, p->pdl));
+    CKI(launch_wgrad(alt ? p->wg_params_alt : p->wg_params, p->num_sms, st, p->wg_cluster, p->pdl && (p->pdl_edges & 2)));
     ++p->launches;
   }
   CKI(mark_busy(p, st));
@@ -1639,16 +1714,29 @@ static int run_fused_step(NppPlan* p, const float* coords, const float* target, 
     rs.ring = reinterpret_cast<unsigned int*>(p->acc + p->ring_off);
     rs.seq0 = (int)(p->step_seq % 3);
     rs.by_step = p->step_mode ? 1 : 0;
-    CKI(launch_update(p, ad, sl.prev, rs, p->pdl, st));
+    CKI(launch_update(p, ad, sl.prev, rs, p->pdl && (p->pdl_edges & 4), st));
   }
   if (!p->step_mode) ++p->step_seq;   // a re-launched step graph advances the ring on the device; its caller adds `iters`
   return 0;
 }
 
+static int train_step_impl(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n,
+                           int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
+                           void* stream);
+
 int npp_train_step(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n, int64_t n_norm,
                    float lr, float beta1, float beta2, float eps, int64_t step, float* loss, void* stream) {
   if (!p || !coords || !target || !loss) return fail("npp_train_step: null argument");
   if (n_norm <= 0) return fail("n_norm must be positive");
+  PairStepScope scope(p, (cudaStream_t)stream);
+  CKI(scope.begin());
+  CKI(train_step_impl(p, coords, target, mask, n, n_norm, lr, beta1, beta2, eps, step, loss, stream));
+  return scope.end();
+}
+
+static int train_step_impl(NppPlan* p, const float* coords, const float* target, const float* mask, int64_t n,
+                           int64_t n_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* loss,
+                           void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   p->launches = 0;
   if (p->fused_step && (!p->step_mode || p->cfg.model == NPP_MODEL_LIGHT)) {
@@ -1742,6 +1830,8 @@ int npp_step_forward_backward(NppPlan* p, const float* coords, const float* targ
   if (n_norm <= 0) return fail("n_norm must be positive");
   if (!p->grads) return fail("npp_plan_bind was called without a gradient arena");
   p->launches = 0;
+  PairStepScope scope(p, (cudaStream_t)stream);   // waits only; npp_step_finish records the event
+  CKI(scope.begin());
   const StepSlots sl = step_slots(p, n_norm);
   CKI(launch_step_chain(p, coords, target, mask, n, sl, (cudaStream_t)stream));
   // until npp_step_finish has run, the step accumulators hold this step's sums: a caller that abandons the step here
@@ -1836,7 +1926,8 @@ int npp_step_finish(NppPlan* p, int64_t n_norm, float lr, float beta1, float bet
   ++p->launches;
   ++p->step_seq;
   p->acc_clean = true;
-  return 0;
+  PairStepScope scope(p, st);
+  return scope.end();
 }
 
 int npp_fit_run(NppPlan* p, const float* coords_all, const float* target_all, const float* mask_all, int64_t n,
@@ -2003,11 +2094,15 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
   CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
   int launches = 0;
+  // plans with the CTA-pair weight-gradient kernel must not run side by side (see PairStepScope): their branches are
+  // chained one behind the other instead of forked
+  bool serial = false;
+  for (int i = 0; i < k; ++i) serial = serial || plans[i]->wg_cluster == 2;
   cudaError_t ce = cudaEventRecord(lead->pref_fork, origin);
   for (int i = 0; i < k && rc == 0 && ce == cudaSuccess; ++i) {
     NppPlan* p = plans[i];
     cudaStream_t bs = p->side_stream;
-    if (i > 0) ce = cudaStreamWaitEvent(bs, lead->pref_fork, 0);
+    if (i > 0) ce = cudaStreamWaitEvent(bs, serial ? plans[i - 1]->tables_evt : lead->pref_fork, 0);
     if (ce != cudaSuccess) break;
     p->capturing = true;
     p->step_mode = true;
@@ -2019,9 +2114,9 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
     }
     p->step_mode = false;
     p->capturing = false;
-    if (rc == 0 && i > 0) {       // join the branch
+    if (rc == 0 && (i > 0 || serial)) {       // join the branch (serial: also the hand-over to the next one)
       ce = cudaEventRecord(p->tables_evt, bs);
-      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, p->tables_evt, 0);
+      if (ce == cudaSuccess && i > 0) ce = cudaStreamWaitEvent(origin, p->tables_evt, 0);
     }
   }
   cudaGraph_t gr = nullptr;

@@ -73,25 +73,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 #ifdef NPP_HANG_DEBUG
-// Debug build only (-DNPP_HANG_DEBUG): a wait that lasts longer than ~2 s reports where it is stuck (source line of the
-// wait, block, thread, parity) into a mapped host buffer and traps, so that a dead-locked kernel becomes a launch
-// failure with a location instead of a hang.
+// Debug build only (-DNPP_HANG_DEBUG): a wait that lasts longer than ~1 s records where it is stuck (source line of the
+// wait, block, thread, parity) in a mapped host buffer, once, and keeps waiting; the host dumps the buffer when its
+// watchdog fires (tests/diag_concurrent_big.py).  try_wait suspends for a hardware time limit before it fails, so the
+// clock is looked at on every failed attempt.
 __device__ unsigned long long* g_npp_hang = nullptr;
 __device__ __noinline__ void npp_report_hang(uint32_t line, uint32_t info) {
   if (g_npp_hang != nullptr) {
     const unsigned long long v = (1ull << 63) | ((unsigned long long)(line & 0x7FFF) << 48) |
                                  ((unsigned long long)(blockIdx.x & 0xFFFF) << 32) |
                                  ((unsigned long long)(threadIdx.x & 0xFFFF) << 16) | (info & 0xFFFF);
-    g_npp_hang[(blockIdx.x * 10 + (threadIdx.x >> 5)) & 1023] = v;
+    g_npp_hang[((blockIdx.x * 12 + (threadIdx.x >> 5)) * 7 + line) & 1023] = v;
     __threadfence_system();
   }
-  __trap();
 }
 __device__ __forceinline__ void npp_spin_check(uint32_t& n, long long& t0, uint32_t line, uint32_t info) {
-  if ((++n & 0x3FFF) == 0) {
-    const long long t = clock64();
-    if (t0 == 0) t0 = t;
-    else if (t - t0 > 4000000000LL) npp_report_hang(line, info);
+  ++n;
+  const long long t = clock64();
+  if (t0 == 0) t0 = t;
+  else if (t - t0 > 2000000000LL) {
+    npp_report_hang(line, info);
+    t0 = t + (1LL << 60);   // reported once
   }
 }
 __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t line) {

@@ -19,8 +19,9 @@ def native():
 
 
 def pytest_collection_modifyitems(config, items):
-    """Every GPU test gets a wall-clock limit (pytest-timeout): a dead-locked kernel must fail the run, not stall it."""
+    """Every GPU test gets a wall-clock limit (pytest-timeout): a dead-locked kernel must fail the run, not stall it.
+    method="thread": the main thread would be blocked inside a CUDA call, where a signal handler never gets to run."""
     import pytest
     for item in items:
         if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
-            item.add_marker(pytest.mark.timeout(600))
+            item.add_marker(pytest.mark.timeout(600, method="thread"))

@@ -358,6 +358,44 @@ def test_two_plans_stepping_concurrently():
         assert abs(last - alone[k][1]) < 0.15 * alone[k][1], (k, last, alone[k][1])
 
 
+@pytest.mark.timeout(180, method="thread")
+def test_three_full_size_fits_from_three_threads_finish():
+    """Three 8192-row NPP_Net_top1 fits enqueued concurrently from three host threads on three streams.  With their
+    kernels overlapping on the device this dead-locked in 6 of 7 runs (DESIGN.md section 6, tests/diag_concurrent_big.py);
+    the library now serialises training launches of plans that use the CTA-pair weight-gradient kernel
+    (PairStepScope in npp_api.cu).  All fits must finish and reproduce the same fits run one after the other."""
+    import npp_b200
+    from npp_b200.plan import EncoderSpec, Plan
+    from npp_b200.search_fits import run_fits
+    K, n, iters = 3, 8192, 60
+    rng = np.random.default_rng(5)
+    freqs = (rng.standard_normal(10) * 10).astype(np.float32)
+    g = torch.Generator().manual_seed(5)
+    coords = torch.stack([torch.randint(0, 512, (iters, n), generator=g),
+                          torch.randint(0, 512, (iters, n), generator=g)], -1).float().cuda()
+    target = torch.rand(iters, n, 3, generator=g).cuda()
+
+    def plans():
+        out = []
+        for k in range(K):
+            enc = EncoderSpec.from_proposals((512, 512), [[97.0, 187.0]], [[40.0 + 3 * k, 36.0 + 2 * k]], freqs)
+            p = Plan(enc, max_rows=n)
+            p.reset_parameters(seed=k)
+            out.append(p)
+        return out
+
+    alone = torch.stack([run_fits([p], coords, target, grouped=False)[0] for p in plans()])
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(K)]
+    for rep in range(3):
+        together = run_fits(plans(), coords, target, streams=streams, grouped=False)
+        torch.cuda.synchronize()
+        assert torch.isfinite(together).all()
+        # same kernels, same order inside a fit: only atomic summation order differs
+        assert (together[:, :5] - alone[:, :5]).abs().max().item() < 2e-3 * alone[:, :5].max().item()
+        assert (together[:, -1] - alone[:, -1]).abs().max().item() < 0.15 * alone[:, -1].max().item()
+
+
 def test_render_into_image():
     """npp_render_into: chunked forward + sigmoid / tanh scattered straight into an [H, W, 3] image
     (NPP_completion/train.py:277-309), against plan.forward + torch ops; ragged last chunk."""
