@@ -149,6 +149,7 @@ struct ChainParams {
   int relu;             // host side only: selects the npp_gemm_kmajor<CLUSTER, true> instantiation
   HeadArgs head;        // used by the EPI_SNAKE_HEAD op, if the chain has one
   int pdl;              // launched with programmatic stream serialization: wait for the previous kernel after the prologue
+  unsigned long long* dbg_state;   // -DNPP_HANG_DEBUG builds: this plan's wait-state buffer (npp_state_record), else nullptr
 };
 
 struct WgUnit {
@@ -176,6 +177,7 @@ struct alignas(64) WgradParams {
   unsigned long long desc_hi;  // 0 = default MN-major SW128 (LBO 8192, SBO 1024)
   int k_adv;                   // 0 = default 2048
   float* bias_acc;             // bias-gradient accumulators (scaled like the deltas), nullptr: nobody wants them
+  unsigned long long* dbg_state;   // -DNPP_HANG_DEBUG builds: this plan's wait-state buffer, else nullptr
 };
 
 template <int NSTAGES>
@@ -307,15 +309,14 @@ __device__ __forceinline__ void publish_progress(uint32_t* slot, uint32_t value)
 __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t need) {
   uint32_t v;
 #ifdef NPP_HANG_DEBUG
-  uint32_t n = 0;
-  long long t0 = 0;
+  npp_state_record(9000, smem_u32(slot), need, 0);
 #endif
   do {
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(slot)) : "memory");
-#ifdef NPP_HANG_DEBUG
-    if (static_cast<int32_t>(v - need) < 0) npp_spin_check(n, t0, 9000 + (__LINE__ & 0xFF), need);
-#endif
   } while (static_cast<int32_t>(v - need) < 0);
+#ifdef NPP_HANG_DEBUG
+  npp_state_record(9000, smem_u32(slot), need, 1);
+#endif
   return v;
 }
 
@@ -808,6 +809,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 #ifdef NPP_PDL_WAIT_FIRST
   grid_dependency_wait();   // experiment: an early-launched CTA holds no TMEM / barrier while it waits
 #endif
+#ifdef NPP_HANG_DEBUG
+  if (threadIdx.x == 0) *npp_state_slot() = cp.dbg_state;   // visible to all warps after the prologue's barrier
+#endif
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, EPI_WARPS>(s, warp);
   // Programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) may overlap the tail of the
   // previous kernel in the stream; nothing below may (a no-op for an ordinary launch).
@@ -1128,6 +1132,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) npp_gemm_kmajor(const __grid_
 #endif
 constexpr int WG_PAIR_STAGES = NPP_WG_PAIR_STAGES;
 constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES / 2) + 512 + 1024;
+// what the pair kernel is LAUNCHED with: the whole 227 KB, so that a CTA of a pair has its SM to itself (see launch_wgrad)
+constexpr int WGRAD_PAIR_LAUNCH_SMEM_BYTES = 232448;
+static_assert(WGRAD_PAIR_SMEM_BYTES <= WGRAD_PAIR_LAUNCH_SMEM_BYTES, "wgrad ring exceeds 227 KB of shared memory");
 
 template <int CLUSTER>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
@@ -1147,6 +1154,9 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
   uint64_t* const alocal = s.afull;
 #ifdef NPP_PDL_WAIT_FIRST
   grid_dependency_wait();
+#endif
+#ifdef NPP_HANG_DEBUG
+  if (threadIdx.x == 0) *npp_state_slot() = p.dbg_state;
 #endif
   const uint32_t tmem_base = gemm_prologue_t<NST, CLUSTER, 4, CLUSTER, 1 + 4, 1>(s, warp);
   grid_dependency_wait();   // programmatic dependent launch: the prologue above overlaps the previous kernel's tail

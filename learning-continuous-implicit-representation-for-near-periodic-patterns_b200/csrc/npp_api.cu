@@ -823,13 +823,16 @@ static int set_smem_attrs() {
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_kmajor<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(npp_gemm_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(npp_gemm_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_PAIR_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(npp_gemm_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_PAIR_LAUNCH_SMEM_BYTES));
   g_smem_attr_done = 1;
   return 0;
 }
 
 // Runs ops[0..n_ops) (device array) as one persistent chain: CTA b owns row stripes b, b+grid, ...
 // cluster == 2: CTA pairs (thread-block clusters of 2) run cta_group::2 UMMAs, each CTA holding half of every weight tile.
+// -DNPP_HANG_DEBUG builds: wait-state buffer of the plan whose entry point is running on this host thread (else nullptr)
+static thread_local unsigned long long* tl_dbg_state = nullptr;
+
 static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, int n_ops, int M, int num_sms,
                         cudaStream_t st, int subs_per_stripe, int cluster = 1, float* zero_a = nullptr, int zero_n = 0,
                         float* zero_b = nullptr, int relu = 0, const HeadArgs* head = nullptr, int pdl = 0) {
@@ -859,6 +862,7 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   cp.relu = relu;
   if (head != nullptr) cp.head = *head;
   cp.pdl = pdl;
+  cp.dbg_state = tl_dbg_state;
   cp.n_ops = n_ops;
   cp.M = M;
   cp.tiles_m = (M + BM - 1) / BM;
@@ -926,8 +930,10 @@ static int launch_chain(const KmajorParams* d_ops, const KmajorParams* h_ops, in
   return 0;
 }
 
-static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int cluster, int pdl = 0) {
+static int launch_wgrad(const WgradParams& w_in, int num_sms, cudaStream_t st, int cluster, int pdl = 0) {
   CKI(set_smem_attrs());
+  WgradParams w = w_in;
+  w.dbg_state = tl_dbg_state;
   if (cluster == 1) {
     const int grid = w.n_units < num_sms ? w.n_units : num_sms;
     npp_gemm_wgrad<1><<<grid, WGRAD_THREADS, WGRAD_SMEM_BYTES, st>>>(w);
@@ -939,7 +945,15 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(WGRAD_THREADS);
-  cfg.dynamicSmemBytes = WGRAD_PAIR_SMEM_BYTES;
+  // The pair kernel asks for ALL the shared memory of an SM although its ring needs 161.5 KB: a CTA of a pair must not
+  // share its SM with blocks of other kernels.  With the 64 KB it used to leave free, update / encode blocks of OTHER
+  // plans could sit on one SM of the pair when it was launched, and fits of several plans running side by side
+  // dead-locked on the device (3 x 8192-row fits: 10 of 12 runs; with the SM to itself 0 of 14, 8 x 2048 rows 0 of 3, nine
+  // NPP_Net_light fits 0 of 4; profiles/r02/concurrent_plans.txt).  The single-CTA instantiation shares its SM with such
+  // blocks without harm (0 of 32), and the chain kernel fills the SM anyway.  NPP_WG_SMEM_SHARE=1 restores the old
+  // request (to reproduce the dead-lock).
+  static const bool smem_share = getenv("NPP_WG_SMEM_SHARE") != nullptr && atoi(getenv("NPP_WG_SMEM_SHARE")) != 0;
+  cfg.dynamicSmemBytes = smem_share ? WGRAD_PAIR_SMEM_BYTES : WGRAD_PAIR_LAUNCH_SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -954,23 +968,23 @@ static int launch_wgrad(const WgradParams& w, int num_sms, cudaStream_t st, int 
   return 0;
 }
 
-// Training launches of two plans that use the CTA-pair weight-gradient kernel never overlap on the GPU.
-// Measured on B200 (tests/diag_concurrent_big.py, profiles/r02/concurrent_plans.txt): three 8192-row NPP_Net fits
-// stepping on three streams from three host threads dead-locked on the device in 6 of 7 runs (eight 2048-row fits: 1 of
-// 6; nine NPP_Net_light fits: 7 of 38), never with the single-CTA instantiation of the weight-gradient kernel (0 of 32)
-// and never with one plan at a time.  No wait of either kernel could be caught spinning (a -DNPP_HANG_DEBUG build whose
-// waits read the clock on every attempt does not hang), the cause is not known.  Until it is, every training entry
-// point of a pair plan holds this mutex while it enqueues, makes its stream wait for the last training launch of every
-// other pair plan, and records its own event: full-size fits of different plans are serialised on the device (one of
-// them fills the GPU anyway), NPP_Net_light plans use the single-CTA kernel and keep running side by side.
-// NPP_PAIR_OVERLAP=1 switches the serialisation off (the stress script uses it to reproduce the dead-lock).
+// Optional serialisation of training launches of plans that use the CTA-pair weight-gradient kernel
+// (NPP_PAIR_SERIALISE=1; off by default).  It was the first containment of the dead-lock described in launch_wgrad
+// (fits of several full-size plans overlapping on the device), before the cause was narrowed down to other blocks
+// sharing an SM with a pair CTA; it is kept as a switch because it needs nothing from the kernels: every training
+// entry point of a pair plan holds this mutex while it enqueues, makes its stream wait for the last training launch of
+// every other pair plan, and records its own event, so steps of different plans never overlap (3 x 8192 rows: 50 ms
+// per search instead of 33 ms; 8 x 2048 rows: 277 ms instead of 89 ms).
+static bool pair_serialise() {
+  static const bool on = getenv("NPP_PAIR_SERIALISE") != nullptr && atoi(getenv("NPP_PAIR_SERIALISE")) != 0;
+  return on;
+}
 static std::mutex g_pair_mu;
 static std::vector<NppPlan*> g_pair_plans;   // live plans with wg_cluster == 2
 class PairStepScope {
  public:
   PairStepScope(NppPlan* p, cudaStream_t st) : p_(p), st_(st) {
-    static const bool overlap_ok = getenv("NPP_PAIR_OVERLAP") != nullptr && atoi(getenv("NPP_PAIR_OVERLAP")) != 0;
-    on_ = p->wg_cluster == 2 && !p->capturing && p->step_evt != nullptr && !overlap_ok;
+    on_ = pair_serialise() && p->wg_cluster == 2 && !p->capturing && p->step_evt != nullptr;
     if (on_) g_pair_mu.lock();
   }
   ~PairStepScope() {
@@ -1241,10 +1255,9 @@ int npp_plan_create(const NppConfig* cfg, NppPlan** out) {
   p->cfg = *cfg;
   p->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("NPP_CLUSTER")) p->cluster = atoi(e) == 1 ? 1 : 2;
-  // Search-stage fits run many plans side by side on one GPU.  With the CTA-pair weight-gradient kernel that occasionally
-  // dead-locked (one fit's stream stuck, ~1 run in 5 with nine concurrent fits, r01 library included; never seen with the
-  // single-CTA kernel in 16 runs, never with one plan at a time): NPP_Net_light takes the single-CTA kernel, whose L2
-  // traffic does not matter at 2048 rows.
+  // Search-stage fits run many plans side by side on one GPU, and a pair CTA keeps its SM to itself (see launch_wgrad):
+  // NPP_Net_light takes the single-CTA weight-gradient kernel, which shares SMs with the other candidates' small kernels
+  // and whose L2 traffic does not matter at 2048 rows (same time per search).
   if (cfg->model == NPP_MODEL_LIGHT) p->wg_cluster = 1;
   if (const char* e = getenv("NPP_WG_CLUSTER")) p->wg_cluster = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("NPP_PDL")) p->pdl = atoi(e) != 0;
@@ -2094,10 +2107,9 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
   CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
   int launches = 0;
-  // plans with the CTA-pair weight-gradient kernel must not run side by side (see PairStepScope): their branches are
-  // chained one behind the other instead of forked
+  // NPP_PAIR_SERIALISE=1 (see PairStepScope): branches of pair plans are chained one behind the other instead of forked
   bool serial = false;
-  for (int i = 0; i < k; ++i) serial = serial || plans[i]->wg_cluster == 2;
+  for (int i = 0; i < k; ++i) serial = serial || (pair_serialise() && plans[i]->wg_cluster == 2);
   cudaError_t ce = cudaEventRecord(lead->pref_fork, origin);
   for (int i = 0; i < k && rc == 0 && ce == cudaSuccess; ++i) {
     NppPlan* p = plans[i];
@@ -2167,17 +2179,25 @@ int npp_debug_pending_class(NppPlan* p, int* ordinal, int* total) {
 }
 
 #ifdef NPP_HANG_DEBUG
-// Debug build only: mapped host buffer (1024 x u64) that stuck waits report into (see ptx_sm100.cuh).
-int npp_debug_hang_buffer(unsigned long long** host_ptr) {
-  static unsigned long long* h = nullptr;
-  if (h == nullptr) {
-    CK(cudaHostAlloc(&h, 1024 * sizeof(unsigned long long), cudaHostAllocMapped));
-    memset(h, 0, 1024 * sizeof(unsigned long long));
-    unsigned long long* d = nullptr;
-    CK(cudaHostGetDevicePointer(&d, h, 0));
-    CK(cudaMemcpyToSymbol(g_npp_hang, &d, sizeof(d)));
+// Debug build only: device buffer of 8 plans x 4096 wait-state words (see npp_state_record in ptx_sm100.cuh); plan
+// `ordinal` (0..7) of the calling host thread is selected with npp_debug_state_select before its training calls, and
+// npp_debug_state_dump copies the whole buffer out on a private stream (it works while kernels hang).
+static unsigned long long* g_state_dev = nullptr;
+static cudaStream_t g_state_stream = nullptr;
+int npp_debug_state_select(int ordinal) {
+  if (g_state_dev == nullptr) {
+    CK(cudaMalloc(&g_state_dev, 8 * 4096 * sizeof(unsigned long long)));
+    CK(cudaMemset(g_state_dev, 0, 8 * 4096 * sizeof(unsigned long long)));
+    CK(cudaStreamCreateWithFlags(&g_state_stream, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
   }
-  if (host_ptr) *host_ptr = h;
+  tl_dbg_state = ordinal >= 0 ? g_state_dev + (size_t)(ordinal & 7) * 4096 : nullptr;
+  return 0;
+}
+int npp_debug_state_dump(unsigned long long* host_out) {
+  if (g_state_dev == nullptr || host_out == nullptr) return fail("no state buffer");
+  CK(cudaMemcpyAsync(host_out, g_state_dev, 8 * 4096 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_state_stream));
+  CK(cudaStreamSynchronize(g_state_stream));
   return 0;
 }
 #endif

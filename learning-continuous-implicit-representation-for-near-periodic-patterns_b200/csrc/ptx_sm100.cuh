@@ -73,33 +73,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 #ifdef NPP_HANG_DEBUG
-// Debug build only (-DNPP_HANG_DEBUG): a wait that lasts longer than ~1 s records where it is stuck (source line of the
-// wait, block, thread, parity) in a mapped host buffer, once, and keeps waiting; the host dumps the buffer when its
-// watchdog fires (tests/diag_concurrent_big.py).  try_wait suspends for a hardware time limit before it fails, so the
-// clock is looked at on every failed attempt.
-__device__ unsigned long long* g_npp_hang = nullptr;
-__device__ __noinline__ void npp_report_hang(uint32_t line, uint32_t info) {
-  if (g_npp_hang != nullptr) {
-    const unsigned long long v = (1ull << 63) | ((unsigned long long)(line & 0x7FFF) << 48) |
-                                 ((unsigned long long)(blockIdx.x & 0xFFFF) << 32) |
-                                 ((unsigned long long)(threadIdx.x & 0xFFFF) << 16) | (info & 0xFFFF);
-    g_npp_hang[((blockIdx.x * 12 + (threadIdx.x >> 5)) * 7 + line) & 1023] = v;
-    __threadfence_system();
-  }
+// Debug build only (-DNPP_HANG_DEBUG): every mbarrier wait writes (source line, barrier, parity, clock) into a per-plan
+// device buffer before it starts spinning and marks the entry "passed" afterwards; the spin loop itself is the
+// production one (instrumenting the loop hid the dead-lock this was written for).  The kernels publish the buffer
+// pointer in the last 8 bytes of their dynamic shared memory (never reached by the carve-up); the host reads the buffer
+// on a private stream while the kernels hang (npp_debug_state_dump).  One slot per (block, warp), written by lane 0.
+__device__ __forceinline__ unsigned long long** npp_state_slot() {
+  extern __shared__ uint8_t npp_dyn_smem[];
+  uint32_t sz;
+  asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(sz));
+  return reinterpret_cast<unsigned long long**>(npp_dyn_smem + sz - 8);
 }
-__device__ __forceinline__ void npp_spin_check(uint32_t& n, long long& t0, uint32_t line, uint32_t info) {
-  ++n;
-  const long long t = clock64();
-  if (t0 == 0) t0 = t;
-  else if (t - t0 > 2000000000LL) {
-    npp_report_hang(line, info);
-    t0 = t + (1LL << 60);   // reported once
-  }
+__device__ __forceinline__ void npp_state_record(uint32_t line, uint32_t bar, uint32_t parity, uint32_t passed) {
+  if ((threadIdx.x & 31) != 0) return;
+  unsigned long long* b = *npp_state_slot();
+  if (b == nullptr) return;
+  b[(blockIdx.x & 255) * 16 + (threadIdx.x >> 5)] =
+      ((unsigned long long)(passed & 1) << 63) | ((unsigned long long)(line & 0x7FFF) << 48) |
+      ((unsigned long long)(bar & 0xFFFF) << 32) | ((unsigned long long)(parity & 1) << 31) |
+      ((unsigned long long)(clock64() >> 10) & 0x7FFFFFFFull);
 }
 __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t line) {
-  uint32_t n = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) npp_spin_check(n, t0, line, parity);
+  npp_state_record(line, smem_u32(bar), parity, 0);
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  npp_state_record(line, smem_u32(bar), parity, 1);
 }
 #define mbar_wait(bar, parity) mbar_wait_impl(bar, parity, __LINE__)
 #else
@@ -110,18 +108,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 __device__ __forceinline__ void mbar_wait_cluster_impl(uint64_t* bar, uint32_t parity, uint32_t line) {
 #ifdef NPP_HANG_DEBUG
-  uint32_t n = 0, ok;
-  long long t0 = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok == 0) npp_spin_check(n, t0, line, parity);
-  } while (ok == 0);
+  npp_state_record(line, smem_u32(bar), parity, 0);
+  mbar_wait_cluster_plain(bar, parity);
+  npp_state_record(line, smem_u32(bar), parity, 1);
 #else
   (void)line;
   mbar_wait_cluster_plain(bar, parity);
@@ -157,12 +146,17 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
 // cta_group::2 load: data lands in the executing CTA's smem, the transaction bytes are credited to the mbarrier at
 // the same offset in CTA 0 of the pair (the leader that issues the 2-SM UMMAs).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+#ifdef NPP_PAIR_MBAR_MAPA
+  uint32_t lead_bar;   // experiment: the leader's barrier through mapa instead of clearing the rank bit of the own address
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(lead_bar) : "r"(smem_u32(bar)));
+#else
+  const uint32_t lead_bar = smem_u32(bar) & 0xFEFFFFFFu;
+#endif
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];"
       :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
-        "r"(c1)
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(lead_bar), "r"(c0), "r"(c1)
       : "memory");
 }
 // arrive on the mbarrier at the same smem offset in CTA `target_rank` of the cluster

@@ -360,10 +360,10 @@ def test_two_plans_stepping_concurrently():
 
 @pytest.mark.timeout(180, method="thread")
 def test_three_full_size_fits_from_three_threads_finish():
-    """Three 8192-row NPP_Net_top1 fits enqueued concurrently from three host threads on three streams.  With their
-    kernels overlapping on the device this dead-locked in 6 of 7 runs (DESIGN.md section 6, tests/diag_concurrent_big.py);
-    the library now serialises training launches of plans that use the CTA-pair weight-gradient kernel
-    (PairStepScope in npp_api.cu).  All fits must finish and reproduce the same fits run one after the other."""
+    """Three 8192-row NPP_Net_top1 fits enqueued concurrently from three host threads on three streams, their kernels
+    overlapping on the device.  This dead-locked in 10 of 12 runs while the CTA-pair weight-gradient kernel left part of
+    its SMs' shared memory to other blocks (tests/diag_concurrent_big.py); it now asks for the
+    whole SM (launch_wgrad in npp_api.cu).  All fits must finish and reproduce the same fits run one after the other."""
     import npp_b200
     from npp_b200.plan import EncoderSpec, Plan
     from npp_b200.search_fits import run_fits
