@@ -162,6 +162,8 @@ struct WgUnit {
   int ncols_left;      // valid columns from col0 to the padded layer width
   int bias_off;        // >= 0: this unit also sums its delta columns over its rows (bias gradient of out-features
                        //   [a_m0, a_m0 + 256)) into WgradParams::bias_acc + bias_off; -1: another unit of the layer does
+  int kb0 = 0, kb1 = 0;  // balanced schedule: explicit range of 64-row blocks [kb0, kb1), the partial sums go to slab
+                         //   `split`; kb1 == 0: the range of row split `split` (kb_per_split blocks); kb1 < 0: empty slot
 };
 
 constexpr int WG_MAX_MAPS = 28;
@@ -177,6 +179,7 @@ struct alignas(64) WgradParams {
   unsigned long long desc_hi;  // 0 = default MN-major SW128 (LBO 8192, SBO 1024)
   int k_adv;                   // 0 = default 2048
   float* bias_acc;             // bias-gradient accumulators (scaled like the deltas), nullptr: nobody wants them
+  int grid_pairs;              // > 0: launch exactly this many CTA pairs (CTAs): the unit table is laid out for that stride
   unsigned long long* dbg_state;   // -DNPP_HANG_DEBUG builds: this plan's wait-state buffer, else nullptr
 };
 
@@ -1136,6 +1139,19 @@ constexpr int WGRAD_PAIR_SMEM_BYTES = WG_PAIR_STAGES * (A_STAGE_BYTES + B_STAGE_
 constexpr int WGRAD_PAIR_LAUNCH_SMEM_BYTES = 232448;
 static_assert(WGRAD_PAIR_SMEM_BYTES <= WGRAD_PAIR_LAUNCH_SMEM_BYTES, "wgrad ring exceeds 227 KB of shared memory");
 
+// 64-row blocks [kb0, kb1) a unit contracts over; false: nothing to do (every warp role skips the unit alike)
+__device__ __forceinline__ bool wg_unit_range(const WgUnit& un, const WgradParams& p, int kb_total, int& kb0, int& kb1) {
+  if (un.kb1 != 0) {
+    kb0 = un.kb0;
+    kb1 = min(un.kb1, kb_total);
+    return kb0 < kb1;
+  }
+  if (un.split >= p.n_splits) return false;
+  kb0 = un.split * p.kb_per_split;
+  kb1 = min(kb0 + p.kb_per_split, kb_total);
+  return kb0 < kb1;
+}
+
 template <int CLUSTER>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_constant__ WgradParams p) {
   constexpr int NST = CLUSTER == 1 ? WG_STAGES : WG_PAIR_STAGES;
@@ -1170,9 +1186,8 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
     PipeStateT<NST> ps;
     for (int u = unit0; u < p.n_units; u += ustride) {
       const WgUnit un = p.units[u];
-      if (un.split >= p.n_splits) continue;
-      const int kb0 = un.split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+      int kb0, kb1;
+      if (!wg_unit_range(un, p, kb_total, kb0, kb1)) continue;
       const CUtensorMap* ma = &p.maps[un.a_map];
       const CUtensorMap* mb = &p.maps[un.b_map];
       const int am0 = un.a_m0 + (int)crank * BM;
@@ -1220,9 +1235,8 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
       uint32_t acc_phase = 0;
       for (int u = unit0; u < p.n_units; u += ustride) {
         const WgUnit un = p.units[u];
-        if (un.split >= p.n_splits) continue;
-        const int kb0 = un.split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+        int kb0, kb1;
+        if (!wg_unit_range(un, p, kb_total, kb0, kb1)) continue;
         mbar_wait(&s.tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -1261,9 +1275,8 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
       PipeStateT<NST> ps;
       for (int u = unit0; u < p.n_units; u += ustride) {
         const WgUnit un = p.units[u];
-        if (un.split >= p.n_splits) continue;
-        const int kb0 = un.split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+        int kb0, kb1;
+        if (!wg_unit_range(un, p, kb_total, kb0, kb1)) continue;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&alocal[ps.stage], ps.phase);
           if (lane == 0) mbar_arrive_remote_relaxed(&s.full[ps.stage], 0);
@@ -1290,12 +1303,11 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) npp_gemm_wgrad(const __grid_
     const uint32_t rd_off = (uint32_t)(cc >> 3) * 8192u + (uint32_t)rg * 128u + (uint32_t)(((cc & 7) ^ rg) << 4);
     for (int u = unit0; u < p.n_units; u += ustride) {
       const WgUnit un = p.units[u];
-      if (un.split >= p.n_splits) continue;
+      int kb0, kb1;
+      if (!wg_unit_range(un, p, kb_total, kb0, kb1)) continue;
       float* out = p.partial + (size_t)un.split * p.slab_stride + un.out_off +
                    (size_t)((int)crank * BM + lane_base + lane) * un.ld;
       {
-        const int kb0 = un.split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
         const bool want = un.bias_off >= 0 && p.bias_acc != nullptr;
         float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int kb = kb0; kb < kb1; ++kb) {

@@ -165,6 +165,8 @@ struct NppPlan {
   KmajorParams* d_step_ops = nullptr;      // fused train step: forward ops (last one with the head epilogue) + dgrad ops
   KmajorParams* d_step_ops_alt = nullptr;  // same, reading the second encoding set
   WgUnit* d_units = nullptr;
+  WgUnit* d_units_bal = nullptr;         // balanced schedule of the current row count (see prepare), 4 * tiles slots
+  bool wg_balanced = false;
   int n_units = 0;
   std::vector<WgUnit> tile_units;        // one entry per (layer, m-tile, n-tile) with split 0: template of every unit table
   std::vector<int> tile_begin;           // first entry of layer i inside tile_units (size layers + 1)
@@ -804,6 +806,63 @@ static int prepare(NppPlan* p, long long n) {
   if (want_splits > p->splits_max) want_splits = p->splits_max;
   w.kb_per_split = (kb_total + want_splits - 1) / want_splits;
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
+  w.grid_pairs = 0;
+  // Balanced schedule.  With one unit per tile and more CTA pairs than tiles but fewer than twice as many (NPP_Net K=3:
+  // 60 tiles, 74 pairs), the kernel takes the time of one whole tile while 19 % of the SMs idle.  Instead, every g
+  // consecutive tiles are contracted by g + 1 pairs, g = ceil(T / (P - T)): pair c of a group takes the first
+  // (g - c) / (g + 1) of tile c's rows (partial sums to slab 0), then the last c / (g + 1) of tile c - 1's (slab 1).
+  // Every tile is cut exactly once, so the update kernel sums two slabs (S = 2); all pairs walk their "own" tile from
+  // row 0 at the same time, which keeps the operand tiles the pairs of one layer share in L2 as before.
+  p->wg_balanced = false;
+  {
+    const int T = (int)p->tile_units.size(), P = p->num_sms / p->wg_cluster;
+    // Measured (B200, cfg2, steady state under the power cap, tests/diag_step_time.py): weight-gradient kernel 136 -> 130 us,
+    // update 36 -> 39 us (second slab), chain 320 -> 324 us, step 485.3 -> 485.9 us: the SMs it puts to work draw the power
+    // the other kernels then lack.  Off by default (NPP_WG_BALANCE=1 switches it on).
+    static const bool balance = getenv("NPP_WG_BALANCE") != nullptr && atoi(getenv("NPP_WG_BALANCE")) != 0;
+    if (balance && p->wg_cluster == 2 && p->splits_auto && w.n_splits == 1 && T < P && 2 * T > P && p->slabs_alloc >= 2) {
+      const int g = (T + (P - T) - 1) / (P - T);
+      if (kb_total >= 8 * (g + 1)) {
+        WgUnit empty{};
+        empty.kb0 = empty.kb1 = -1;
+        empty.bias_off = -1;
+        std::vector<WgUnit> head, tail;
+        for (int t0 = 0; t0 < T; t0 += g) {
+          const int r = std::min(g, T - t0);
+          const long long total = (long long)r * kb_total;
+          for (int c = 0; c <= r; ++c) {
+            const long long lo = c * total / (r + 1), hi = (c + 1) * total / (r + 1);
+            WgUnit h = empty, t = empty;
+            if (c < r) {
+              h = p->tile_units[t0 + c];
+              h.split = 0;
+              h.kb0 = 0;
+              h.kb1 = (int)(hi - (long long)c * kb_total);
+            }
+            if (c >= 1) {
+              t = p->tile_units[t0 + c - 1];
+              t.split = 1;
+              t.kb0 = (int)(lo - (long long)(c - 1) * kb_total);
+              t.kb1 = kb_total;
+            }
+            head.push_back(h);
+            tail.push_back(t);
+          }
+        }
+        const int chunks = (int)head.size();
+        if (chunks <= P) {
+          head.insert(head.end(), tail.begin(), tail.end());
+          if (p->d_units_bal == nullptr) CK(cudaMalloc(&p->d_units_bal, (size_t)4 * T * sizeof(WgUnit)));
+          CK(cudaMemcpy(p->d_units_bal, head.data(), head.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
+          w.units = p->d_units_bal;
+          w.n_units = (int)head.size();
+          w.grid_pairs = chunks;      // pair c: unit c (head), then unit c + chunks (tail)
+          w.n_splits = 2;             // slabs the update kernel sums
+          p->wg_balanced = true;
+        }
+      }
+    }
+  }
   w.partial = p->partial;
   w.slab_stride = p->slab_stride;
   w.bias_acc = getenv("NPP_WG_NOBIAS") ? nullptr : p->acc;   // (timing experiments only: the bias gradients are then missing)
@@ -941,6 +1000,7 @@ static int launch_wgrad(const WgradParams& w_in, int num_sms, cudaStream_t st, i
     return 0;
   }
   int grid = 2 * w.n_units < num_sms ? 2 * w.n_units : num_sms / 2 * 2;
+  if (w.grid_pairs > 0) grid = 2 * w.grid_pairs;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -1348,6 +1408,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_step_ops);
   cudaFree(p->d_step_ops_alt);
   cudaFree(p->d_units);
+  cudaFree(p->d_units_bal);
   for (auto& g : p->groups) cudaFree(g.d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1901,6 +1962,7 @@ int npp_step_wgrad(NppPlan* p, int32_t layer_begin, int32_t layer_end, int64_t n
   WgradParams w = p->enc_set ? p->wg_params_alt : p->wg_params;
   w.units = gt->d_units;
   w.n_units = gt->n_units;
+  w.grid_pairs = 0;
   w.kb_per_split = (kb_total + S - 1) / S;
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
   {
