@@ -316,6 +316,9 @@ __device__ __forceinline__ uint32_t wait_progress(const uint32_t* slot, uint32_t
 #endif
   do {
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(slot)) : "memory");
+#ifdef NPP_SPIN_SLEEP_NS
+    if (static_cast<int32_t>(v - need) < 0) __nanosleep(NPP_SPIN_SLEEP_NS);
+#endif
   } while (static_cast<int32_t>(v - need) < 0);
 #ifdef NPP_HANG_DEBUG
   npp_state_record(9000, smem_u32(slot), need, 1);

@@ -103,6 +103,9 @@ __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, u
 #else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+#ifdef NPP_SPIN_SLEEP_NS
+    __nanosleep(NPP_SPIN_SLEEP_NS);   // experiment: energy of the spinning warps under the power cap
+#endif
   }
 }
 #endif
