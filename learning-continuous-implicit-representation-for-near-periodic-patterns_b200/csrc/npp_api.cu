@@ -165,6 +165,8 @@ struct NppPlan {
   KmajorParams* d_step_ops = nullptr;      // fused train step: forward ops (last one with the head epilogue) + dgrad ops
   KmajorParams* d_step_ops_alt = nullptr;  // same, reading the second encoding set
   WgUnit* d_units = nullptr;
+  WgUnit* d_tile_units = nullptr;        // tile_units on the device: the unit table of a launch without row splits
+  int splits_override = 0;               // > 0: row splits of the next prepare() instead of splits_fill (npp_multi_fit_run)
   WgUnit* d_units_bal = nullptr;         // balanced schedule of the current row count (see prepare), 4 * tiles slots
   bool wg_balanced = false;
   int n_units = 0;
@@ -616,6 +618,8 @@ static int alloc_plan_memory(NppPlan* p) {
   p->n_units = (int)units.size();
   CK(cudaMalloc(&p->d_units, units.size() * sizeof(WgUnit)));
   CK(cudaMemcpy(p->d_units, units.data(), units.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p->d_tile_units, p->tile_units.size() * sizeof(WgUnit)));
+  CK(cudaMemcpy(p->d_tile_units, p->tile_units.data(), p->tile_units.size() * sizeof(WgUnit), cudaMemcpyHostToDevice));
   p->wg_src_bufs = src_bufs;
   return 0;
 }
@@ -801,12 +805,16 @@ static int prepare(NppPlan* p, long long n) {
   w.n_units = p->n_units;
   w.rows = (int)n;
   const int kb_total = (int)((n + BK - 1) / BK);
-  int want_splits = p->splits_fill;
+  int want_splits = p->splits_override > 0 ? p->splits_override : p->splits_fill;
   if (p->splits_auto) want_splits = std::max(want_splits, (int)((n + WG_ROWS_PER_SPLIT - 1) / WG_ROWS_PER_SPLIT));
   if (want_splits > p->splits_max) want_splits = p->splits_max;
   w.kb_per_split = (kb_total + want_splits - 1) / want_splits;
   w.n_splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
   w.grid_pairs = 0;
+  if (w.n_splits == 1 && p->splits_fill > 1) {   // fewer row splits than the unit table was laid out for: no idle CTAs
+    w.units = p->d_tile_units;
+    w.n_units = (int)p->tile_units.size();
+  }
   // Balanced schedule.  With one unit per tile and more CTA pairs than tiles but fewer than twice as many (NPP_Net K=3:
   // 60 tiles, 74 pairs), the kernel takes the time of one whole tile while 19 % of the SMs idle.  Instead, every g
   // consecutive tiles are contracted by g + 1 pairs, g = ceil(T / (P - T)): pair c of a group takes the first
@@ -1409,6 +1417,7 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_step_ops_alt);
   cudaFree(p->d_units);
   cudaFree(p->d_units_bal);
+  cudaFree(p->d_tile_units);
   for (auto& g : p->groups) cudaFree(g.d_units);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
@@ -1802,6 +1811,10 @@ int npp_train_step(NppPlan* p, const float* coords, const float* target, const f
                    float lr, float beta1, float beta2, float eps, int64_t step, float* loss, void* stream) {
   if (!p || !coords || !target || !loss) return fail("npp_train_step: null argument");
   if (n_norm <= 0) return fail("n_norm must be positive");
+  if (p->splits_override != 0 && !p->capturing) {   // left over from a grouped fit (npp_multi_fit_run)
+    p->splits_override = 0;
+    p->prepared_n = -1;
+  }
   PairStepScope scope(p, (cudaStream_t)stream);
   CKI(scope.begin());
   CKI(train_step_impl(p, coords, target, mask, n, n_norm, lr, beta1, beta2, eps, step, loss, stream));
@@ -2146,6 +2159,14 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
   CKI(set_smem_attrs());
   for (int i = 0; i < k; ++i) {
     NppPlan* p = plans[i];
+    // Row splits of the weight-gradient GEMM: a fit on its own is fastest with 4 (103 us per step against 109 with 1), but
+    // side by side the fits compete for SMs and every split is another CTA with its prologue: nine candidates x 300
+    // iterations take 46.1 / 44.1 / 41.8 / 39.9 ms with 4 / 3 / 2 / 1 splits (tools/bench_search_fits.py --mode grouped).
+    const int want_override = (k >= 3 && p->cfg.model == NPP_MODEL_LIGHT && p->splits_auto) ? 1 : 0;
+    if (p->splits_override != want_override) {
+      p->splits_override = want_override;
+      p->prepared_n = -1;
+    }
     CKI(prepare(p, n));           // synchronises and copies op tables: must happen outside the capture
     p->pref[0].valid = p->pref[1].valid = false;
     CK(cudaStreamSynchronize(p->side_stream));
