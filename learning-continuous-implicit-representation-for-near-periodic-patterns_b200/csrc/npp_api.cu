@@ -132,7 +132,12 @@ struct NppPlan {
     long long n = 0;
     bool valid = false;
     cudaEvent_t done = nullptr;
+    int tag = -1;                             // unrolled iteration it was encoded for (npp_multi_fit_run), else -1
   } pref[2];                                  // one per encoding set
+  int iter_tag = -1;                          // unrolled iteration being captured (matches PrefRec::tag), else -1
+  int enc_step_off = 0;                       // re-launched step graph: the encode kernel reads batch *d_step + enc_step_off
+  cudaStream_t enc_stream2 = nullptr;         // capture branch of the encodings pipelined inside npp_multi_fit_run
+  cudaEvent_t enc_fork = nullptr;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t pref_fork = nullptr;
   int head_width = 0;  // W/2
@@ -1115,7 +1120,7 @@ static int launch_encode(NppPlan* p, const float* coords, long long n, int set, 
     npp_encode_search_kernel<<<blocks, 256, 0, st>>>(coords, (int)n, p->enc, p->bufs[b1].ptr, p->Ep, p->bufs[bp].ptr,
                                                      p->Ap, zero_loss ? p->acc : nullptr,
                                                      zero_loss ? (int)p->acc_zero_floats : 0, zero_loss,
-                                                     p->step_mode ? p->d_step : nullptr);
+                                                     p->step_mode ? p->d_step : nullptr, p->enc_step_off);
     CK(cudaGetLastError());
     ++p->launches;
     return 0;
@@ -1142,7 +1147,7 @@ static int select_encoding(NppPlan* p, const float* coords, long long n, cudaStr
                            bool* prefetched) {
   int hit = -1;
   for (int i = 0; i < 2; ++i)
-    if (p->pref[i].valid && p->pref[i].coords == coords && p->pref[i].n == n) hit = i;
+    if (p->pref[i].valid && p->pref[i].coords == coords && p->pref[i].n == n && p->pref[i].tag == p->iter_tag) hit = i;
   if (hit >= 0) {
     // npp_encode_prefetch already wrote this batch's encoding into set `hit` (on the side stream, while earlier
     // work was running): wait for it, switch sets, and let the chain kernel clear the step accumulators
@@ -1409,6 +1414,8 @@ int npp_plan_destroy(NppPlan* p) {
   cudaFree(p->d_fwd_ops_alt);
   if (p->side_stream) cudaStreamDestroy(p->side_stream);
   if (p->pref_fork) cudaEventDestroy(p->pref_fork);
+  if (p->enc_fork) cudaEventDestroy(p->enc_fork);
+  if (p->enc_stream2) cudaStreamDestroy(p->enc_stream2);
   if (p->tables_evt) cudaEventDestroy(p->tables_evt);
   if (p->coop_evt) cudaEventDestroy(p->coop_evt);
   for (int i = 0; i < 2; ++i) if (p->pref[i].done) cudaEventDestroy(p->pref[i].done);
@@ -1492,6 +1499,37 @@ int npp_encode_prefetch(NppPlan* p, const float* coords, int64_t n, void* stream
   p->pref[set].coords = coords;
   p->pref[set].n = n;
   p->pref[set].valid = true;
+  p->pref[set].tag = -1;
+  return 0;
+}
+
+// Inside the capture of npp_multi_fit_run (branch stream bs, unrolled iteration p->iter_tag about to be captured): encodes
+// the batch of the NEXT iteration (*d_step + 1) into the encoding set this iteration does not use, on a second capture
+// stream forked from bs, so that it runs beside this iteration's chain kernel instead of in front of the next one.
+static int capture_prefetch_next(NppPlan* p, const float* coords, long long n, cudaStream_t bs, int* set_out) {
+  if (p->enc_stream2 == nullptr) {
+    CK(cudaStreamCreateWithFlags(&p->enc_stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->enc_fork, cudaEventDisableTiming));
+  }
+  int this_set = p->enc_set;   // the set the iteration about to be captured reads: its own prefetch, else an in-line encode
+  for (int i = 0; i < 2; ++i)
+    if (p->pref[i].valid && p->pref[i].tag == p->iter_tag) this_set = i;
+  const int set = 1 - this_set;
+  if (p->pref[set].valid) return fail("capture_prefetch_next: both encoding sets are taken");
+  CK(cudaEventRecord(p->enc_fork, bs));
+  CK(cudaStreamWaitEvent(p->enc_stream2, p->enc_fork, 0));
+  const int launches = p->launches;
+  p->enc_step_off = 1;
+  const int rc = launch_encode(p, coords, n, set, p->enc_stream2, nullptr);
+  p->enc_step_off = 0;
+  if (rc != 0) return rc;
+  p->launches = launches;   // counted by the iteration that consumes it
+  CK(cudaEventRecord(p->pref[set].done, p->enc_stream2));
+  p->pref[set].coords = coords;
+  p->pref[set].n = n;
+  p->pref[set].valid = true;
+  p->pref[set].tag = p->iter_tag + 1;
+  *set_out = set;
   return 0;
 }
 
@@ -2191,6 +2229,12 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
   int unroll = 5;
   if (const char* e = getenv("NPP_FIT_UNROLL")) unroll = std::max(1, atoi(e));
   while (unroll > 1 && iters % unroll != 0) --unroll;
+  // NPP_FIT_PIPELINE=1 (off by default): inside a launch the encoding of iteration u + 1 runs beside the chain kernel of
+  // iteration u instead of in front of its own.  Measured slower for nine candidates (42.6 against 38.6 ms per search:
+  // the extra fork / join per iteration costs more than the 8 us encode kernel it hides).
+  bool pipeline = false;
+  if (const char* e = getenv("NPP_FIT_PIPELINE")) pipeline = unroll > 1 && atoi(e) != 0;
+  for (int i = 0; i < k; ++i) pipeline = pipeline && plans[i]->cfg.model == NPP_MODEL_LIGHT;
   // capture: the lead plan's side stream is the origin, every other plan's side stream a branch forked from it
   cudaStream_t origin = lead->side_stream;
   CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
@@ -2208,13 +2252,22 @@ int npp_multi_fit_run(NppPlan* const* plans, int32_t k, const float* const* coor
     p->capturing = true;
     p->step_mode = true;
     for (int u = 0; u < unroll && rc == 0; ++u) {
-      rc = npp_train_step(p, coords_all[i], target_all[i], mask_all ? mask_all[i] : nullptr, n, n, lrate, beta1, beta2, eps,
-                          first_steps[i], losses[i], bs);
+      p->iter_tag = u;
+      int next_set = -1;
+      if (pipeline && u + 1 < unroll) rc = capture_prefetch_next(p, coords_all[i], n, bs, &next_set);
+      if (rc == 0)
+        rc = npp_train_step(p, coords_all[i], target_all[i], mask_all ? mask_all[i] : nullptr, n, n, lrate, beta1, beta2,
+                            eps, first_steps[i], losses[i], bs);
+      // the next iteration's encoding has read the step counter before it advances
+      if (rc == 0 && next_set >= 0 && cudaStreamWaitEvent(bs, p->pref[next_set].done, 0) != cudaSuccess)
+        rc = fail("npp_multi_fit_run: cudaStreamWaitEvent failed");
       if (rc == 0) {
         npp_step_advance_kernel<<<1, 1, 0, bs>>>(p->d_step);
         launches += p->launches + 1;
       }
     }
+    p->iter_tag = -1;
+    p->pref[0].valid = p->pref[1].valid = false;
     p->step_mode = false;
     p->capturing = false;
     if (rc == 0 && (i > 0 || serial)) {       // join the branch (serial: also the hand-over to the next one)

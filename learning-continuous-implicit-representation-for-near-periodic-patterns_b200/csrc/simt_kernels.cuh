@@ -285,10 +285,11 @@ __global__ void __launch_bounds__(256) npp_encode_search_kernel(const float* __r
                                                                 __half* __restrict__ pos, int ldp,
                                                                 float* __restrict__ zero_a, int zero_a_n,
                                                                 float* __restrict__ zero_b,
-                                                                const int* __restrict__ step) {
-  // step != nullptr (npp_fit_run's re-launched step graph): batch *step of a [iters, n, 2] array, loss slot *step
+                                                                const int* __restrict__ step, int step_off) {
+  // step != nullptr (npp_fit_run's re-launched step graph): batch *step (+ step_off: encoded one iteration ahead) of a
+  // [iters, n, 2] array, loss slot *step
   if (step != nullptr) {
-    const int sidx = *step;
+    const int sidx = *step + step_off;
     coords += (size_t)sidx * n * 2;
     if (zero_b != nullptr) zero_b += sidx;
   }
